@@ -1,0 +1,188 @@
+/*
+ * scae_b200.h -- C ABI of libscae_b200.so: the two SCAE likelihood hot paths as sm_100a CUDA kernels.
+ *
+ * The reference (bdsaglam/torch-scae, pure Python) has no FFI; its boundary for these paths is the Python module
+ * API.  Each entry point below names the reference code it replaces (paths relative to torch_scae/ in the
+ * reference).  The Python mirror of that API (torch_scae_b200/part_decoder.py, object_decoder.py) binds these
+ * symbols with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (int64 where stated), at least 16-byte aligned;
+ *     nothing is allocated, freed or retained by the library; outputs are caller-allocated;
+ *   - "nullable" pointers may be NULL: a NULL input means "absent" with the reference's semantics for None,
+ *     a NULL output is simply not written;
+ *   - all work is enqueued on `stream` (a cudaStream_t) and is asynchronous with respect to the host;
+ *   - return value 0 = success, otherwise a negative SCAE_E* code; scae_last_error() returns a thread-local
+ *     human-readable message for the last failing call on this thread;
+ *   - re-entrant; no global state besides that message and per-device cached attributes.
+ *
+ * Shapes use the reference's symbols: B batch, M templates (= part capsules), C channels, h x w template,
+ * H x W image, O object capsules, V votes per object (= M), A = 8V+7 the per-capsule MLP output width.
+ */
+#ifndef SCAE_B200_H_
+#define SCAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCAE_B200_ABI_VERSION 1
+
+#define SCAE_OK 0
+#define SCAE_EINVAL (-1)   /* bad shape / flag / NULL where a pointer is required / misaligned pointer */
+#define SCAE_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed */
+#define SCAE_ELIMIT (-3)   /* shape exceeds what the kernels support (see scae_*_limits in DESIGN.md) */
+
+typedef void* scae_stream_t; /* cudaStream_t */
+
+int scae_abi_version(void);
+const char* scae_last_error(void);
+/* Compiled-for architecture string, e.g. "sm_100a". */
+const char* scae_build_arch(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Hot path 1: template warp + per-pixel template-mixture Gaussian log-likelihood
+ * replaces TemplateBasedImageDecoder.forward (part_decoder.py:152-243: F.affine_grid + F.grid_sample, background
+ * component, alpha/temperature mixing logits, log_safe(presence)) fused with GaussianMixture.log_prob
+ * (distributions.py:41-48) as evaluated by SCAE.loss (stacked_capsule_auto_encoder.py:220).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+#define SCAE_TMPL_MODE_ALPHA 0       /* use_alpha_channel=True : logits = warp(templates_alpha)           */
+#define SCAE_TMPL_MODE_TEMPERATURE 1 /* use_alpha_channel=False: logits = loc / (softplus(t+.5)+1e-4)     */
+
+/* The learnt scalars are passed RAW (as stored in the reference's state_dict) as device pointers so that no host
+ * synchronisation is needed; the kernels apply sigmoid / softplus themselves (part_decoder.py:192,:210,:216,:221). */
+typedef struct scae_tmpl_args {
+  const float* templates;         /* [B,M,C,h,w]                                                          */
+  const float* templates_alpha;   /* [M,h,w]      alpha mode; NULL in temperature mode                    */
+  const float* pose;              /* [B,M,6]      used directly as the 2x3 affine_grid theta              */
+  const float* presence;          /* [B,M]        nullable                                                */
+  const float* bg_image;          /* [B,C,H,W]    nullable; when NULL bg_value must be given              */
+  const float* bg_value;          /* [1] raw      nullable iff bg_image given                             */
+  const float* bg_mixing_logit;   /* [1] raw      alpha mode                                              */
+  const float* temperature_logit; /* [1] raw      temperature mode                                        */
+  const float* scale;             /* [1] raw learnt output scale; NULL => sigma = 1                       */
+  int B, M, C, h, w, H, W;
+  int mode;                       /* SCAE_TMPL_MODE_*                                                     */
+} scae_tmpl_args;
+
+/* log_prob[B,C,H,W] = pdf.log_prob(x);  ll[B] (nullable) = sum over (C,H,W);  cache[B,2,C,H,W] (nullable) holds
+ * the two per-pixel logsumexp terms the backward kernel needs. */
+int scae_tmpl_ll_fwd(const scae_tmpl_args* a, const float* x, float* log_prob, float* ll, float* cache,
+                     scae_stream_t stream);
+
+/* Bytes of scratch scae_tmpl_ll_bwd needs for its per-CTA partial sums of the batch-reduced gradients. */
+size_t scae_tmpl_ll_bwd_workspace_bytes(const scae_tmpl_args* a);
+
+/* Gradients of  sum(grad_log_prob * log_prob)  w.r.t. every differentiable input:
+ *   g_templates[B,M,C,h,w], g_pose[B,M,6] (required); g_presence[B,M], g_bg_image[B,C,H,W], g_alpha[M,h,w]
+ *   (nullable); g_scalars[4] = d/d raw {bg_value, bg_mixing_logit, temperature_logit, scale} (required; entries
+ *   for absent parameters are written as 0).  Deterministic: batch-reduced gradients are summed in a fixed order. */
+int scae_tmpl_ll_bwd(const scae_tmpl_args* a, const float* x, const float* grad_log_prob, const float* cache,
+                     float* g_templates, float* g_pose, float* g_presence, float* g_bg_image, float* g_alpha,
+                     float* g_scalars, void* workspace, size_t workspace_bytes, scae_stream_t stream);
+
+/* Materialises what the reference's decoder returns eagerly (part_decoder.py:239-243) and the mixture's point
+ * estimates (distributions.py:37-39, :50-77 with straight_through_gradient=False); every output nullable:
+ *   transformed_templates[B,M+1,C,H,W], mixing_logits[B,M+1,(alpha?1:C),H,W] (presence already added),
+ *   mode[B,C,H,W], mean[B,C,H,W].  No gradients (validation / logging path). */
+int scae_tmpl_render(const scae_tmpl_args* a, float* transformed_templates, float* mixing_logits, float* mode,
+                     float* mean, scae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Hot path 2: object->part vote composition + part-pose mixture likelihood
+ * replaces the post-MLP half of CapsuleLayer.forward (object_decoder.py:160-236), cv_ops.geometric_transform
+ * (cv_ops.py:20-76) for votes, CapsuleObjectDecoder.forward's glue (:413-415) and CapsuleLikelihood.__call__
+ * (:257-372).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+#define SCAE_CAPS_SIMILARITY 1u        /* similarity_transform=True  (cv_ops.py:51-54)                      */
+#define SCAE_CAPS_LEARN_VOTE_SCALE 2u  /* learn_vote_scale=True      (object_decoder.py:223-227)            */
+#define SCAE_CAPS_ALLOW_DEFORM 4u      /* allow_deformations=True    (object_decoder.py:168-169)            */
+#define SCAE_CAPS_RELU_GRAD 8u         /* bwd only: multiply g_all_param by (all_param > 0), i.e. fuse the
+                                          backward of the MLP's final ReLU (nn_ext.py:19-31)                */
+
+typedef struct scae_caps_args {
+  const float* all_param;   /* [B,O,A] per-capsule MLP outputs, split as [6V | 6 | 1 | V | V] (:91-99)      */
+  const float* cpr_static;  /* [O,V,6]                                                                    */
+  const float* bias_cvr;    /* [O,6]   caps_bias_list[0]                                                   */
+  const float* bias_caps;   /* [O]     caps_bias_list[1]                                                   */
+  const float* bias_vote;   /* [O,V]   caps_bias_list[2]                                                   */
+  const float* bias_scale;  /* [O,V]   caps_bias_list[3]                                                   */
+  const float* noise_caps;  /* [B,O]   nullable; already scaled: (rand-.5)*noise_scale (:201)              */
+  const float* noise_vote;  /* [B,O,V] nullable                                                            */
+  const float* x;           /* [B,V,6] part poses                                                          */
+  const float* presence;    /* [B,V]   nullable                                                            */
+  const float* dummy_vote;  /* [V,6]                                                                       */
+  int B, O, V;
+  unsigned flags;           /* SCAE_CAPS_*                                                                 */
+} scae_caps_args;
+
+/* Every tensor of the AttrDict CapsuleObjectDecoder.forward returns (object_decoder.py:229-236,:361-372,:413-415),
+ * plus per-example partial sums; all nullable except `posterior` when a backward pass will follow. */
+typedef struct scae_caps_outputs {
+  float* vote;                    /* [B,O,V,6]                                                             */
+  float* scale;                   /* [B,O,V]                                                               */
+  float* vote_presence;           /* [B,O,V]                                                               */
+  float* presence_logit_per_caps; /* [B,O]  (the reference's [B,O,1])                                      */
+  float* presence_logit_per_vote; /* [B,O,V]                                                               */
+  float* caps_presence;           /* [B,O]   max over V                                                    */
+  int32_t* caps_presence_arg;     /* [B,O]   argmax over V (lowest index on ties); needed by backward      */
+  float* ll_per_example;          /* [B]     sum_v presence * logsumexp_o; log_prob = mean over B          */
+  float* reg_per_example;         /* [B]     sum cpr_dynamic^2 / 2; cpr_dynamic_reg_loss = sum / B         */
+  float* vote_presence_binary;    /* [B,O,V] 0/1                                                           */
+  float* winner;                  /* [B,V,6]                                                               */
+  float* winner_presence;         /* [B,V]                                                                 */
+  int64_t* winner_idx;            /* [B,V]   argmax over O (lowest index on ties); needed by backward      */
+  int64_t* is_from_capsule;       /* [B,V]   winner_idx / V (sic, object_decoder.py:334)                   */
+  float* soft_winner;             /* [B,V,6]                                                               */
+  float* soft_winner_presence;    /* [B,V]                                                                 */
+  float* posterior_mixing_prob;   /* [B,O,V]                                                               */
+  float* mixing_log_prob;         /* [B,O+1,V]                                                             */
+  float* mixing_logit;            /* [B,O+1,V]                                                             */
+} scae_caps_outputs;
+
+int scae_caps_ll_fwd(const scae_caps_args* a, const scae_caps_outputs* out, scae_stream_t stream);
+
+/* Upstream gradients, one per differentiable output; all nullable (NULL = zero). */
+typedef struct scae_caps_upstream {
+  const float* g_ll_per_example;          /* [B]                                                          */
+  const float* g_reg_per_example;         /* [B]                                                          */
+  const float* g_posterior_mixing_prob;   /* [B,O,V]                                                      */
+  const float* g_caps_presence;           /* [B,O]                                                        */
+  const float* g_vote_presence;           /* [B,O,V]                                                      */
+  const float* g_soft_winner;             /* [B,V,6]                                                      */
+  const float* g_soft_winner_presence;    /* [B,V]                                                        */
+  const float* g_winner;                  /* [B,V,6]                                                      */
+  const float* g_winner_presence;         /* [B,V]                                                        */
+  const float* g_vote;                    /* [B,O,V,6]                                                    */
+  const float* g_scale;                   /* [B,O,V]                                                      */
+  const float* g_presence_logit_per_caps; /* [B,O]                                                        */
+  const float* g_presence_logit_per_vote; /* [B,O,V]                                                      */
+  const float* g_mixing_logit;            /* [B,O+1,V]                                                    */
+  const float* g_mixing_log_prob;         /* [B,O+1,V]                                                    */
+} scae_caps_upstream;
+
+/* Saved forward results the backward kernel reads instead of recomputing. */
+typedef struct scae_caps_saved {
+  const float* posterior_mixing_prob; /* [B,O,V]  required                                                */
+  const int32_t* caps_presence_arg;   /* [B,O]    required iff g_caps_presence given                      */
+  const int64_t* winner_idx;          /* [B,V]    required iff g_winner / g_winner_presence given         */
+} scae_caps_saved;
+
+size_t scae_caps_ll_bwd_workspace_bytes(const scae_caps_args* a);
+
+/* g_all_param[B,O,A] (required); g_shared[O,A] (required) = sum over B of the gradient w.r.t. the pre-activation
+ * sums, laid out like one all_param row, i.e. [g_cpr_static(6V) | g_bias_cvr(6) | g_bias_caps(1) | g_bias_vote(V) |
+ * g_bias_scale(V)] per capsule; g_dummy_vote[V,6], g_x[B,V,6], g_presence[B,V] nullable.  Deterministic. */
+int scae_caps_ll_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_caps_upstream* up,
+                     float* g_all_param, float* g_shared, float* g_dummy_vote, float* g_x, float* g_presence,
+                     void* workspace, size_t workspace_bytes, scae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCAE_B200_H_ */

@@ -1,0 +1,132 @@
+"""Set-transformer object encoder.  Stays in PyTorch (small dense matmuls; BASELINE.json north_star).
+
+Module tree / state-dict names as in the reference's set_transformer.py:24-223 (q/k/v/o projectors, ln0/ln1, fc,
+seeds, inducing points ``I``).  The presence handling reproduces the reference: ``(1 - presence) * 1e32`` is
+subtracted from the attention logits before the 1/sqrt(d) scaling (set_transformer.py:41-43).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def qkv_attention(queries, keys, values, presence=None):
+    logits = torch.matmul(queries, keys.transpose(1, 2))
+    if presence is not None:
+        logits = logits - (1. - presence.unsqueeze(-2)) * 1e32
+    weights = F.softmax(logits / math.sqrt(queries.shape[-1]), -1)
+    return torch.matmul(weights, values)
+
+
+class MultiHeadQKVAttention(nn.Module):
+    def __init__(self, d_k, d_v, n_heads):
+        super().__init__()
+        self.d_k, self.d_v, self.n_heads = d_k, d_v, n_heads
+        d_k_p = int(math.ceil(d_k / n_heads)) * n_heads
+        d_v_p = int(math.ceil(d_v / n_heads)) * n_heads
+        self.q_projector = nn.Linear(d_k, d_k_p)
+        self.k_projector = nn.Linear(d_k, d_k_p)
+        self.v_projector = nn.Linear(d_v, d_v_p)
+        self.o_projector = nn.Linear(d_v_p, d_v)
+
+    def _split_heads(self, t):
+        B, L, _ = t.shape
+        H = self.n_heads
+        return t if H == 1 else t.view(B, L, H, -1).permute(2, 0, 1, 3).reshape(H * B, L, -1)
+
+    def forward(self, queries, keys, values, presence=None):
+        assert queries.shape[2] == keys.shape[2]
+        assert keys.shape[1] == values.shape[1]
+        if presence is not None:
+            assert values.shape[:2] == presence.shape
+        B, N, _ = queries.shape
+        H = self.n_heads
+        q = self._split_heads(self.q_projector(queries))
+        k = self._split_heads(self.k_projector(keys))
+        v = self._split_heads(self.v_projector(values))
+        if presence is not None and H > 1:
+            presence = presence.repeat(H, 1)
+        o = qkv_attention(q, k, v, presence)
+        if H > 1:
+            o = o.view(H, B, N, -1).permute(1, 2, 0, 3).reshape(B, N, -1)
+        return self.o_projector(o)
+
+
+class MAB(nn.Module):
+    def __init__(self, d, n_heads, layer_norm=False):
+        super().__init__()
+        self.layer_norm = layer_norm
+        self.mqkv = MultiHeadQKVAttention(d_k=d, d_v=d, n_heads=n_heads)
+        if layer_norm:
+            self.ln0 = nn.LayerNorm(d)
+            self.ln1 = nn.LayerNorm(d)
+        self.fc = nn.Linear(d, d)
+
+    def forward(self, queries, keys, presence=None):
+        h = self.mqkv(queries, keys, keys, presence) + queries
+        if presence is not None:
+            assert presence.shape[1] == queries.shape[1] == keys.shape[1]
+            h = h * presence.unsqueeze(-1)
+        if self.layer_norm:
+            h = self.ln0(h)
+        h = h + F.relu(self.fc(h))
+        if self.layer_norm:
+            h = self.ln1(h)
+        return h
+
+
+class SAB(nn.Module):
+    def __init__(self, d, n_heads, layer_norm=False):
+        super().__init__()
+        self.mab = MAB(d=d, n_heads=n_heads, layer_norm=layer_norm)
+
+    def forward(self, x, presence=None):
+        return self.mab(x, x, presence)
+
+
+class ISAB(nn.Module):
+    def __init__(self, d, n_heads, n_inducing_points, layer_norm=False):
+        super().__init__()
+        self.mab0 = MAB(d=d, n_heads=n_heads, layer_norm=layer_norm)
+        self.mab1 = MAB(d=d, n_heads=n_heads, layer_norm=layer_norm)
+        self.I = nn.Parameter(nn.init.xavier_uniform_(torch.zeros(1, n_inducing_points, d)))
+
+    def forward(self, x, presence=None):
+        h = self.mab0(self.I.expand(x.shape[0], -1, -1), x, presence)
+        return self.mab1(x, h)
+
+
+class PMA(nn.Module):
+    def __init__(self, d, n_heads, n_seeds, layer_norm=False):
+        super().__init__()
+        self.mab = MAB(d=d, n_heads=n_heads, layer_norm=layer_norm)
+        self.S = nn.Parameter(nn.init.xavier_uniform_(torch.zeros(1, n_seeds, d)))
+
+    def forward(self, x, presence=None):
+        return self.mab(self.S.expand(x.shape[0], -1, -1), x, presence)
+
+
+class SetTransformer(nn.Module):
+    """(B, M, dim_in) part descriptions -> (B, n_outputs, dim_out) object encodings."""
+
+    def __init__(self, dim_in, dim_hidden, dim_out, n_outputs, n_layers, n_heads, layer_norm=False,
+                 n_inducing_points: int = None):
+        super().__init__()
+        self.fc1 = nn.Linear(dim_in, dim_hidden)
+        if n_inducing_points is None:
+            blocks = [SAB(d=dim_hidden, n_heads=n_heads, layer_norm=layer_norm) for _ in range(n_layers)]
+        else:
+            blocks = [ISAB(d=dim_hidden, n_heads=n_heads, layer_norm=layer_norm,
+                           n_inducing_points=n_inducing_points) for _ in range(n_layers)]
+        self.sabs = nn.ModuleList(blocks)
+        self.fc2 = nn.Linear(dim_hidden, dim_out)
+        self.seeds = nn.Parameter(nn.init.xavier_uniform_(torch.zeros(1, n_outputs, dim_out)))
+        self.multi_head_attention = MultiHeadQKVAttention(d_k=dim_out, d_v=dim_out, n_heads=n_heads)
+
+    def forward(self, x, presence=None):
+        h = self.fc1(x)
+        for block in self.sabs:
+            h = block(h, presence)
+        z = self.fc2(h)
+        return self.multi_head_attention(self.seeds.expand(x.shape[0], -1, -1), z, z, presence)
