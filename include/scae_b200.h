@@ -131,6 +131,7 @@ typedef struct scae_caps_outputs {
   float* presence_logit_per_vote; /* [B,O,V]                                                               */
   float* caps_presence;           /* [B,O]   max over V                                                    */
   int32_t* caps_presence_arg;     /* [B,O]   argmax over V (lowest index on ties); needed by backward      */
+  float* log_prob_per_point;      /* [B,V]   logsumexp_o of the posterior logits, before presence weighting */
   float* ll_per_example;          /* [B]     sum_v presence * logsumexp_o; log_prob = mean over B          */
   float* reg_per_example;         /* [B]     sum cpr_dynamic^2 / 2; cpr_dynamic_reg_loss = sum / B         */
   float* vote_presence_binary;    /* [B,O,V] 0/1                                                           */
@@ -169,6 +170,7 @@ typedef struct scae_caps_upstream {
 /* Saved forward results the backward kernel reads instead of recomputing. */
 typedef struct scae_caps_saved {
   const float* posterior_mixing_prob; /* [B,O,V]  required                                                */
+  const float* log_prob_per_point;    /* [B,V]    required                                                */
   const int32_t* caps_presence_arg;   /* [B,O]    required iff g_caps_presence given                      */
   const int64_t* winner_idx;          /* [B,V]    required iff g_winner / g_winner_presence given         */
 } scae_caps_saved;

@@ -1,0 +1,55 @@
+"""Builds libscae_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+Used by ``__graft_entry__.build()`` and ``python -m torch_scae_b200.build``.  The library has no PyTorch or Python
+dependency: plain CUDA runtime, ``extern "C"`` entry points declared in include/scae_b200.h.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB_PATH = os.path.join(CSRC, 'libscae_b200.so')
+SOURCES = ['api.cu', 'caps_ll.cu', 'tmpl_ll.cu']
+HEADERS = ['common.cuh', 'tmpl_common.cuh', os.path.join('..', '..', 'include', 'scae_b200.h')]
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found; cannot build libscae_b200.so')
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compiles every .cu into one shared library; returns its path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace('.cu', '.o'))
+        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        if verbose:
+            cmd.insert(1, '-Xptxas=-v')
+            print(' '.join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+        objs.append(obj)
+    cmd = [nvcc, '-shared', '-o', LIB_PATH, *objs, '-gencode', 'arch=compute_100a,code=sm_100a']
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

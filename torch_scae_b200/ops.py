@@ -1,0 +1,234 @@
+"""``torch.autograd.Function`` wrappers around the C-ABI kernels (the only callers of libscae_b200.so).
+
+PyTorch is plumbing here: it owns device memory and the stream; the arithmetic of both hot paths happens in
+csrc/tmpl_ll.cu and csrc/caps_ll.cu.  All tensors crossing the boundary are made contiguous fp32 first.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (CAPS_OUTPUT_FIELDS, CAPS_UPSTREAM_FIELDS, CapsArgs, CapsOutputs, CapsSaved, CapsUpstream, TmplArgs,
+                   check, ptr)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    """contiguous fp32 CUDA tensor (no copy when it already is one); None passes through."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.ScaeError('torch_scae_b200 runs on CUDA only (no CPU fallback); got a CPU tensor')
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# =================================================================================================================
+# hot path 1
+# =================================================================================================================
+
+def _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit, temperature_logit,
+               scale, output_size):
+    B, M, C, h, w = templates.shape
+    H, W = output_size
+    alpha_mode = templates_alpha is not None
+    a = TmplArgs(ptr(templates), ptr(templates_alpha), ptr(pose), ptr(presence), ptr(bg_image), ptr(bg_value),
+                 ptr(bg_mixing_logit) if alpha_mode else None, None if alpha_mode else ptr(temperature_logit),
+                 ptr(scale), B, M, C, h, w, H, W,
+                 _lib.TMPL_MODE_ALPHA if alpha_mode else _lib.TMPL_MODE_TEMPERATURE)
+    return a
+
+
+class TemplateMixtureLogProb(torch.autograd.Function):
+    """(log_prob [B,C,H,W], ll [B]) of x under the template mixture; see include/scae_b200.h scae_tmpl_ll_fwd/bwd.
+
+    Differentiable w.r.t. templates, pose, presence, bg_image and the decoder parameters; ``x`` is data (no grad).
+    """
+
+    @staticmethod
+    def forward(ctx, templates, pose, presence, bg_image, x, templates_alpha, bg_value, bg_mixing_logit,
+                temperature_logit, scale, output_size):
+        lib = _lib.load()
+        tensors = [_f32c(t) for t in (templates, pose, presence, bg_image, x, templates_alpha, bg_value,
+                                      bg_mixing_logit, temperature_logit, scale)]
+        templates, pose, presence, bg_image, x, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, \
+            scale = tensors
+        B, M, C, h, w = templates.shape
+        H, W = output_size
+        if tuple(x.shape) != (B, C, H, W):
+            raise ValueError(f'log_prob target has shape {tuple(x.shape)}, expected {(B, C, H, W)}')
+        if bg_image is None and bg_value is None:
+            # same failure as the reference (part_decoder.py:192 reads self.bg_value)
+            raise AttributeError("'TemplateBasedImageDecoder' object has no attribute 'bg_value'")
+        args = _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit,
+                          temperature_logit, scale, (H, W))
+        log_prob = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
+        ll = torch.empty(B, device=x.device, dtype=torch.float32)
+        cache = torch.empty(B, 2, C, H, W, device=x.device, dtype=torch.float32)
+        check(lib.scae_tmpl_ll_fwd(ctypes.byref(args), ptr(x), ptr(log_prob), ptr(ll), ptr(cache), _stream()),
+              'scae_tmpl_ll_fwd')
+        ctx.save_for_backward(*[t for t in tensors if t is not None], cache)
+        ctx.present = [t is not None for t in tensors]
+        ctx.output_size = (H, W)
+        ctx.set_materialize_grads(False)
+        return log_prob, ll
+
+    @staticmethod
+    def backward(ctx, g_log_prob, g_ll):
+        lib = _lib.load()
+        saved = list(ctx.saved_tensors)
+        cache = saved.pop()
+        it = iter(saved)
+        templates, pose, presence, bg_image, x, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale = \
+            [next(it) if p else None for p in ctx.present]
+        B, M, C, h, w = templates.shape
+        H, W = ctx.output_size
+        if g_log_prob is None and g_ll is None:
+            return (None,) * 11
+        if g_ll is not None:
+            g = g_ll.reshape(B, 1, 1, 1).expand(B, C, H, W)
+            g = g + g_log_prob if g_log_prob is not None else g
+        else:
+            g = g_log_prob
+        g = _f32c(g)
+        args = _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit,
+                          temperature_logit, scale, (H, W))
+        dev = templates.device
+        g_templates = torch.empty_like(templates)
+        g_pose = torch.empty_like(pose)
+        g_presence = torch.empty_like(presence) if presence is not None else None
+        g_bg_image = torch.empty_like(bg_image) if bg_image is not None else None
+        g_alpha = torch.empty_like(templates_alpha) if templates_alpha is not None else None
+        g_scalars = torch.empty(4, device=dev, dtype=torch.float32)
+        ws_bytes = lib.scae_tmpl_ll_bwd_workspace_bytes(ctypes.byref(args))
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        check(lib.scae_tmpl_ll_bwd(ctypes.byref(args), ptr(x), ptr(g), ptr(cache), ptr(g_templates), ptr(g_pose),
+                                   ptr(g_presence), ptr(g_bg_image), ptr(g_alpha), ptr(g_scalars), ptr(ws), ws_bytes,
+                                   _stream()), 'scae_tmpl_ll_bwd')
+
+        def scalar(i, p):
+            return g_scalars[i:i + 1].reshape(p.shape) if p is not None else None
+        return (g_templates, g_pose, g_presence, g_bg_image, None, g_alpha, scalar(0, bg_value),
+                scalar(1, bg_mixing_logit), scalar(2, temperature_logit), scalar(3, scale), None)
+
+
+def template_render(templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit,
+                    temperature_logit, scale, output_size, want=('transformed_templates', 'mixing_logits')):
+    """No-grad materialisation through scae_tmpl_render; returns a dict with the requested tensors."""
+    lib = _lib.load()
+    templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale = \
+        [_f32c(t.detach()) if t is not None else None for t in (
+            templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale)]
+    if bg_image is None and bg_value is None:
+        raise AttributeError("'TemplateBasedImageDecoder' object has no attribute 'bg_value'")
+    B, M, C, h, w = templates.shape
+    H, W = output_size
+    args = _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit,
+                      temperature_logit, scale, (H, W))
+    dev = templates.device
+    shapes = dict(transformed_templates=(B, M + 1, C, H, W),
+                  mixing_logits=(B, M + 1, 1 if templates_alpha is not None else C, H, W),
+                  mode=(B, C, H, W), mean=(B, C, H, W))
+    out = {k: torch.empty(shapes[k], device=dev, dtype=torch.float32) for k in want}
+    check(lib.scae_tmpl_render(ctypes.byref(args), ptr(out.get('transformed_templates')),
+                               ptr(out.get('mixing_logits')), ptr(out.get('mode')), ptr(out.get('mean')), _stream()),
+          'scae_tmpl_render')
+    return out
+
+
+# =================================================================================================================
+# hot path 2
+# =================================================================================================================
+
+# order of the tensors CapsuleVoteLikelihood returns
+CAPS_RETURNS = ('vote', 'scale', 'vote_presence', 'presence_logit_per_caps', 'presence_logit_per_vote',
+                'caps_presence', 'll_per_example', 'reg_per_example', 'vote_presence_binary', 'winner',
+                'winner_presence', 'is_from_capsule', 'soft_winner', 'soft_winner_presence', 'posterior_mixing_prob',
+                'mixing_log_prob', 'mixing_logit')
+_CAPS_NON_DIFF = ('vote_presence_binary', 'is_from_capsule')
+
+
+def _caps_args(all_param, cpr_static, biases, noise_caps, noise_vote, x, presence, dummy_vote, flags):
+    B, O, A = all_param.shape
+    V = x.shape[1]
+    return CapsArgs(ptr(all_param), ptr(cpr_static), ptr(biases[0]), ptr(biases[1]), ptr(biases[2]), ptr(biases[3]),
+                    ptr(noise_caps), ptr(noise_vote), ptr(x), ptr(presence), ptr(dummy_vote), B, O, V, flags)
+
+
+class CapsuleVoteLikelihood(torch.autograd.Function):
+    """Everything CapsuleObjectDecoder.forward computes after the per-capsule MLPs, as one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, all_param, cpr_static, b0, b1, b2, b3, dummy_vote, x, presence, noise_caps, noise_vote, flags):
+        lib = _lib.load()
+        all_param, cpr_static, b0, b1, b2, b3, dummy_vote, x, presence, noise_caps, noise_vote = \
+            [_f32c(t) for t in (all_param, cpr_static, b0, b1, b2, b3, dummy_vote, x, presence, noise_caps, noise_vote)]
+        B, O, A = all_param.shape
+        V = x.shape[1]
+        if A != 8 * V + 7:
+            raise ValueError(f'all_param has {A} columns, expected 8*V+7 = {8 * V + 7}')
+        dev = all_param.device
+        f = dict(device=dev, dtype=torch.float32)
+        shapes = dict(vote=(B, O, V, 6), scale=(B, O, V), vote_presence=(B, O, V),
+                      presence_logit_per_caps=(B, O, 1), presence_logit_per_vote=(B, O, V), caps_presence=(B, O),
+                      log_prob_per_point=(B, V), ll_per_example=(B,), reg_per_example=(B,),
+                      vote_presence_binary=(B, O, V), winner=(B, V, 6), winner_presence=(B, V),
+                      soft_winner=(B, V, 6), soft_winner_presence=(B, V), posterior_mixing_prob=(B, O, V),
+                      mixing_log_prob=(B, O + 1, V), mixing_logit=(B, O + 1, V))
+        out = {k: torch.empty(s, **f) for k, s in shapes.items()}
+        out['caps_presence_arg'] = torch.empty(B, O, device=dev, dtype=torch.int32)
+        out['winner_idx'] = torch.empty(B, V, device=dev, dtype=torch.int64)
+        out['is_from_capsule'] = torch.empty(B, V, device=dev, dtype=torch.int64)
+        args = _caps_args(all_param, cpr_static, (b0, b1, b2, b3), noise_caps, noise_vote, x, presence, dummy_vote,
+                          flags)
+        outs = CapsOutputs(*[ptr(out[k]) for k in CAPS_OUTPUT_FIELDS])
+        check(lib.scae_caps_ll_fwd(ctypes.byref(args), ctypes.byref(outs), _stream()), 'scae_caps_ll_fwd')
+        inputs = (all_param, cpr_static, b0, b1, b2, b3, dummy_vote, x, presence, noise_caps, noise_vote)
+        ctx.present = [t is not None for t in inputs]
+        ctx.save_for_backward(*[t for t in inputs if t is not None], out['posterior_mixing_prob'],
+                              out['log_prob_per_point'], out['caps_presence_arg'], out['winner_idx'])
+        ctx.flags = flags
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(*[out[k] for k in _CAPS_NON_DIFF])
+        return tuple(out[k] for k in CAPS_RETURNS)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        saved = list(ctx.saved_tensors)
+        winner_idx = saved.pop()
+        caps_arg = saved.pop()
+        lse = saved.pop()
+        posterior = saved.pop()
+        it = iter(saved)
+        all_param, cpr_static, b0, b1, b2, b3, dummy_vote, x, presence, noise_caps, noise_vote = \
+            [next(it) if p else None for p in ctx.present]
+        B, O, A = all_param.shape
+        V = x.shape[1]
+        g = {k: _f32c(v) for k, v in zip(CAPS_RETURNS, grads) if k not in _CAPS_NON_DIFF}
+        up = CapsUpstream(*[ptr(g.get(k[2:])) for k in CAPS_UPSTREAM_FIELDS])
+        sv = CapsSaved(ptr(posterior), ptr(lse), ptr(caps_arg), ptr(winner_idx))
+        args = _caps_args(all_param, cpr_static, (b0, b1, b2, b3), noise_caps, noise_vote, x, presence, dummy_vote,
+                          ctx.flags)
+        dev = all_param.device
+        g_all = torch.empty_like(all_param)
+        g_shared = torch.empty(O, A, device=dev, dtype=torch.float32)
+        g_dummy = torch.empty(V, 6, device=dev, dtype=torch.float32) if ctx.needs_input_grad[6] else None
+        g_x = torch.empty_like(x) if ctx.needs_input_grad[7] else None
+        g_presence = torch.empty_like(presence) if presence is not None and ctx.needs_input_grad[8] else None
+        ws_bytes = lib.scae_caps_ll_bwd_workspace_bytes(ctypes.byref(args))
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        check(lib.scae_caps_ll_bwd(ctypes.byref(args), ctypes.byref(sv), ctypes.byref(up), ptr(g_all), ptr(g_shared),
+                                   ptr(g_dummy), ptr(g_x), ptr(g_presence), ptr(ws), ws_bytes, _stream()),
+              'scae_caps_ll_bwd')
+        g_static = g_shared[:, :6 * V].reshape(cpr_static.shape)
+        g_b0 = g_shared[:, 6 * V:6 * V + 6].reshape(b0.shape)
+        g_b1 = g_shared[:, 6 * V + 6].reshape(b1.shape)
+        g_b2 = g_shared[:, 6 * V + 7:7 * V + 7].reshape(b2.shape)
+        g_b3 = g_shared[:, 7 * V + 7:].reshape(b3.shape)
+        return (g_all, g_static, g_b0, g_b1, g_b2, g_b3, g_dummy.reshape(dummy_vote.shape) if g_dummy is not None else None,
+                g_x, g_presence, None, None, None)
