@@ -1,0 +1,156 @@
+"""GPU parity, hot path 2: csrc/caps_ll.cu through the C ABI vs the oracle and the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): rel <= 1e-5 on log-likelihoods / losses, rel <= 1e-4 on gradients, max-norm
+relative (max|a-b| / max|b|) against the fp64 oracle evaluated on the same fp32-representable inputs.
+"""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, sub
+from gpu_util import CAPS_UP, DEV, capsule_cuda, capsule_oracle, make_capsule_inputs, strict_fp32
+from test_oracle_golden import CAPSULE, CAPSULE_FLAGS
+
+pytestmark = pytest.mark.gpu
+TOL_LL, TOL_OUT, TOL_GRAD = 1e-5, 1e-5, 1e-4
+DEFAULT = dict(similarity=False, learn_vote_scale=True, allow_deformations=True)
+FWD_KEYS = ('vote', 'scale', 'vote_presence', 'presence_logit_per_caps', 'presence_logit_per_vote', 'caps_presence',
+            'vote_presence_binary', 'winner', 'winner_presence', 'soft_winner', 'soft_winner_presence',
+            'posterior_mixing_prob', 'mixing_log_prob', 'mixing_logit', 'll_per_example', 'reg_per_example')
+GRAD_KEYS = ('g_all_param', 'g_cpr_static', 'g_dummy_vote', 'g_x', 'g_presence', 'g_b0', 'g_b1', 'g_b2', 'g_b3')
+
+
+def _f32(d):
+    """round the fp64 synthetic inputs to fp32-representable values so both sides see identical numbers"""
+    def r(t):
+        if isinstance(t, torch.Tensor):
+            return t.float().double()
+        if isinstance(t, list):
+            return [r(x) for x in t]
+        if isinstance(t, dict):
+            return {k: r(v) for k, v in t.items()}
+        return t
+    return {k: r(v) for k, v in d.items()}
+
+
+def _compare(got, ref, keys, tol, ctx):
+    for k in keys:
+        if k not in ref or ref[k] is None:
+            continue
+        if ref[k].dtype == torch.int64:
+            assert torch.equal(got[k].cpu(), ref[k]), (ctx, k)
+            continue
+        e = rel_err(got[k], ref[k].reshape(got[k].shape))
+        assert e < tol, (ctx, k, e)
+
+
+@pytest.mark.parametrize('B,O,V', [(8, 10, 40), (8, 32, 40), (5, 32, 64), (6, 32, 24), (3, 35, 6), (2, 3, 130),
+                                   (1, 1, 1)])
+def test_kernel_vs_fp64_oracle(B, O, V):
+    d = _f32(make_capsule_inputs(B, O, V, seed=B * 1000 + O * 10 + V))
+    ref = capsule_oracle(d, DEFAULT)
+    got = capsule_cuda(d, DEFAULT)
+    _compare(got, ref, FWD_KEYS, TOL_OUT, (B, O, V))
+    assert rel_err(got['log_prob'], ref['log_prob']) < TOL_LL
+    assert torch.equal(got['is_from_capsule'].cpu(), ref['is_from_capsule'])
+    _compare(got, ref, GRAD_KEYS, TOL_GRAD, (B, O, V))
+
+
+@pytest.mark.parametrize('flags', [dict(similarity=True, learn_vote_scale=False, allow_deformations=False),
+                                   dict(similarity=True, learn_vote_scale=True, allow_deformations=True),
+                                   dict(similarity=False, learn_vote_scale=False, allow_deformations=True)])
+@pytest.mark.parametrize('presence,noise', [(True, True), (False, False)])
+def test_kernel_flag_and_optional_input_combinations(flags, presence, noise):
+    d = _f32(make_capsule_inputs(4, 7, 9, presence=presence, noise=noise, seed=7))
+    ref = capsule_oracle(d, flags)
+    got = capsule_cuda(d, flags)
+    _compare(got, ref, FWD_KEYS, TOL_OUT, flags)
+    _compare(got, ref, GRAD_KEYS, TOL_GRAD, flags)
+
+
+def test_training_subset_of_upstream_gradients():
+    """default SCAE training only feeds log_prob, posterior, caps_presence and the regulariser back (vote_type='enc')"""
+    which = ('ll_per_example', 'reg_per_example', 'posterior_mixing_prob', 'caps_presence')
+    d = _f32(make_capsule_inputs(6, 32, 40, seed=11))
+    ref = capsule_oracle(d, DEFAULT, which)
+    got = capsule_cuda(d, DEFAULT, which)
+    _compare(got, ref, GRAD_KEYS, TOL_GRAD, 'train-subset')
+    assert float(got['g_dummy_vote'].abs().max()) == 0.0      # measured in the survey: no grad in the default config
+
+
+@pytest.mark.parametrize('case', CAPSULE)
+def test_module_vs_reference_golden(case):
+    """CapsuleObjectDecoder (batched MLPs + fused kernel) with the reference's weights, inputs and noise draws."""
+    from golden.cases import CAPSULE_CASES
+    from torch_scae_b200.object_decoder import CapsuleLayer, CapsuleObjectDecoder
+    strict_fp32()
+    c = CAPSULE_CASES[case]
+    g = load_golden('capsule_' + case)
+    layer = CapsuleLayer(c['O'], c['F'], c['V'], c['D'], hidden_sizes=c['hidden'],
+                         learn_vote_scale=c['learn_vote_scale'], allow_deformations=c['allow_deformations'],
+                         noise_type=c['noise_type'], noise_scale=c['noise_scale'], similarity_transform=c['similarity'])
+    dec = CapsuleObjectDecoder(layer)
+    dec.load_state_dict(sub(g, 'param.'), strict=True)
+    dec.to(DEV)
+    enc = g['obj_encoding'].to(DEV)
+    x = g['x'].to(DEV).requires_grad_(True)
+    presence = g['presence'].to(DEV).requires_grad_(True) if 'presence' in g else None
+    noise = (g['noise_caps'].to(DEV), g['noise_vote'].to(DEV)) if 'noise_caps' in g else None
+    res = dec(enc, x, presence, noise=noise)
+    out = sub(g, 'out.')
+    assert set(out) == set(res.keys())
+    for k, ref in out.items():
+        if ref.dtype == torch.int64:
+            assert torch.equal(res[k].cpu(), ref), k
+        else:
+            assert rel_err(res[k], ref) < (TOL_LL if k in ('log_prob', 'cpr_dynamic_reg_loss') else 2e-5), k
+    loss = 1.7 * res.log_prob + 0.9 * res.cpr_dynamic_reg_loss
+    for k, w in sub(g, 'weight.').items():
+        loss = loss + 0.3 * (res[k] * w.to(DEV)).sum()
+    loss.backward()
+    assert rel_err(x.grad, g['g_x']) < TOL_GRAD
+    if presence is not None:
+        assert rel_err(presence.grad, g['g_presence']) < TOL_GRAD
+    grads = {k: v for k, v in sub(g, 'g_param.').items()}
+    assert rel_err(dec.dummy_vote.grad, grads['dummy_vote']) < TOL_GRAD
+    assert rel_err(layer.cpr_static.grad, grads['capsule_layer.cpr_static']) < TOL_GRAD
+    for i in range(4):
+        ref = grads[f'capsule_layer.caps_bias_list.{i}']
+        got = layer.caps_bias_list[i].grad
+        if float(ref.abs().max()) == 0.0:
+            assert got is None or float(got.abs().max()) == 0.0
+        else:
+            assert rel_err(got, ref) < TOL_GRAD, i
+
+
+def test_full_size_properties():
+    """BASELINE config sizes (B=1024, O=32, V=40): size-independent properties instead of an oracle run."""
+    B, O, V = 1024, 32, 40
+    d = make_capsule_inputs(B, O, V, seed=3, dtype=torch.float32)
+    which = ('ll_per_example', 'posterior_mixing_prob', 'caps_presence', 'reg_per_example')
+    a = capsule_cuda(d, DEFAULT, which)
+    b = capsule_cuda(d, DEFAULT, which)
+    for k in a:                                              # deterministic: bit-identical reruns
+        assert torch.equal(a[k], b[k]), k
+    post = a['posterior_mixing_prob']
+    assert float(post.min()) >= 0 and float(post.sum(1).max()) <= 1 + 1e-5       # dummy component takes the rest
+    mlp = a['mixing_log_prob']
+    assert rel_err(mlp.exp().sum(1), torch.ones(B, V)) < 1e-5
+    assert torch.equal(a['caps_presence'], a['vote_presence'].max(-1)[0])
+    idx = a['posterior_mixing_prob'].argmax(1)               # hard winner = argmax of the posterior over objects
+    win = torch.gather(a['vote'], 1, idx.view(B, 1, V, 1).expand(B, 1, V, 6)).squeeze(1)
+    assert torch.equal(win, a['winner'])
+    # batch permutation equivariance: per-example results do not depend on the batch position / CTA assignment
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    dp = dict(d)
+    for k in ('all_param', 'x', 'presence', 'noise_caps', 'noise_vote'):
+        dp[k] = d[k][perm]
+    dp['up'] = {k: v[perm] for k, v in d['up'].items()}
+    p = capsule_cuda(dp, DEFAULT, which)
+    for k in ('ll_per_example', 'posterior_mixing_prob', 'soft_winner', 'g_all_param'):
+        assert torch.equal(p[k], a[k][perm.to(a[k].device)]), k
+    # linearity of the backward pass in the upstream gradient
+    d2 = dict(d)
+    d2['up'] = {k: 2 * v for k, v in d['up'].items()}
+    c = capsule_cuda(d2, DEFAULT, which)
+    assert rel_err(c['g_all_param'], 2 * a['g_all_param']) < 1e-6
+    assert rel_err(c['g_cpr_static'], 2 * a['g_cpr_static']) < 1e-5

@@ -1,0 +1,120 @@
+"""GPU parity of the whole SCAE (PyTorch modules + both fused kernels) against the reference's golden vectors, and
+against the CPU oracle model on a mid-size configuration."""
+import pytest
+import torch
+
+from conftest import l2_rel_err, load_golden, rel_err, sub
+from gpu_util import DEV, strict_fp32
+from test_oracle_golden import SCAE
+
+pytestmark = pytest.mark.gpu
+TOL_LL, TOL_GRAD = 1e-5, 1e-4
+
+
+@pytest.mark.parametrize('case', SCAE)
+def test_scae_vs_reference_golden(case):
+    from golden.cases import scae_case_params
+    from torch_scae_b200 import factory
+    strict_fp32()
+    g = load_golden('scae_' + case)
+    model = factory.make_scae(scae_case_params(case))
+    model.load_state_dict(sub(g, 'param.'), strict=True)
+    model.to(DEV).train()
+    image, label = g['image'].to(DEV), g['label'].to(DEV)
+    noise = dict(part_presence=g['noise_part_presence'].to(DEV), caps=g['noise_caps'].to(DEV),
+                 vote=g['noise_vote'].to(DEV))
+    res = model(image, noise=noise)
+    loss, log = model.loss(res, image, label)
+    assert rel_err(loss, g['loss']) < TOL_LL
+    for k, ref in sub(g, 'log.').items():
+        assert rel_err(log[k], ref) < TOL_LL, k
+    for k, ref in sub(g, 'out.').items():
+        if k == 'rec_log_prob':
+            got = res.rec.pdf.log_prob(image)
+        elif k == 'rec_mixing_logits':
+            with torch.no_grad():
+                got = res.rec.mixing_logits
+        else:
+            got = res[k]
+        if ref.dtype == torch.int64:
+            assert torch.equal(got.cpu(), ref), k
+        else:
+            assert rel_err(got, ref) < 2e-5, k
+    assert float(model.calculate_accuracy(res, label)) == float(g['accuracy'])
+    loss.backward()
+    sd_grads = {}
+    for name, p in model.named_parameters():
+        sd_grads[name] = p.grad
+    # stacked per-capsule MLP parameters -> reference names
+    ref_grads = sub(g, 'g_param.')
+    layer = model.obj_decoder.capsule_layer
+    for mod_name, mod in (('mlps', layer.mlps), ('caps_mlps', layer.caps_mlps)):
+        for suffix, p in mod._named():
+            for i in range(mod.n):
+                sd_grads[f'obj_decoder.capsule_layer.{mod_name}.{i}.{suffix}'] = p.grad[i]
+    worst = 0.0
+    for k, ref in ref_grads.items():
+        got = sd_grads[k]
+        if float(ref.abs().max()) == 0.0:
+            assert got is None or float(got.abs().max()) == 0.0, k
+            continue
+        # gradients that flow through the pose of the warped templates inherit the bilinear cell-flip noise
+        # (part encoder weights): norm-wise criterion there, max-norm everywhere else
+        e = l2_rel_err(got, ref) if k.startswith('part_encoder.') else rel_err(got, ref)
+        worst = max(worst, e)
+        assert e < (2e-3 if k.startswith('part_encoder.') else TOL_GRAD), (k, e)
+
+
+def test_reconstruct_alternatives_are_lazy_and_renderable():
+    from golden.cases import tiny_model_params
+    from torch_scae_b200 import factory
+    params = tiny_model_params()
+    params['scae_params']['reconstruct_alternatives'] = True
+    model = factory.make_scae(params).to(DEV).eval()
+    with torch.no_grad():
+        res = model(torch.rand(3, 1, 20, 20, device=DEV))
+        assert not res.is_materialized('transformed_templates')
+        for key, batch in (('bottom_up_rec', 3), ('top_down_rec', 3), ('top_down_per_caps_rec', 3 * 4)):
+            img = res[key].pdf.mode()
+            assert img.shape == (batch, 1, 20, 20) and bool(torch.isfinite(img).all())
+        assert res.transformed_templates.shape == (3, 6, 1, 20, 20)
+
+
+def test_mid_size_model_vs_cpu_oracle():
+    """MNIST-shaped model (40x40, 40 part caps, 32 object caps, batch 16): loss and gradients vs the CPU oracle."""
+    from oracle import scae_model
+    from torch_scae_b200 import factory
+    strict_fp32()
+    torch.manual_seed(0)
+    params = dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=32,
+                  scae_params=dict(reconstruct_alternatives=False))
+    model = factory.make_scae(params)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if 'templates_alpha' in name or 'cpr_static' in name or 'caps_bias_list' in name:
+                p.copy_(0.1 * torch.randn_like(p))
+    cfg = factory.prepare_model_params(**params)
+    B = 16
+    image = torch.rand(B, 1, 40, 40)
+    label = torch.randint(0, 10, (B,))
+    noise = dict(part_presence=(torch.rand(B, 40) - .5) * 4, caps=(torch.rand(B, 32, 1) - .5) * 4,
+                 vote=(torch.rand(B, 32, 40) - .5) * 4)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    ref_res = scae_model.scae_forward(sd, cfg, image, noise, training=True)
+    ref_loss, ref_log = scae_model.scae_loss(ref_res, cfg, image, label)
+    ref_loss.backward()
+
+    model.to(DEV).train()
+    res = model(image.to(DEV), noise={k: v.to(DEV) for k, v in noise.items()})
+    loss, log = model.loss(res, image.to(DEV), label.to(DEV))
+    loss.backward()
+    assert rel_err(loss, ref_loss) < TOL_LL
+    for k in ref_log:
+        assert rel_err(log[k], ref_log[k]) < TOL_LL, k
+    for k in ('part_decoder.templates_alpha', 'part_decoder.bg_value', 'part_decoder.bg_mixing_logit',
+              'template_generator.template_logits', 'obj_decoder.capsule_layer.cpr_static',
+              'obj_encoder.fc1.weight'):
+        got = dict(model.named_parameters())[k].grad
+        assert rel_err(got, sd[k].grad) < TOL_GRAD, k
+    got = model.part_encoder.att_conv.weight.grad
+    assert l2_rel_err(got, sd['part_encoder.att_conv.weight'].grad) < 2e-3

@@ -1,0 +1,177 @@
+"""GPU parity, hot path 1: csrc/tmpl_ll.cu through the C ABI vs the oracle and the reference's golden vectors.
+
+Tolerances: rel <= 1e-5 on log-likelihoods, rel <= 1e-4 on gradients (max-norm relative vs the fp64 oracle).  Pose
+gradients are the documented exception: bilinear floor() makes them discontinuous, the
+reference's own fp32-vs-fp64 pose gradients differ by 3.7e-3 max-norm, so they are checked norm-wise (relative L2)
+and by the fraction of elements within 1e-4.
+"""
+import pytest
+import torch
+
+from conftest import l2_rel_err, load_golden, rel_err, sub
+from gpu_util import DEV, make_template_inputs, template_cuda, template_oracle
+from test_oracle_golden import DECODER
+
+pytestmark = pytest.mark.gpu
+TOL_LL, TOL_GRAD = 1e-5, 1e-4
+POSE_L2, POSE_FRAC = 2e-3, 0.97
+
+
+def _f32(d):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v.float().double()
+        elif isinstance(v, dict):
+            out[k] = {kk: vv.float().double() for kk, vv in v.items()}
+        else:
+            out[k] = v
+    return out
+
+
+def check_pose_grad(got, ref, ctx):
+    got, ref = got.double().cpu(), ref.double()
+    l2 = l2_rel_err(got, ref)
+    frac = float(((got - ref).abs() <= 1e-4 * ref.abs().max()).double().mean())
+    assert l2 < POSE_L2 and frac >= POSE_FRAC, (ctx, 'g_pose', l2, frac)
+
+
+def _compare(got, ref, ctx):
+    assert rel_err(got['log_prob'], ref['log_prob']) < TOL_LL, ctx
+    if 'll' in got:
+        assert rel_err(got['ll'], ref['log_prob'].flatten(1).sum(1)) < TOL_LL, ctx
+    for k in ref:
+        if not k.startswith('g_') or k == 'g_pose':
+            continue
+        r = ref[k].reshape(got[k].shape)
+        if float(r.abs().max()) == 0.0:
+            assert float(got[k].abs().max()) == 0.0, (ctx, k)
+        else:
+            e = rel_err(got[k], r)
+            assert e < TOL_GRAD, (ctx, k, e)
+    check_pose_grad(got['g_pose'], ref['g_pose'], ctx)
+
+
+CONFIGS = [
+    # B, M, C, h, w, H, W, alpha            (1-3: MNIST cfg; 4: likelihood stress; 5: colour)
+    (6, 40, 1, 11, 11, 40, 40, True),
+    (3, 64, 1, 21, 21, 64, 64, True),
+    (4, 24, 3, 11, 11, 32, 32, True),
+    (4, 24, 3, 11, 11, 32, 32, False),
+    (3, 40, 1, 11, 11, 28, 28, True),      # the reference tests' 28x28 images
+    (2, 5, 2, 7, 9, 12, 10, False),        # non-square, C=2
+    (2, 3, 1, 5, 5, 70, 9, True),          # several row tiles
+    (2, 3, 1, 5, 5, 9, 70, False),         # several column tiles
+    (1, 1, 1, 1, 1, 1, 1, True),           # degenerate sizes
+]
+
+
+@pytest.mark.parametrize('cfg', CONFIGS)
+def test_kernel_vs_fp64_oracle(cfg):
+    B, M, C, h, w, H, W, alpha = cfg
+    d = _f32(make_template_inputs(B, M, C, h, w, H, W, alpha=alpha, seed=sum(cfg[:7])))
+    _compare(template_cuda(d), template_oracle(d), cfg)
+
+
+@pytest.mark.parametrize('alpha', [True, False])
+@pytest.mark.parametrize('presence,bg_image,learn_scale', [(False, False, False), (True, True, True),
+                                                           (False, True, False), (True, False, True)])
+def test_optional_inputs(alpha, presence, bg_image, learn_scale):
+    d = _f32(make_template_inputs(3, 6, 3, 6, 4, 11, 13, alpha=alpha, presence=presence, bg_image=bg_image,
+                                  learn_scale=learn_scale, seed=5))
+    _compare(template_cuda(d), template_oracle(d), (alpha, presence, bg_image, learn_scale))
+
+
+def _decoder_from_golden(case):
+    from golden.cases import DECODER_CASES
+    from torch_scae_b200.part_decoder import TemplateBasedImageDecoder
+    c = DECODER_CASES[case]
+    g = load_golden('decoder_' + case)
+    dec = TemplateBasedImageDecoder(c['M'], c['tsize'], c['osize'], learn_output_scale=c['learn_scale'],
+                                    use_alpha_channel=c['alpha'], background_value=c['bg_value'])
+    dec.load_state_dict(sub(g, 'param.'), strict=True)
+    return dec.to(DEV), g
+
+
+@pytest.mark.parametrize('case', DECODER)
+def test_module_vs_reference_golden(case):
+    dec, g = _decoder_from_golden(case)
+    leaf = {k: g[k].to(DEV).requires_grad_(True) for k in ('templates', 'pose', 'presence', 'bg_image') if k in g}
+    res = dec(leaf['templates'], leaf['pose'], leaf.get('presence'), leaf.get('bg_image'))
+    lp = res.pdf.log_prob(g['x'].to(DEV))
+    assert rel_err(lp, g['log_prob']) < TOL_LL
+    (lp * g['weight'].to(DEV)).sum().backward()
+    assert rel_err(leaf['templates'].grad, g['g_templates']) < TOL_GRAD
+    check_pose_grad(leaf['pose'].grad, g['g_pose'], case)
+    for k in ('presence', 'bg_image'):
+        if k in leaf:
+            assert rel_err(leaf[k].grad, g['g_' + k]) < TOL_GRAD, k
+    for k, p in dec.named_parameters():
+        ref = g['g_param.' + k]
+        if float(ref.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert rel_err(p.grad, ref) < TOL_GRAD, k
+
+
+@pytest.mark.parametrize('case', DECODER)
+def test_render_vs_reference_golden(case):
+    """transformed_templates / mixing_logits / mode / mean materialised by the render kernel (no-grad path)."""
+    dec, g = _decoder_from_golden(case)
+    with torch.no_grad():
+        args = [g[k].to(DEV) if k in g else None for k in ('templates', 'pose', 'presence', 'bg_image')]
+        res = dec(*args)
+        assert res.transformed_templates.shape == g['transformed_templates'].shape      # (B, M+1, C, H, W)
+        assert rel_err(res.transformed_templates, g['transformed_templates']) < TOL_LL
+        assert rel_err(res.mixing_logits, g['mixing_logits']) < TOL_LL
+        assert rel_err(res.pdf.mixing_log_prob(), g['mixing_log_prob']) < TOL_LL
+        fresh = dec(*args).pdf                          # point estimates straight from the kernel
+        assert rel_err(fresh.mean(), g['mean']) < TOL_LL
+        assert rel_err(fresh.mode(), g['mode']) < TOL_LL
+        if 'mode_maximum' in g:
+            assert rel_err(dec(*args).pdf.mode(maximum=True), g['mode_maximum']) < TOL_LL
+        assert res.pdf.n_components == g['transformed_templates'].shape[1]
+
+
+def test_gradient_through_materialised_tensors():
+    """recon_mse_weight > 0 differentiates through pdf.mode(): served by differentiable torch ops, off the hot path"""
+    dec, g = _decoder_from_golden('alpha_c1')
+    t = g['templates'].to(DEV).requires_grad_(True)
+    res = dec(t, g['pose'].to(DEV), g['presence'].to(DEV))
+    ((g['x'].to(DEV) - res.pdf.mode()) ** 2).sum().backward()
+    assert t.grad is not None and float(t.grad.abs().max()) > 0
+
+
+def test_missing_background_raises_like_reference():
+    from torch_scae_b200.part_decoder import TemplateBasedImageDecoder
+    dec = TemplateBasedImageDecoder(3, (5, 5), (8, 8), use_alpha_channel=True, background_value=False).to(DEV)
+    res = dec(torch.rand(2, 3, 1, 5, 5, device=DEV), torch.rand(2, 3, 6, device=DEV))
+    with pytest.raises(AttributeError):             # part_decoder.py:192 reads self.bg_value
+        res.pdf.log_prob(torch.rand(2, 1, 8, 8, device=DEV))
+
+
+def test_full_size_properties():
+    """BASELINE config 2 (B=1024, MNIST shapes): size-independent properties."""
+    B, M, C, h, w, H, W = 1024, 40, 1, 11, 11, 40, 40
+    d = make_template_inputs(B, M, C, h, w, H, W, alpha=True, seed=1, dtype=torch.float32)
+    a = template_cuda(d)
+    b = template_cuda(d)
+    for k in a:                                              # deterministic
+        assert torch.equal(a[k], b[k]), k
+    assert rel_err(a['ll'], a['log_prob'].flatten(1).sum(1)) < 1e-5
+    # a mixture density integrates to one: log_prob <= log N(0|0, sigma=1) everywhere
+    assert float(a['log_prob'].max()) <= -0.9189385 + 1e-5
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    dp = dict(d)
+    for k in ('templates', 'pose', 'presence', 'x', 'weight'):
+        dp[k] = d[k][perm]
+    p = template_cuda(dp)
+    for k in ('log_prob', 'g_templates', 'g_pose', 'g_presence'):
+        assert torch.equal(p[k], a[k][perm.to(a[k].device)]), k
+    d2 = dict(d)
+    d2['weight'] = 2 * d['weight']
+    c = template_cuda(d2)
+    assert rel_err(c['g_templates'], 2 * a['g_templates']) < 1e-6
+    assert rel_err(c['g_templates_alpha'], 2 * a['g_templates_alpha']) < 1e-5
+    # templates with zero presence get no template gradient and -inf-like logits do not produce NaNs
+    assert bool(torch.isfinite(a['g_templates']).all()) and bool(torch.isfinite(a['g_pose']).all())
