@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""SCAE train-step benchmark on synthetic MNIST-shaped data (BASELINE.json metric: train images/sec; likelihood-kernel
+achieved GB/s vs the measured HBM peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's fused sm_100a path
+    python bench.py --impl reference [--steps K] [--warmup W]        # the reference's CPU path (oracle port), host cores
+
+A "step" = forward + SCAE.loss + backward + (gradient all-reduce) + RMSprop update on one batch of 1024 images per GPU
+(BASELINE.json configs[1]; weak scaling: 8 GPUs = configs[2]'s global batch 8192).  Timing: CUDA events on the
+launching stream bracketed by barrier + synchronize, max over ranks.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'scae_train_images_per_sec'
+UNIT = 'images/s'
+
+
+def model_params(n_obj_caps):
+    """MNIST SCAE default = the reference's configs/model/mnist.yaml (reconstruct_alternatives: false)."""
+    return dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=n_obj_caps,
+                scae_params=dict(reconstruct_alternatives=False))
+
+
+def workload_name(n_obj_caps, batch):
+    return (f'MNIST SCAE default (mnist.yaml: 1x40x40, 40 part caps, {n_obj_caps} obj caps, 11x11 templates), '
+            f'batch {batch} per GPU, fwd+loss+bwd+RMSprop, synthetic data')
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# algorithmic HBM bytes per image (SURVEY.md section 8d / DESIGN.md section 5)
+# ---------------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(M=40, C=1, h=11, w=11, H=40, W=40, O=32):
+    V, A = M, 8 * M + 7
+    tmpl_in = 4 * (M * C * h * w + 6 * M + M + C * H * W)                 # templates, pose, presence, x
+    f1 = tmpl_in + 4 * C * H * W + 4 * 2 * C * H * W + 4                  # + log_prob, lse cache, ll
+    b1 = tmpl_in + 4 * C * H * W + 4 * 2 * C * H * W + 4 * (M * C * h * w + 7 * M)   # + grad_out, cache, g_templates/pose/presence
+    caps_in = 4 * O * A + 4 * O * (V + 1) + 4 * 7 * V                     # all_param, noises, x + presence
+    # API-complete forward: every tensor of the reference's result dict
+    f2 = caps_in + 4 * (O * V * (6 + 7) + 2 * (O + 1) * V + 2 * O + O + V * (6 + 1 + 6 + 1 + 1) + 2) + 8 * 2 * V
+    # backward: inputs + saved posterior/lse + upstream (posterior, caps_presence, ll, reg) + g_all_param (written by the
+    # kernel, re-read and re-written by the finalisation pass)
+    b2 = caps_in + 4 * (O * V + V) + 4 * (O * V + O + 2) + 4 * O * A * 3
+    return dict(scae_tmpl_ll_fwd=f1, scae_tmpl_ll_bwd=b1, scae_caps_ll_fwd=f2, scae_caps_ll_bwd=b2)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampling
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.FIELDS}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(',')]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None,
+                    sm_max_mhz=int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                    reasons=reasons, samples=len(self.samples))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_train_throughput(n_obj_caps, batch, steps, warmup, threads=None):
+    """images/s of fwd + loss + bwd + RMSprop of the oracle port (reference op sequence, per-capsule MLP loops,
+    materialised B x K x H x W tensors) on the host CPU."""
+    from oracle import scae_model
+    from torch_scae_b200 import factory
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    params = model_params(n_obj_caps)
+    cfg = factory.prepare_model_params(**params)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point())
+          for k, v in factory.make_scae(params).state_dict().items()}
+    leaves = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.RMSprop(leaves, lr=3e-5, momentum=0.9, eps=1e-2 / float(batch) ** 2)
+    image = torch.rand(batch, 1, 40, 40)
+    label = torch.randint(0, 10, (batch,))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        res = scae_model.scae_forward(sd, cfg, image, None, training=True)
+        loss, _ = scae_model.scae_loss(res, cfg, image, label)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * len(times) / total, 1000.0 * total / len(times), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = args.cpu_batch
+    steps = args.steps if args.steps else 10
+    warmup = args.warmup if args.warmup is not None else 3
+    steps = min(steps, 20)
+    warmup = min(warmup, 3)
+    value, ms, threads = cpu_train_throughput(args.n_obj_caps, batch, steps, warmup)
+    sample = (f'{steps} timed steps of batch {batch} (bounded sample of the batch-{args.batch} workload; CPU throughput '
+              f'is batch-size independent, SURVEY.md section 6) after {warmup} warm-ups')
+    line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, impl='reference', n_gpus=args.gpus, steps=steps,
+                warmup=warmup, ms_per_step=round(ms, 3), higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='fp32', data='synthetic',
+                config=dict(workload=workload_name(args.n_obj_caps, args.batch), n_obj_caps=args.n_obj_caps,
+                            batch_per_step=batch),
+                cpu_baseline=dict(value=round(value, 2), unit=UNIT, cores=threads, kind='port', sample=sample),
+                e2e=dict(value=round(value, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch.distributed as dist
+    from torch_scae_b200 import ddp, factory, ops
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the fused path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    # strict fp32 everywhere (no TF32 in the cuDNN / cuBLAS parts of the step)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+
+    B = args.batch
+    steps = args.steps if args.steps else 50
+    warmup = max(3, args.warmup if args.warmup is not None else 10)
+    torch.manual_seed(42)                                   # identical initial weights on every rank
+    model = factory.make_scae(model_params(args.n_obj_caps)).to(dev).train()
+    ddp.broadcast_parameters(model)
+    bucket = ddp.FlatGradBucket(model)
+    opt = torch.optim.RMSprop(model.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2, foreach=True)
+    torch.manual_seed(42 + rank)                            # different synthetic shard per rank
+    host_image = torch.rand(B, 1, 40, 40).pin_memory()
+    host_label = torch.randint(0, 10, (B,)).pin_memory()
+    image, label = host_image.to(dev), host_label.to(dev)
+    host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step(img, lab):
+        bucket.zero()
+        res = model(img)
+        loss, _ = model.loss(res, img, lab)
+        loss.backward()
+        bucket.all_reduce_mean()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(n):
+            fn()
+        end.record()
+        barrier()
+        ms = torch.tensor([start.elapsed_time(end)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+
+    for _ in range(warmup):
+        step(image, label)
+    assert bucket.check_views(), 'gradient views were replaced; flat bucket all-reduce would be stale'
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # (1) device-resident throughput, with per-entry-point kernel timing
+    with ops.KernelTimer() as timer:
+        ms_step = timed(lambda: step(image, label), steps)
+    kstats = timer.summary()
+
+    # (2) end to end: pinned host batch -> device every step, loss read back to the host every step
+    def e2e_step():
+        img = host_image.to(dev, non_blocking=True)
+        lab = host_label.to(dev, non_blocking=True)
+        loss = step(img, lab)
+        host_loss.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()           # the user reads the loss every step
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, steps)
+    clocks = sampler.summary() if rank == 0 else None
+
+    # (3) O=10 variant (BASELINE.json's parenthetical) for the record, short run
+    extra = {}
+    if rank == 0 and not args.no_extra and world == 1:
+        del opt, bucket
+        m2 = factory.make_scae(model_params(10)).to(dev).train()
+        b2 = ddp.FlatGradBucket(m2)
+        o2 = torch.optim.RMSprop(m2.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2, foreach=True)
+
+        def step2():
+            b2.zero()
+            r = m2(image)
+            l, _ = m2.loss(r, image, label)
+            l.backward()
+            o2.step()
+        for _ in range(5):
+            step2()
+        ms2 = timed(step2, max(10, steps // 2))
+        extra['n_obj_caps_10'] = dict(value=round(B * 1000.0 / ms2, 1), unit=UNIT, ms_per_step=round(ms2, 3))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    bytes_per_image = algorithmic_bytes(O=args.n_obj_caps)
+    kernels = {}
+    launches = 0
+    for name, (calls, n_launch, total_ms) in kstats.items():
+        avg_ms = total_ms / calls
+        gbs = bytes_per_image[name] * B / (avg_ms * 1e-3) / 1e9
+        kernels[name] = dict(ms=round(avg_ms, 4), launches_per_call=n_launch // calls,
+                             algorithmic_bytes=bytes_per_image[name] * B, achieved_gbs=round(gbs, 1),
+                             frac_of_hbm_peak=round(gbs / peak, 4), share_of_step=round(avg_ms / ms_step, 4))
+        launches += n_launch
+    dominant = max(kernels, key=lambda k: kernels[k]['ms'])
+    traffic = ncu_traffic().get(dominant)
+    roofline = dict(kernel=dominant, bound='hbm', achieved=kernels[dominant]['achieved_gbs'], peak=peak, unit='GB/s',
+                    frac=kernels[dominant]['frac_of_hbm_peak'], traffic=traffic, peak_source=peak_src,
+                    note='path-1 kernels are fp32-issue / shared-memory bound by construction (the B x K x H x W tensor '
+                         'is never written); see DESIGN.md section 5 and the `kernels` object for all four entry points')
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, ms_cpu, threads = cpu_train_throughput(args.n_obj_caps, args.cpu_batch, 12, 2)
+        cpu = dict(value=round(v, 2), unit=UNIT, cores=threads, kind='port',
+                   sample=f'12 timed steps of batch {args.cpu_batch} (fwd+loss+bwd+RMSprop) after 2 warm-ups, '
+                          f'{ms_cpu:.0f} ms/step; oracle port of the reference op sequence on the host CPU')
+
+    value = B * world * 1000.0 / ms_step
+    e2e_value = B * world * 1000.0 / ms_e2e
+    line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
+                ms_per_step=round(ms_step, 4), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
+                data='synthetic',
+                config=dict(workload=workload_name(args.n_obj_caps, B), n_obj_caps=args.n_obj_caps,
+                            global_batch=B * world, parallelism=f'dp{world}', tf32=False,
+                            l2_policy='per-step working set (>190 MB of activations per 1024 images) exceeds the 126 MB L2',
+                            note="BASELINE.json's parenthetical says 10 obj caps; the reference's mnist.yaml:4 says 32 "
+                                 "(used here); the 10-capsule variant is under extra.n_obj_caps_10"),
+                e2e=dict(value=round(e2e_value, 1), unit=UNIT, ms_per_step=round(ms_e2e, 4),
+                         h2d_bytes_per_step=int(host_image.numel() * 4 + host_label.numel() * 8) * world,
+                         d2h_bytes_per_step=4 * world),
+                gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu, clocks=clocks, extra=extra)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='images per GPU per step')
+    ap.add_argument('--n-obj-caps', type=int, default=32)
+    ap.add_argument('--cpu-batch', type=int, default=128, help='batch of the bounded CPU sample (BASELINE configs[0])')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -88,7 +88,7 @@ def make_capsule_inputs(B, O, V, *, presence=True, noise=True, seed=0, dtype=tor
              biases=[0.1 * n(1, O, 1, 6), 0.1 * n(1, O, 1), 0.1 * n(1, O, V), 0.1 * n(1, O, V)],
              dummy_vote=0.1 * n(1, 1, V, 6), x=pose_to_affine(0.5 * n(B, V, 6)))
     d['presence'] = r(B, V) if presence else None
-    if presence:
+    if presence and B * V > 1:
         d['presence'].view(-1)[1] = 0.0
     d['noise_caps'] = (r(B, O, 1) - .5) * 4 if noise else None
     d['noise_vote'] = (r(B, O, V) - .5) * 4 if noise else None

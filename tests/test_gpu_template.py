@@ -29,14 +29,19 @@ def _f32(d):
     return out
 
 
-def check_pose_grad(got, ref, ctx):
+def check_pose_grad(got, ref, ctx, ref_fp32=None):
+    """Pose gradients: within 1e-4 max-norm, or -- where bilinear cell flips dominate -- no worse than the reference's
+    own fp32 (ATen) deviation from fp64 on the same inputs (`ref_fp32`), or the absolute floor measured in the survey."""
     got, ref = got.double().cpu(), ref.double()
+    if rel_err(got, ref) < TOL_GRAD:
+        return
     l2 = l2_rel_err(got, ref)
     frac = float(((got - ref).abs() <= 1e-4 * ref.abs().max()).double().mean())
-    assert l2 < POSE_L2 and frac >= POSE_FRAC, (ctx, 'g_pose', l2, frac)
+    floor = POSE_L2 if ref_fp32 is None else 1.25 * l2_rel_err(ref_fp32.double(), ref) + 1e-4
+    assert l2 < floor and frac >= POSE_FRAC, (ctx, 'g_pose', l2, floor, frac)
 
 
-def _compare(got, ref, ctx):
+def _compare(got, ref, ctx, ref_fp32=None):
     assert rel_err(got['log_prob'], ref['log_prob']) < TOL_LL, ctx
     if 'll' in got:
         assert rel_err(got['ll'], ref['log_prob'].flatten(1).sum(1)) < TOL_LL, ctx
@@ -49,7 +54,7 @@ def _compare(got, ref, ctx):
         else:
             e = rel_err(got[k], r)
             assert e < TOL_GRAD, (ctx, k, e)
-    check_pose_grad(got['g_pose'], ref['g_pose'], ctx)
+    check_pose_grad(got['g_pose'], ref['g_pose'], ctx, None if ref_fp32 is None else ref_fp32['g_pose'])
 
 
 CONFIGS = [
@@ -70,7 +75,7 @@ CONFIGS = [
 def test_kernel_vs_fp64_oracle(cfg):
     B, M, C, h, w, H, W, alpha = cfg
     d = _f32(make_template_inputs(B, M, C, h, w, H, W, alpha=alpha, seed=sum(cfg[:7])))
-    _compare(template_cuda(d), template_oracle(d), cfg)
+    _compare(template_cuda(d), template_oracle(d), cfg, template_oracle(d, torch.float32))
 
 
 @pytest.mark.parametrize('alpha', [True, False])
@@ -79,7 +84,8 @@ def test_kernel_vs_fp64_oracle(cfg):
 def test_optional_inputs(alpha, presence, bg_image, learn_scale):
     d = _f32(make_template_inputs(3, 6, 3, 6, 4, 11, 13, alpha=alpha, presence=presence, bg_image=bg_image,
                                   learn_scale=learn_scale, seed=5))
-    _compare(template_cuda(d), template_oracle(d), (alpha, presence, bg_image, learn_scale))
+    _compare(template_cuda(d), template_oracle(d), (alpha, presence, bg_image, learn_scale),
+             template_oracle(d, torch.float32))
 
 
 def _decoder_from_golden(case):
@@ -134,12 +140,18 @@ def test_render_vs_reference_golden(case):
 
 
 def test_gradient_through_materialised_tensors():
-    """recon_mse_weight > 0 differentiates through pdf.mode(): served by differentiable torch ops, off the hot path"""
+    """Gradients *through the materialised tensors* (pdf.mean(), pdf.mode() when recon_mse_weight > 0) are served by
+    differentiable torch CUDA ops, off the hot path; they must agree with the oracle."""
+    from oracle import template_likelihood as tl
     dec, g = _decoder_from_golden('alpha_c1')
     t = g['templates'].to(DEV).requires_grad_(True)
     res = dec(t, g['pose'].to(DEV), g['presence'].to(DEV))
-    ((g['x'].to(DEV) - res.pdf.mode()) ** 2).sum().backward()
-    assert t.grad is not None and float(t.grad.abs().max()) > 0
+    ((g['x'].to(DEV) - res.pdf.mean()) ** 2).sum().backward()
+    t64 = g['templates'].double().requires_grad_(True)
+    params = {k: v.double() for k, v in sub(g, 'param.').items()}
+    loc, sigma, logits = tl.decode(t64, g['pose'].double(), g['x'].shape[-2:], g['presence'].double(), None, **params)
+    ((g['x'].double() - tl.mixture_mean(loc, logits)) ** 2).sum().backward()
+    assert rel_err(t.grad, t64.grad) < TOL_GRAD
 
 
 def test_missing_background_raises_like_reference():

@@ -16,6 +16,45 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class KernelTimer:
+    """Optional per-entry-point device timing (CUDA events on the launching stream) and launch counting.
+
+    ``with ops.KernelTimer() as t: ...`` records an event pair around every C-ABI call made inside the block;
+    ``t.summary()`` (after a synchronize) returns {entry point: (calls, kernel launches, total ms)}.  bench.py uses
+    it for the roofline numbers; it is off (zero overhead) otherwise.
+    """
+    active = None
+
+    def __init__(self):
+        self.records = {}
+
+    def __enter__(self):
+        KernelTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        KernelTimer.active = None
+
+    def summary(self):
+        out = {}
+        for name, recs in self.records.items():
+            out[name] = (len(recs), sum(r[2] for r in recs), sum(r[0].elapsed_time(r[1]) for r in recs))
+        return out
+
+
+def _timed(name, launches, fn, *args):
+    """Calls a C-ABI entry point, bracketing it with CUDA events when a KernelTimer is active."""
+    t = KernelTimer.active
+    if t is None:
+        return fn(*args)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    rc = fn(*args)
+    end.record()
+    t.records.setdefault(name, []).append((start, end, launches))
+    return rc
+
+
 def _f32c(t):
     """contiguous fp32 CUDA tensor (no copy when it already is one); None passes through."""
     if t is None:
@@ -69,8 +108,8 @@ class TemplateMixtureLogProb(torch.autograd.Function):
         log_prob = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
         ll = torch.empty(B, device=x.device, dtype=torch.float32)
         cache = torch.empty(B, 2, C, H, W, device=x.device, dtype=torch.float32)
-        check(lib.scae_tmpl_ll_fwd(ctypes.byref(args), ptr(x), ptr(log_prob), ptr(ll), ptr(cache), _stream()),
-              'scae_tmpl_ll_fwd')
+        check(_timed('scae_tmpl_ll_fwd', 1, lib.scae_tmpl_ll_fwd, ctypes.byref(args), ptr(x), ptr(log_prob), ptr(ll),
+                     ptr(cache), _stream()), 'scae_tmpl_ll_fwd')
         ctx.save_for_backward(*[t for t in tensors if t is not None], cache)
         ctx.present = [t is not None for t in tensors]
         ctx.output_size = (H, W)
@@ -106,9 +145,10 @@ class TemplateMixtureLogProb(torch.autograd.Function):
         g_scalars = torch.empty(4, device=dev, dtype=torch.float32)
         ws_bytes = lib.scae_tmpl_ll_bwd_workspace_bytes(ctypes.byref(args))
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
-        check(lib.scae_tmpl_ll_bwd(ctypes.byref(args), ptr(x), ptr(g), ptr(cache), ptr(g_templates), ptr(g_pose),
-                                   ptr(g_presence), ptr(g_bg_image), ptr(g_alpha), ptr(g_scalars), ptr(ws), ws_bytes,
-                                   _stream()), 'scae_tmpl_ll_bwd')
+        # kernel launches: the backward kernel + the partial-sum reductions (alpha gradient, scalar gradients)
+        check(_timed('scae_tmpl_ll_bwd', 3 if g_alpha is not None else 2, lib.scae_tmpl_ll_bwd, ctypes.byref(args),
+                     ptr(x), ptr(g), ptr(cache), ptr(g_templates), ptr(g_pose), ptr(g_presence), ptr(g_bg_image),
+                     ptr(g_alpha), ptr(g_scalars), ptr(ws), ws_bytes, _stream()), 'scae_tmpl_ll_bwd')
 
         def scalar(i, p):
             return g_scalars[i:i + 1].reshape(p.shape) if p is not None else None
@@ -186,7 +226,8 @@ class CapsuleVoteLikelihood(torch.autograd.Function):
         args = _caps_args(all_param, cpr_static, (b0, b1, b2, b3), noise_caps, noise_vote, x, presence, dummy_vote,
                           flags)
         outs = CapsOutputs(*[ptr(out[k]) for k in CAPS_OUTPUT_FIELDS])
-        check(lib.scae_caps_ll_fwd(ctypes.byref(args), ctypes.byref(outs), _stream()), 'scae_caps_ll_fwd')
+        check(_timed('scae_caps_ll_fwd', 1, lib.scae_caps_ll_fwd, ctypes.byref(args), ctypes.byref(outs), _stream()),
+              'scae_caps_ll_fwd')
         inputs = (all_param, cpr_static, b0, b1, b2, b3, dummy_vote, x, presence, noise_caps, noise_vote)
         ctx.present = [t is not None for t in inputs]
         ctx.save_for_backward(*[t for t in inputs if t is not None], out['posterior_mixing_prob'],
@@ -222,9 +263,10 @@ class CapsuleVoteLikelihood(torch.autograd.Function):
         g_presence = torch.empty_like(presence) if presence is not None and ctx.needs_input_grad[8] else None
         ws_bytes = lib.scae_caps_ll_bwd_workspace_bytes(ctypes.byref(args))
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
-        check(lib.scae_caps_ll_bwd(ctypes.byref(args), ctypes.byref(sv), ctypes.byref(up), ptr(g_all), ptr(g_shared),
-                                   ptr(g_dummy), ptr(g_x), ptr(g_presence), ptr(ws), ws_bytes, _stream()),
-              'scae_caps_ll_bwd')
+        # kernel launches: backward kernel + finalize + reduction of the shared-parameter partials (+ dummy-vote sum)
+        check(_timed('scae_caps_ll_bwd', 3 + (1 if g_dummy is not None else 0), lib.scae_caps_ll_bwd,
+                     ctypes.byref(args), ctypes.byref(sv), ctypes.byref(up), ptr(g_all), ptr(g_shared), ptr(g_dummy),
+                     ptr(g_x), ptr(g_presence), ptr(ws), ws_bytes, _stream()), 'scae_caps_ll_bwd')
         g_static = g_shared[:, :6 * V].reshape(cpr_static.shape)
         g_b0 = g_shared[:, 6 * V:6 * V + 6].reshape(b0.shape)
         g_b1 = g_shared[:, 6 * V + 6].reshape(b1.shape)
