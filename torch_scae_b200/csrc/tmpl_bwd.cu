@@ -279,54 +279,57 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_ll_bwd_gather_kernel(con
           const float* t8 = s.tp + (size_t)(m0 + mm) * 8;
           const float Ax = t8[0], Bx = t8[1], Cx = t8[2], Ay = t8[3], By = t8[4], Cy = t8[5];
           const float txa = (float)(txi + 2), tya = (float)(tyi + 2);
-          // rows of the image that can see this texel: invert [tx; ty] = [Ax Bx; Ay By][X; Y] + [Cx; Cy]
+          // Footprint of this texel in the image: invert [tx; ty] = [Ax Bx; Ay By][X; Y] + [Cx; Cy] around the texel
+          // (half-width 1 texel per axis) to get a bounding box in normalised image coordinates.  Texels whose box
+          // misses the image are skipped outright; the others get their row range from it.
           int i_lo = 0, i_hi = a.H - 1;
+          bool visible = true;
           const float det = Ax * By - Bx * Ay;
           if (fabsf(det) > 1e-20f) {
-            const float inv = 1.0f / det;
-            const float Yc = (Ax * (tya - Cy) - Ay * (txa - Cx)) * inv;
-            const float hy = (fabsf(Ay) + fabsf(Ax)) * fabsf(inv);
-            if (fabsf(Yc) <= 1e6f && hy <= 1e6f) {
+            const float inv = 1.0f / det, ainv = fabsf(inv);
+            const float dx = txa - Cx, dy = tya - Cy;
+            const float Xc = (By * dx - Bx * dy) * inv, Yc = (Ax * dy - Ay * dx) * inv;
+            const float hx = (fabsf(By) + fabsf(Bx)) * ainv, hy = (fabsf(Ay) + fabsf(Ax)) * ainv;
+            if (fabsf(Xc) <= 1e6f && fabsf(Yc) <= 1e6f && hx <= 1e6f && hy <= 1e6f) {   // also false for NaN
+              const float mx = 2.0f / fW, my = 2.0f / fH;                                // one pixel of slack
+              visible = (Xc - hx <= 1.0f + mx) && (Xc + hx >= -1.0f - mx) && (Yc - hy <= 1.0f + my) &&
+                        (Yc + hy >= -1.0f - my);
+              // row index of Y: i = ((Y + 1) H - 1) / 2
               const float flo = ((Yc - hy + 1.0f) * fH - 1.0f) * 0.5f - 1.0f;
               const float fhi = ((Yc + hy + 1.0f) * fH - 1.0f) * 0.5f + 1.0f;
               i_lo = max(0, (int)floorf(fminf(fmaxf(flo, -2.0f), fH + 1.0f)));
               i_hi = min(a.H - 1, (int)ceilf(fminf(fmaxf(fhi, -2.0f), fH + 1.0f)));
             }
           }
-          const bool has_x = fabsf(Ax) > 1e-12f, has_y = fabsf(Ay) > 1e-12f;
-          const float rAx = has_x ? 1.0f / Ax : 0.0f, rAy = has_y ? 1.0f / Ay : 0.0f;
-          const float* gslot = gbuf + (size_t)mm * HW * kPad;
-          for (int i = i_lo + sub; i <= i_hi; i += R) {
-            const float Yi = s.ys[i];
-            const float cxr = fmaf(Yi, Bx, Cx), cyr = fmaf(Yi, By, Cy);
-            // columns with |Ax X + cxr - txa| < 1 and |Ay X + cyr - tya| < 1, as an interval of X
-            float lo = -2.0f, hi = 2.0f;
-            if (has_x) {
-              const float p = (txa - 1.0f - cxr) * rAx, q = (txa + 1.0f - cxr) * rAx;
-              lo = fmaxf(lo, fminf(p, q));
-              hi = fminf(hi, fmaxf(p, q));
-            } else if (!(fabsf(cxr - txa) < 1.0f)) {
-              hi = -3.0f;
-            }
-            if (has_y) {
-              const float p = (tya - 1.0f - cyr) * rAy, q = (tya + 1.0f - cyr) * rAy;
-              lo = fmaxf(lo, fminf(p, q));
-              hi = fminf(hi, fmaxf(p, q));
-            } else if (!(fabsf(cyr - tya) < 1.0f)) {
-              hi = -3.0f;
-            }
-            if (!(hi >= lo)) continue;
-            const int j_lo = max(0, (int)floorf(((lo + 1.0f) * fW - 1.0f) * 0.5f) - 1);
-            const int j_hi = min(a.W - 1, (int)ceilf(((hi + 1.0f) * fW - 1.0f) * 0.5f) + 1);
-            const float* grow = gslot + (size_t)i * a.W * kPad;
-            for (int j = j_lo; j <= j_hi; ++j) {
-              const float Xj = s.xs[j];
-              const float wx = 1.0f - fabsf(fmaf(Xj, Ax, cxr) - txa);
-              const float wy = 1.0f - fabsf(fmaf(Xj, Ay, cyr) - tya);
-              const float wgt = fmaxf(wx, 0.0f) * fmaxf(wy, 0.0f);
-              const Texel<kPad> gv = ld_texel<kPad>(grow + (size_t)j * kPad);
+          if (visible) {
+            // per row the admissible X form an interval: centre(Y) +- half-width from each axis that depends on X
+            const bool has_x = fabsf(Ax) > 1e-12f, has_y = fabsf(Ay) > 1e-12f;
+            const float rAx = has_x ? 1.0f / Ax : 0.0f, rAy = has_y ? 1.0f / Ay : 0.0f;
+            const float cx0 = (txa - Cx) * rAx, cxs = -Bx * rAx, hwx = has_x ? fabsf(rAx) : 4.0f;
+            const float cy0 = (tya - Cy) * rAy, cys = -By * rAy, hwy = has_y ? fabsf(rAy) : 4.0f;
+            const float jscale = 0.5f * fW, joff = 0.5f * fW - 0.5f;                     // j = X * W/2 + (W/2 - 1/2)
+            const float* gslot = gbuf + (size_t)mm * HW * kPad;
+            for (int i = i_lo + sub; i <= i_hi; i += R) {
+              const float Yi = s.ys[i];
+              const float cxr = fmaf(Yi, Bx, Cx), cyr = fmaf(Yi, By, Cy);
+              if (!has_x && !(fabsf(cxr - txa) < 1.0f)) continue;                        // row cannot see the texel
+              if (!has_y && !(fabsf(cyr - tya) < 1.0f)) continue;
+              const float mx_c = fmaf(Yi, cxs, cx0), my_c = fmaf(Yi, cys, cy0);
+              const float lo = fmaxf(fmaxf(mx_c - hwx, my_c - hwy), -2.0f);
+              const float hi = fminf(fminf(mx_c + hwx, my_c + hwy), 2.0f);
+              if (!(hi >= lo)) continue;
+              const int j_lo = max(0, (int)floorf(fmaf(lo, jscale, joff)) - 1);
+              const int j_hi = min(a.W - 1, (int)ceilf(fmaf(hi, jscale, joff)) + 1);
+              const float* grow = gslot + (size_t)i * a.W * kPad;
+              for (int j = j_lo; j <= j_hi; ++j) {
+                const float Xj = s.xs[j];
+                const float wx = 1.0f - fabsf(fmaf(Xj, Ax, cxr) - txa);
+                const float wy = 1.0f - fabsf(fmaf(Xj, Ay, cyr) - tya);
+                const float wgt = fmaxf(wx, 0.0f) * fmaxf(wy, 0.0f);
+                const Texel<kPad> gv = ld_texel<kPad>(grow + (size_t)j * kPad);
 #pragma unroll
-              for (int c = 0; c < kPad; ++c) av[c] = fmaf(wgt, gv.v[c], av[c]);
+                for (int c = 0; c < kPad; ++c) av[c] = fmaf(wgt, gv.v[c], av[c]);
+              }
             }
           }
         }

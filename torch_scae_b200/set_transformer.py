@@ -11,6 +11,16 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+def _layer_norm(x, ln):
+    """nn.LayerNorm's arithmetic with the affine part as plain elementwise ops.
+
+    For the tiny feature width used here (d=16) ATen's fused LayerNorm backward spends 0.24 ms per call in its
+    gamma/beta reduction kernel (profiles/r01a); normalising without affine parameters and applying weight/bias
+    separately gives the same values and lets the parameter gradients come from ordinary column reductions.
+    """
+    return F.layer_norm(x, ln.normalized_shape, None, None, ln.eps) * ln.weight + ln.bias
+
+
 def qkv_attention(queries, keys, values, presence=None):
     logits = torch.matmul(queries, keys.transpose(1, 2))
     if presence is not None:
@@ -69,10 +79,10 @@ class MAB(nn.Module):
             assert presence.shape[1] == queries.shape[1] == keys.shape[1]
             h = h * presence.unsqueeze(-1)
         if self.layer_norm:
-            h = self.ln0(h)
+            h = _layer_norm(h, self.ln0)
         h = h + F.relu(self.fc(h))
         if self.layer_norm:
-            h = self.ln1(h)
+            h = _layer_norm(h, self.ln1)
         return h
 
 
