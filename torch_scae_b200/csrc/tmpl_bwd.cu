@@ -9,12 +9,18 @@
 // The template / alpha gradient is a *transposed* bilinear interpolation.  Written as a scatter it needs 8 float
 // atomics on shared memory per (pixel, template); on sm_100a those are ATOMS.CAST spin loops and neighbouring pixels hit
 // the same texel (templates are magnified), which made the first version of this kernel 18x slower than the forward
-// pass.  The kernel below instead uses a GATHER: phase A (pixel-parallel) parks g_loc / g_logit of the current template
-// group in shared memory; phase B (texel-parallel) lets every texel walk its own footprint in the image -- the pixels
-// with |tx(pixel) - texel_x| < 1 and |ty(pixel) - texel_y| < 1, found by inverting the affine map -- and accumulate
-// hat(tx - texel_x) * hat(ty - texel_y) * g in registers.  hat() is continuous, so no per-pixel cell decision is needed,
-// there are no atomics, and the result is bit-reproducible.  The scatter variant is kept as a fallback for images whose
-// gradient buffer does not fit in shared memory (and for A/B testing: SCAE_TMPL_BWD=atomic).
+// pass (profiles/r01a).  Two atomics-free, bit-reproducible formulations are implemented:
+//
+//  * SCAN (default): one warp owns one (image, template) pair and walks the image row-major, 32 pixels per pass.
+//    Along a row the sampling coordinates move on a straight line, so the bilinear cell index is monotone: pixels that
+//    fall into the same cell are CONTIGUOUS lanes.  A segmented warp scan (shuffles) pre-reduces the four corner
+//    contributions per cell, and only the last lane of each segment does a plain read-modify-write on the warp's private
+//    gradient atlas in shared memory -- corner by corner and row by row, so no two lanes ever touch the same address in
+//    the same step and the summation order is fixed.  No CTA barriers, no gradient buffer, any image size.
+//  * GATHER (SCAE_TMPL_BWD=gather): phase A (pixel-parallel) parks g_loc / g_logit of a template group in shared
+//    memory; phase B (texel-parallel) lets every texel invert the affine map, walk its own footprint in the image and
+//    accumulate hat(tx - x) * hat(ty - y) * g in registers.  Kept for A/B testing (1.5 ms vs the scan's time at the
+//    MNIST config: the footprints of neighbouring texels differ too much for good SIMT efficiency).
 #include <stdlib.h>
 #include <string.h>
 
@@ -352,177 +358,263 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_ll_bwd_gather_kernel(con
 }
 
 // ================================================================================================================
-// scatter variant with shared-memory float atomics (fallback; non-deterministic summation order)
+// scan variant (default): warp per (image, template), segmented-scan scatter
 // ================================================================================================================
+constexpr int kScanThreads = 256;
+
 template <int C, bool kAlpha>
-__global__ void __launch_bounds__(kTmplThreads, 2) tmpl_ll_bwd_atomic_kernel(const scae_tmpl_args a,
-                                                                             const float* __restrict__ x,
-                                                                             const float* __restrict__ gout,
-                                                                             const float* __restrict__ cache,
-                                                                             const TmplBwdOut out, const TmplGeom g) {
+__global__ void __launch_bounds__(kScanThreads, 3) tmpl_ll_bwd_scan_kernel(const scae_tmpl_args a,
+                                                                           const float* __restrict__ x,
+                                                                           const float* __restrict__ gout,
+                                                                           const float* __restrict__ cache,
+                                                                           const TmplBwdOut out, const TmplGeom g) {
   using TT = TexTraits<C, kAlpha>;
-  constexpr int kPad = TT::kPad, PIX = TT::kPixMax;
+  constexpr int kPad = TT::kPad, NCH = TT::kCh;
   extern __shared__ __align__(16) float smem[];
-  const TmplSmem s = tmpl_carve(smem, a, g, g.atlas_floats);
-  float* gatlas = s.extra;
-  const int nwarps = (blockDim.x + 31) >> 5;
-  float* wpart = s.red + 64;
-  tmpl_prologue(s, a, g, g.atlas_floats);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int atlas_floats = g.atlas_floats;               // one padded template, multiple of 4 floats
+  float* atlas = smem + (size_t)warp * 2 * atlas_floats;  // this warp's value atlas
+  float* gatlas = atlas + atlas_floats;                   // ... and gradient atlas
+  float* red = smem + (size_t)nwarps * 2 * atlas_floats;  // [64] block-reduction scratch
+  float* xs = red + 64;                                   // [W] affine_grid base coordinates
+  float* ys = xs + a.W;                                   // [H]
+  for (int e = lane; e < 2 * atlas_floats; e += 32) atlas[e] = 0.0f;
+  for (int e = threadIdx.x; e < a.W; e += blockDim.x) xs[e] = base_coord(e, a.W);
+  for (int e = threadIdx.x; e < a.H; e += blockDim.x) ys[e] = base_coord(e, a.H);
   const TmplScalars sc = tmpl_scalars(a);
-  const int HW = a.H * a.W, hw = a.h * a.w;
-  const int col = threadIdx.x % g.tw, rg = threadIdx.x / g.tw;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool thread_ok = (int)threadIdx.x < g.tw * g.k;
+  const int HW = a.H * a.W, hw = a.h * a.w, pw = g.pw, ph = g.ph;
   const float lim_x = (float)a.w + 2.5f, lim_y = (float)a.h + 2.5f;
-  const unsigned row = (unsigned)(g.pw * kPad), tex_stride = (unsigned)(g.ph * g.pw * kPad);
+  const unsigned row = (unsigned)(pw * kPad);
   const unsigned base0 = 0u - kMagicBits * (row + (unsigned)kPad);
-  const float inv_w = 1.0f / (float)a.w, inv_hw = 1.0f / (float)hw;
+  const float hw_x = 0.5f * (float)a.w, hw_y = 0.5f * (float)a.h;
+  const float inv_pw = 1.0f / (float)pw;
   float* my_alpha_partial = (kAlpha && out.alpha_partials) ? out.alpha_partials + (size_t)blockIdx.x * a.M * hw : nullptr;
   if (my_alpha_partial)
     for (int e = threadIdx.x; e < a.M * hw; e += blockDim.x) my_alpha_partial[e] = 0.0f;
   ScalarAcc acc;
+  __syncthreads();   // partial row zeroed before any warp accumulates into it
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-    __syncthreads();
-    load_pose_table(s, a, b);
-    for (int m0 = 0; m0 < a.M; m0 += g.mc) {
-      const int mc = min(g.mc, a.M - m0);
-      __syncthreads();
-      stage_atlas<C, kAlpha>(s.atlas, a, b, m0, mc, g.pw, g.ph);
-      for (int e = threadIdx.x; e < nwarps * g.mc * 8; e += blockDim.x) wpart[e] = 0.0f;
-      __syncthreads();
-      for (int ty = 0; ty < g.tiles_y; ++ty) {
-        for (int tx = 0; tx < g.tiles_x; ++tx) {
-          const int j = tx * g.tw + col;
-          const bool col_ok = thread_ok && j < a.W;
-          const int row0 = ty * g.k * g.ppt + rg;
-          const float X = col_ok ? s.xs[j] : 0.0f;
-          float Y[PIX], xv[PIX][C], G[PIX][C], Nc[PIX][C], Dc[PIX][C];
+    // background component: once per pixel, by warp 0
+    if (warp == 0) {
+      for (int p = lane; p < HW; p += 32) {
+        float xv[C], G[C], Nc[C], Dc[C];
+        const size_t px0 = (size_t)b * C * HW + p;
 #pragma unroll
-          for (int u = 0; u < PIX; ++u) {
-            const int i = row0 + u * g.k;
-            const bool ok = col_ok && u < g.ppt && i < a.H;
-            Y[u] = ok ? s.ys[i] : 0.0f;
-            const size_t px0 = (size_t)b * C * HW + (size_t)i * a.W + j;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              const size_t px = px0 + (size_t)c * HW;
-              const size_t cx = (size_t)b * 2 * C * HW + (size_t)c * HW + (size_t)i * a.W + j;
-              xv[u][c] = ok ? __ldg(x + px) : 0.0f;
-              G[u][c] = ok ? __ldg(gout + px) : 0.0f;
-              Nc[u][c] = ok ? __ldg(cache + cx) : 0.0f;
-              Dc[u][c] = ok ? __ldg(cache + cx + (size_t)C * HW) : 0.0f;
-            }
-            if (m0 == 0 && ok) bwd_background<C, kAlpha>(a, sc, xv[u], G[u], Nc[u], Dc[u], px0, HW, out.g_bg_image, acc);
-          }
-          for (int mm = 0; mm < mc; ++mm) {
-            const float* t8 = s.tp + (size_t)(m0 + mm) * 8;
-            const float4 pa = *reinterpret_cast<const float4*>(t8);
-            const float4 pb = *reinterpret_cast<const float4*>(t8 + 4);
-            const float cx = fmaf(X, pa.x, pa.z), cy = fmaf(X, pa.w, pb.y);
-            const unsigned base = base0 + (unsigned)mm * tex_stride;
-            float sgx = 0.f, sgxy = 0.f, sgy = 0.f, sgyy = 0.f, spres = 0.f;
-#pragma unroll
-            for (int u = 0; u < PIX; ++u) {
-              if (u < g.ppt) {
-                Tap t;
-                tap_setup<kPad>(fmaf(Y[u], pa.y, cx), fmaf(Y[u], pb.x, cy), lim_x, lim_y, row, base, t);
-                const float* q = s.atlas + t.off;
-                const Texel<kPad> t00 = ld_texel<kPad>(q), t10 = ld_texel<kPad>(q + kPad);
-                const Texel<kPad> t01 = ld_texel<kPad>(q + row), t11 = ld_texel<kPad>(q + row + kPad);
-                float glp, gtx, gty;
-                const Texel<kPad> gv = bwd_pixel<C, kAlpha, kPad>(sc, t00, t10, t01, t11, t, pb.z, xv[u], G[u], Nc[u],
-                                                                  Dc[u], acc, glp, gtx, gty);
-                float* gq = gatlas + t.off;
-#pragma unroll
-                for (int c = 0; c < C + (kAlpha ? 1 : 0); ++c) {
-                  if (gv.v[c] != 0.0f) {
-                    atomicAdd(gq + c, gv.v[c] * t.w00);
-                    atomicAdd(gq + kPad + c, gv.v[c] * t.w10);
-                    atomicAdd(gq + row + c, gv.v[c] * t.w01);
-                    atomicAdd(gq + row + kPad + c, gv.v[c] * t.w11);
-                  }
-                }
-                sgx += gtx;
-                sgxy = fmaf(gtx, Y[u], sgxy);
-                sgy += gty;
-                sgyy = fmaf(gty, Y[u], sgyy);
-                spres += glp;
-              }
-            }
-            float v7[7] = {X * sgx, sgxy, sgx, X * sgy, sgyy, sgy, spres};
-#pragma unroll
-            for (int q7 = 0; q7 < 7; ++q7) v7[q7] = warp_sum(v7[q7]);
-            if (lane == 0) {
-              float* wp = wpart + ((size_t)warp * g.mc + mm) * 8;
-#pragma unroll
-              for (int q7 = 0; q7 < 7; ++q7) wp[q7] += v7[q7];
-            }
-          }
+        for (int c = 0; c < C; ++c) {
+          const size_t cx = (size_t)b * 2 * C * HW + (size_t)c * HW + p;
+          xv[c] = __ldg(x + px0 + (size_t)c * HW);
+          G[c] = __ldg(gout + px0 + (size_t)c * HW);
+          Nc[c] = __ldg(cache + cx);
+          Dc[c] = __ldg(cache + cx + (size_t)C * HW);
         }
+        bwd_background<C, kAlpha>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
       }
-      __syncthreads();
+    }
+    for (int m = warp; m < a.M; m += nwarps) {
+      // ---- per-template setup (all lanes compute the same coefficients) -----------------------------------------
+      const float* pp = a.pose + ((size_t)b * a.M + m) * 6;
+      const float Ax = __ldg(pp + 0) * hw_x, Bx = __ldg(pp + 1) * hw_x, Cx = (__ldg(pp + 2) + 1.0f) * hw_x + 1.5f;
+      const float Ay = __ldg(pp + 3) * hw_y, By = __ldg(pp + 4) * hw_y, Cy = (__ldg(pp + 5) + 1.0f) * hw_y + 1.5f;
+      const float pres = a.presence ? __ldg(a.presence + (size_t)b * a.M + m) : 1.0f;
+      const float lpres = a.presence ? log_safe_f(pres) : 0.0f;
       {
-        const int n = mc * C * hw;
-        float* dst = out.g_templates + ((size_t)b * a.M + m0) * C * hw;
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-          const int plane = (int)(((float)e + 0.5f) * inv_hw), rem = e - plane * hw;
-          const int y = (int)(((float)rem + 0.5f) * inv_w), xx = rem - y * a.w;
-          const int m = plane / C, c = plane - m * C;
-          dst[e] = gatlas[(((size_t)m * g.ph + (y + 2)) * g.pw + (xx + 2)) * kPad + c];
+        const float* src = a.templates + ((size_t)b * a.M + m) * C * hw;
+        const float inv_w = 1.0f / (float)a.w;
+        for (int e = lane; e < hw; e += 32) {
+          const int y = (int)(((float)e + 0.5f) * inv_w), xx = e - y * a.w;
+          float* q = atlas + ((size_t)(y + 2) * pw + (xx + 2)) * kPad;
+#pragma unroll
+          for (int c = 0; c < C; ++c) q[c] = __ldg(src + (size_t)c * hw + e);
+          if (kAlpha) q[C] = __ldg(a.templates_alpha + (size_t)m * hw + e);
         }
-        if (kAlpha && my_alpha_partial) {
-          const int na = mc * hw;
-          for (int e = threadIdx.x; e < na; e += blockDim.x) {
-            const int m = (int)(((float)e + 0.5f) * inv_hw), rem = e - m * hw;
-            const int y = (int)(((float)rem + 0.5f) * inv_w), xx = rem - y * a.w;
-            my_alpha_partial[(size_t)m0 * hw + e] += gatlas[(((size_t)m * g.ph + (y + 2)) * g.pw + (xx + 2)) * kPad + C];
+      }
+      __syncwarp();
+      float sgx = 0.f, sgxX = 0.f, sgxY = 0.f, sgy = 0.f, sgyX = 0.f, sgyY = 0.f, spres = 0.f;
+
+      // ---- passes of 32 consecutive pixels (row-major) -----------------------------------------------------------
+      int i = lane / a.W, j = lane - i * a.W;
+      const int di = 32 / a.W, dj = 32 - di * a.W;
+      for (int p0 = 0; p0 < HW; p0 += 32) {
+        const int p = p0 + lane;
+        const bool valid = p < HW;
+        float xv[C], G[C], Nc[C], Dc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const size_t px = (size_t)b * C * HW + (size_t)c * HW + p;
+          const size_t cx = (size_t)b * 2 * C * HW + (size_t)c * HW + p;
+          xv[c] = valid ? __ldg(x + px) : 0.0f;
+          G[c] = valid ? __ldg(gout + px) : 0.0f;        // G = 0 switches a dead lane off
+          Nc[c] = valid ? __ldg(cache + cx) : 0.0f;
+          Dc[c] = valid ? __ldg(cache + cx + (size_t)C * HW) : 0.0f;
+        }
+        const float X = xs[valid ? j : 0], Y = ys[valid ? i : 0];
+        Tap t;
+        tap_setup<kPad>(fmaf(Y, Bx, fmaf(X, Ax, Cx)), fmaf(Y, By, fmaf(X, Ay, Cy)), lim_x, lim_y, row, base0, t);
+        const float* q = atlas + t.off;
+        const Texel<kPad> t00 = ld_texel<kPad>(q), t10 = ld_texel<kPad>(q + kPad);
+        const Texel<kPad> t01 = ld_texel<kPad>(q + row), t11 = ld_texel<kPad>(q + row + kPad);
+        float glp, gtx, gty;
+        const Texel<kPad> gv = bwd_pixel<C, kAlpha, kPad>(sc, t00, t10, t01, t11, t, lpres, xv, G, Nc, Dc, acc, glp, gtx, gty);
+        sgx += gtx;
+        sgxX = fmaf(gtx, X, sgxX);
+        sgxY = fmaf(gtx, Y, sgxY);
+        sgy += gty;
+        sgyX = fmaf(gty, X, sgyX);
+        sgyY = fmaf(gty, Y, sgyY);
+        spres += glp;
+
+        // ---- segmented scan over lanes that share (row, cell) -------------------------------------------------------
+        float v[4][NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          v[0][c] = gv.v[c] * t.w00;
+          v[1][c] = gv.v[c] * t.w10;
+          v[2][c] = gv.v[c] * t.w01;
+          v[3][c] = gv.v[c] * t.w11;
+        }
+        const unsigned key = valid ? t.off : 0xFFFFFFFFu;
+        const unsigned key_prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const int i_prev = __shfl_up_sync(0xffffffffu, i, 1);
+        const bool head = lane == 0 || key != key_prev || i != i_prev;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const int seg_start = 31 - __clz(heads & (0xFFFFFFFFu >> (31 - lane)));
+        const int dist = lane - seg_start;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              const float up = __shfl_up_sync(0xffffffffu, v[k][c], d);
+              if (dist >= d) v[k][c] += up;
+            }
+        }
+        const bool tail = valid && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+        // ---- segment tails update the warp's gradient atlas: corner by corner, row by row => no address collisions ---
+        const int i_first = __shfl_sync(0xffffffffu, i, 0);
+        const int i_last = __shfl_sync(0xffffffffu, valid ? i : -1, 31 - __clz(__ballot_sync(0xffffffffu, valid)));
+        float* gq = gatlas + t.off;
+        for (int r = i_first; r <= i_last; ++r) {
+          const bool mine = tail && i == r;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (mine) {
+              float* dst = gq + (k & 1 ? kPad : 0) + (k & 2 ? row : 0);
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) dst[c] += v[k][c];
+            }
+            __syncwarp();
           }
         }
-        flush_pose(s, a, out, wpart, nwarps, g.mc, b, m0, mc);
+        // advance to the next pass
+        i += di;
+        j += dj;
+        if (j >= a.W) {
+          j -= a.W;
+          ++i;
+        }
       }
-      __syncthreads();
-      for (int e = threadIdx.x; e < g.atlas_floats; e += blockDim.x) gatlas[e] = 0.0f;
+
+      // ---- pose / presence gradients of (b, m) -------------------------------------------------------------------
+      {
+        float v7[7] = {sgxX, sgxY, sgx, sgyX, sgyY, sgy, spres};
+#pragma unroll
+        for (int q7 = 0; q7 < 7; ++q7) v7[q7] = warp_sum(v7[q7]);
+        if (lane == 0) {
+          float* gp = out.g_pose + ((size_t)b * a.M + m) * 6;
+          gp[0] = v7[0] * hw_x;
+          gp[1] = v7[1] * hw_x;
+          gp[2] = v7[2] * hw_x;
+          gp[3] = v7[3] * hw_y;
+          gp[4] = v7[4] * hw_y;
+          gp[5] = v7[5] * hw_y;
+          if (out.g_presence) out.g_presence[(size_t)b * a.M + m] = pres < kLogSafeEps ? 0.0f : v7[6] / pres;
+        }
+      }
+      __syncwarp();
+      // ---- flush + clear the gradient atlas ----------------------------------------------------------------------
+      {
+        float* dst = out.g_templates + ((size_t)b * a.M + m) * C * hw;
+        for (int e = lane; e < pw * ph; e += 32) {
+          const int yy = (int)(((float)e + 0.5f) * inv_pw), xx = e - yy * pw;
+          float* q = gatlas + (size_t)e * kPad;
+          if (yy >= 2 && yy < ph - 2 && xx >= 2 && xx < pw - 2) {
+            const int te = (yy - 2) * a.w + (xx - 2);
+#pragma unroll
+            for (int c = 0; c < C; ++c) dst[(size_t)c * hw + te] = q[c];
+            if (kAlpha && my_alpha_partial) my_alpha_partial[(size_t)m * hw + te] += q[C];
+          }
+#pragma unroll
+          for (int c = 0; c < kPad; ++c) q[c] = 0.0f;
+        }
+      }
+      __syncwarp();
     }
   }
-  write_scalar_partials(a, sc, kAlpha, acc, s.red, out.scalar_partials + (size_t)blockIdx.x * 4);
+  write_scalar_partials(a, sc, kAlpha, acc, red, out.scalar_partials + (size_t)blockIdx.x * 4);
 }
 
 // ================================================================================================================
 // host
 // ================================================================================================================
-static const size_t kBwdSmemBudget = 100 * 1024;   // two CTAs per SM
+static const size_t kBwdSmemBudget = 100 * 1024;   // gather variant: two CTAs per SM
 
 struct BwdPlan {
   TmplGeom g;
   bool gather;
 };
 
-static bool force_atomic() {
+static bool want_gather() {
   const char* e = getenv("SCAE_TMPL_BWD");
-  return e != nullptr && strcmp(e, "atomic") == 0;
+  return e != nullptr && strcmp(e, "gather") == 0;
 }
 
 static int tmpl_bwd_plan(const scae_tmpl_args* a, BwdPlan* p) {
   const int kpad = tmpl_texel_floats(a);
-  const size_t warps = kTmplThreads / 32;
-  const size_t wpart_bytes = warps * a->M * 8 * sizeof(float);        // budgeted for the worst case mc = M
-  const size_t gbuf_tmpl = (size_t)a->H * a->W * kpad * sizeof(float);
-  const size_t atlas_tmpl = (size_t)(a->w + 4) * (a->h + 4) * kpad * sizeof(float);
-  const size_t fixed = wpart_bytes + ((size_t)a->M * 8 + a->W + a->H + 64 + 8) * sizeof(float) + 64;
-  p->gather = !force_atomic() && fixed + gbuf_tmpl + atlas_tmpl <= (size_t)max_smem_optin();
-  int rc;
-  if (p->gather) {
-    rc = tmpl_geometry(a, gbuf_tmpl, wpart_bytes, kBwdSmemBudget, &p->g);
-    if (rc != SCAE_OK) return rc;
-    p->g.gbuf_floats = (int)((size_t)p->g.mc * a->H * a->W * kpad);     // H*W*kpad*mc: kpad in {1,2,4}; pad to 4 floats
-    p->g.gbuf_floats = (p->g.gbuf_floats + 3) / 4 * 4;
-    p->g.smem_bytes += 16;
-    p->g.split = 4;
-  } else {
-    rc = tmpl_geometry(a, atlas_tmpl, wpart_bytes, kBwdSmemBudget, &p->g);
-    if (rc != SCAE_OK) return rc;
+  const size_t limit = (size_t)max_smem_optin();
+  p->gather = false;
+  if (want_gather()) {
+    const size_t warps = kTmplThreads / 32;
+    const size_t wpart_bytes = warps * a->M * 8 * sizeof(float);        // budgeted for the worst case mc = M
+    const size_t gbuf_tmpl = (size_t)a->H * a->W * kpad * sizeof(float);
+    const size_t atlas_tmpl = (size_t)(a->w + 4) * (a->h + 4) * kpad * sizeof(float);
+    const size_t fixed = wpart_bytes + ((size_t)a->M * 8 + a->W + a->H + 64 + 8) * sizeof(float) + 64;
+    if (fixed + gbuf_tmpl + atlas_tmpl <= limit) {
+      int rc = tmpl_geometry(a, gbuf_tmpl, wpart_bytes, kBwdSmemBudget, &p->g);
+      if (rc != SCAE_OK) return rc;
+      p->g.gbuf_floats = (int)(((size_t)p->g.mc * a->H * a->W * kpad + 3) / 4 * 4);
+      p->g.smem_bytes += 16;
+      p->g.split = 4;
+      p->gather = true;
+      return SCAE_OK;
+    }
   }
+  // scan variant: one padded value atlas + one gradient atlas per warp, nothing that scales with the image
+  TmplGeom& g = p->g;
+  memset(&g, 0, sizeof(g));
+  g.pw = a->w + 4;
+  g.ph = a->h + 4;
+  g.mc = 1;
+  g.atlas_floats = (int)(((size_t)g.pw * g.ph * kpad + 3) / 4 * 4);
+  int threads = kScanThreads;
+  size_t smem;
+  for (;;) {
+    smem = ((size_t)(threads / 32) * 2 * g.atlas_floats + 64 + a->W + a->H + 8) * sizeof(float);
+    if (smem <= limit || threads == 32) break;
+    threads /= 2;                                   // very large templates: fewer warps per CTA
+  }
+  SCAE_REQUIRE(smem <= limit, SCAE_ELIMIT, "tmpl bwd: a %dx%d template does not fit in shared memory", a->h, a->w);
+  g.threads = threads;
+  g.smem_bytes = smem;
+  int per_sm = (int)(limit / smem);
+  const int by_threads = 2048 / threads;
+  if (per_sm > by_threads) per_sm = by_threads;
+  if (per_sm > 3) per_sm = 3;                      // compiled with __launch_bounds__(256, 3)
+  if (per_sm < 1) per_sm = 1;
+  const long slots = (long)sm_count() * per_sm;
+  g.grid = a->B < slots ? a->B : (int)slots;
   return SCAE_OK;
 }
 
@@ -569,7 +661,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_bwd(
       if (rc != SCAE_OK) return rc;
       kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, x, grad_log_prob, cache, out, g);
     } else {
-      auto kern = tmpl_ll_bwd_atomic_kernel<kC, kA>;
+      auto kern = tmpl_ll_bwd_scan_kernel<kC, kA>;
       rc = tmpl_prepare_kernel(kern, g.smem_bytes);
       if (rc != SCAE_OK) return rc;
       kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, x, grad_log_prob, cache, out, g);
