@@ -78,6 +78,27 @@ def test_kernel_vs_fp64_oracle(cfg):
     _compare(template_cuda(d), template_oracle(d), cfg, template_oracle(d, torch.float32))
 
 
+def test_extreme_poses():
+    """Degenerate sampling geometries: every pixel in one bilinear cell (tiny scale / zero pose: exercises the
+    cross-row collision path of the backward scan), singular matrices, 90-degree rotations, templates entirely outside
+    the image, exact-integer sample coordinates."""
+    B, M, C, h, w, H, W = 2, 9, 1, 11, 11, 40, 40
+    d = make_template_inputs(B, M, C, h, w, H, W, alpha=True, seed=77)
+    poses = torch.tensor([[0.011, 0., 0.3, 0., 0.011, -0.2], [0., 0., 0., 0., 0., 0.], [0.5, 0.5, 0., 0.5, 0.5, 0.],
+                          [0., 1., 0., -1., 0., 0.], [0.5, 0., 5.0, 0., 0.5, 0.], [1., 0., 0., 0., 1., 0.],
+                          [0.3, 0., 0., 0., 0., 0.], [2., 0., 0.1, 0., 3., -0.1], [1e-9, 0.5, 0., 0.5, 1e-9, 0.]],
+                         dtype=torch.float64)
+    d['pose'] = poses.unsqueeze(0).repeat(B, 1, 1)
+    d = _f32(d)
+    got, ref = template_cuda(d), template_oracle(d)
+    assert rel_err(got['log_prob'], ref['log_prob']) < TOL_LL
+    for k in ('g_templates', 'g_templates_alpha', 'g_presence', 'g_bg_value', 'g_bg_mixing_logit'):
+        assert rel_err(got[k], ref[k].reshape(got[k].shape)) < TOL_GRAD, k
+    # pose gradients at exactly-integer / degenerate coordinates are one-sided derivatives: compare away from those
+    keep = [0, 2, 4, 6, 7]
+    assert rel_err(got['g_pose'][:, keep], ref['g_pose'][:, keep]) < 1e-3
+
+
 @pytest.mark.parametrize('alpha', [True, False])
 @pytest.mark.parametrize('presence,bg_image,learn_scale', [(False, False, False), (True, True, True),
                                                            (False, True, False), (True, False, True)])

@@ -496,16 +496,37 @@ __global__ void __launch_bounds__(kScanThreads, 3) tmpl_ll_bwd_scan_kernel(const
         const int i_first = __shfl_sync(0xffffffffu, i, 0);
         const int i_last = __shfl_sync(0xffffffffu, valid ? i : -1, 31 - __clz(__ballot_sync(0xffffffffu, valid)));
         float* gq = gatlas + t.off;
-        for (int r = i_first; r <= i_last; ++r) {
-          const bool mine = tail && i == r;
+        // A pass of 32 consecutive pixels can straddle image rows.  Within one row the cells of different segments are
+        // distinct; across rows they could coincide (extreme magnification), so check once with MATCH and only then
+        // fall back to updating row by row.
+        bool by_row = false;
+        if (i_first != i_last) {
+          const unsigned tails = __ballot_sync(0xffffffffu, tail);
+          const unsigned peers = __match_any_sync(0xffffffffu, tail ? key : (0xFFFFFF00u | (unsigned)lane));
+          by_row = __any_sync(0xffffffffu, tail && (peers & tails & ~(1u << lane)) != 0u);
+        }
+        if (!by_row) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (mine) {
+            if (tail) {
               float* dst = gq + (k & 1 ? kPad : 0) + (k & 2 ? row : 0);
 #pragma unroll
               for (int c = 0; c < NCH; ++c) dst[c] += v[k][c];
             }
             __syncwarp();
+          }
+        } else {
+          for (int r = i_first; r <= i_last; ++r) {
+            const bool mine = tail && i == r;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (mine) {
+                float* dst = gq + (k & 1 ? kPad : 0) + (k & 2 ? row : 0);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) dst[c] += v[k][c];
+              }
+              __syncwarp();
+            }
           }
         }
         // advance to the next pass

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import math_ops
+from . import math_ops, skinny
 from .attrdict import AttrDict, LazyAttrDict
 from .distributions import TemplateMixture
 from .nn_ext import MLP, choose_activation, relu1
@@ -44,7 +44,9 @@ class TemplateGenerator(nn.Module):
         raw_templates = self.template_nonlin(self.template_logits)
         if self.colorize_templates and feature is not None:
             B, M = feature.shape[:2]
-            color = self.templates_color_mlp(feature.reshape(B * M, -1))
+            color = feature.reshape(B * M, -1)
+            for layer in self.templates_color_mlp:      # Linear/ReLU chain; tall-skinny -> split-K weight grads
+                color = skinny.linear(color, layer) if isinstance(layer, nn.Linear) else layer(color)
             if self.color_nonlin == relu1:
                 color = color + .99
             color = self.color_nonlin(color).view(B, M, -1)

@@ -10,6 +10,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import skinny
+
 
 def _layer_norm(x, ln):
     """nn.LayerNorm's arithmetic with the affine part as plain elementwise ops.
@@ -52,15 +54,15 @@ class MultiHeadQKVAttention(nn.Module):
             assert values.shape[:2] == presence.shape
         B, N, _ = queries.shape
         H = self.n_heads
-        q = self._split_heads(self.q_projector(queries))
-        k = self._split_heads(self.k_projector(keys))
-        v = self._split_heads(self.v_projector(values))
+        q = self._split_heads(skinny.linear(queries, self.q_projector))
+        k = self._split_heads(skinny.linear(keys, self.k_projector))
+        v = self._split_heads(skinny.linear(values, self.v_projector))
         if presence is not None and H > 1:
             presence = presence.repeat(H, 1)
         o = qkv_attention(q, k, v, presence)
         if H > 1:
             o = o.view(H, B, N, -1).permute(1, 2, 0, 3).reshape(B, N, -1)
-        return self.o_projector(o)
+        return skinny.linear(o, self.o_projector)
 
 
 class MAB(nn.Module):
@@ -80,7 +82,7 @@ class MAB(nn.Module):
             h = h * presence.unsqueeze(-1)
         if self.layer_norm:
             h = _layer_norm(h, self.ln0)
-        h = h + F.relu(self.fc(h))
+        h = h + F.relu(skinny.linear(h, self.fc))
         if self.layer_norm:
             h = _layer_norm(h, self.ln1)
         return h
@@ -135,8 +137,8 @@ class SetTransformer(nn.Module):
         self.multi_head_attention = MultiHeadQKVAttention(d_k=dim_out, d_v=dim_out, n_heads=n_heads)
 
     def forward(self, x, presence=None):
-        h = self.fc1(x)
+        h = skinny.linear(x, self.fc1)
         for block in self.sabs:
             h = block(h, presence)
-        z = self.fc2(h)
+        z = skinny.linear(h, self.fc2)
         return self.multi_head_attention(self.seeds.expand(x.shape[0], -1, -1), z, z, presence)
