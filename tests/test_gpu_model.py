@@ -84,8 +84,10 @@ def test_mid_size_model_vs_cpu_oracle():
     """MNIST-shaped model (40x40, 40 part caps, 32 object caps, batch 16): loss and gradients vs the CPU oracle."""
     from oracle import scae_model
     from torch_scae_b200 import factory
+    import numpy as np
     strict_fp32()
     torch.manual_seed(0)
+    np.random.seed(0)          # TemplateGenerator's orthogonal init draws from numpy (part_decoder.py:63)
     params = dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=32,
                   scae_params=dict(reconstruct_alternatives=False))
     model = factory.make_scae(params)
@@ -116,5 +118,7 @@ def test_mid_size_model_vs_cpu_oracle():
               'obj_encoder.fc1.weight'):
         got = dict(model.named_parameters())[k].grad
         assert rel_err(got, sd[k].grad) < TOL_GRAD, k
-    got = model.part_encoder.att_conv.weight.grad
-    assert l2_rel_err(got, sd['part_encoder.att_conv.weight'].grad) < 2e-3
+    # gradients that flow through the pose of the warped templates inherit the bilinear cell-flip noise: norm-wise
+    for k in ('part_encoder.att_conv.weight', 'part_encoder.encoder.network.0.weight'):
+        got = dict(model.named_parameters())[k].grad
+        assert l2_rel_err(got, sd[k].grad) < 2e-3, k

@@ -94,9 +94,13 @@ def test_extreme_poses():
     assert rel_err(got['log_prob'], ref['log_prob']) < TOL_LL
     for k in ('g_templates', 'g_templates_alpha', 'g_presence', 'g_bg_value', 'g_bg_mixing_logit'):
         assert rel_err(got[k], ref[k].reshape(got[k].shape)) < TOL_GRAD, k
-    # pose gradients at exactly-integer / degenerate coordinates are one-sided derivatives: compare away from those
-    keep = [0, 2, 4, 6, 7]
+    # Pose gradients are one-sided derivatives wherever a sample lands exactly on a texel boundary (zero pose, the
+    # identity, the 90-degree rotation, and the singular diagonal pose, which puts the whole anti-diagonal i+j=39 on
+    # tx = 7.0): there the value is continuous but the derivative depends on the last bit of the coordinate, so those
+    # poses are only checked for finiteness; the others must match.
+    keep = [0, 4, 6, 7]
     assert rel_err(got['g_pose'][:, keep], ref['g_pose'][:, keep]) < 1e-3
+    assert bool(torch.isfinite(got['g_pose']).all())
 
 
 @pytest.mark.parametrize('alpha', [True, False])

@@ -47,7 +47,7 @@ class _SplitKLinear(torch.autograd.Function):
         return gx, gw, gb
 
 
-def linear(x, layer, max_weight_elems=64 * 256, min_rows=8192):
+def linear(x, layer, max_weight_elems=256 * 256, min_rows=8192):
     """``layer(x)`` for an nn.Linear; uses the split-K weight gradient when the layer is small and x is tall."""
     rows = x.numel() // x.shape[-1]
     if layer.weight.numel() <= max_weight_elems and rows >= min_rows and torch.is_grad_enabled() and x.is_cuda:
