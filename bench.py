@@ -158,7 +158,7 @@ def run_reference(args):
                             batch_per_step=batch),
                 cpu_baseline=dict(value=round(value, 2), unit=UNIT, cores=threads, kind='port', sample=sample),
                 e2e=dict(value=round(value, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -311,12 +311,26 @@ def run_gpu(args):
                          h2d_bytes_per_step=int(host_image.numel() * 4 + host_label.numel() * 8) * world,
                          d2h_bytes_per_step=4 * world),
                 gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu, clocks=clocks, extra=extra)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+RESULT_OUT = sys.stdout
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL prints its version banner to fd 1 on the GPU boxes, and other
+    libraries may chat there too, so keep a private handle on the real stdout for the result line and point fd 1 at
+    stderr for everything else."""
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
