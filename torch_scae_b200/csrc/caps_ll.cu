@@ -18,6 +18,7 @@
 namespace scae {
 
 constexpr int kCapsThreads = 128;
+constexpr int kCapsIlp = 4;      // objects processed per loop iteration as independent dependency chains
 
 __host__ __device__ inline int caps_imgs_per_cta(int V) { return V >= kCapsThreads ? 1 : kCapsThreads / V; }
 
@@ -31,7 +32,7 @@ __host__ __device__ inline size_t caps_fwd_smem_floats(int imgs, int O, int V) {
   return (size_t)imgs * O * 8 + (size_t)imgs * O * (V | 1) + 2 * (size_t)imgs * V;
 }
 __host__ __device__ inline size_t caps_bwd_smem_floats(int imgs, int O) {
-  return (size_t)imgs * O * 8 * 2 + 7 * (kCapsThreads + 1);
+  return (size_t)imgs * O * 8 * 2 + (size_t)kCapsIlp * 7 * (kCapsThreads + 1);
 }
 
 // ---- phase 0 (both directions): capsule-level quantities per (image, object) -------------------------------------
@@ -116,63 +117,117 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
   for (int i = threadIdx.x; i < n_items; i += kCapsThreads) {
     const int bi = i / V, v = i - bi * V, b = b0 + bi;
     const size_t bv = (size_t)b * V + v;
-    float x[6], sw[6], wv[6];
+    float x[6];
 #pragma unroll
-    for (int p = 0; p < 6; ++p) {
-      x[p] = __ldg(a.x + bv * 6 + p);
-      sw[p] = __ldg(a.dummy_vote + (size_t)v * 6 + p);   // the dummy component enters the mixture first, weight 1
-      wv[p] = 0.0f;
-    }
+    for (int p = 0; p < 6; ++p) x[p] = __ldg(a.x + bv * 6 + p);
     const float pres = a.presence ? __ldg(a.presence + bv) : 1.0f;
-    Lse post, mix;
-    post.init(kDummyLog + kDummyLog);   // dummy logit + dummy log-density (object_decoder.py:273-292)
-    mix.init(kDummyLog);
-    float swp = 0.0f, best = -INFINITY, wvp = 0.0f, regsum = 0.0f;
-    int widx = 0;
-    const float* rowb = a.all_param + (size_t)b * O * A;
-
-    for (int oo = 0; oo < O; ++oo) {
-      const float* r = R + ((size_t)bi * O + oo) * 8;
-      const size_t bov = ((size_t)b * O + oo) * V + v;
-      const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
-      CapsPair c;
-      caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, r, oo, v, bov, deform, learn, c);
-      float q = 0.0f;
+    // kCapsIlp independent streaming-softmax chains (objects oo, oo+1, ... of one iteration): at ~9 resident warps per
+    // SM the kernel is latency bound, and the chains give the scheduler independent work; they are merged below.
+    Lse post_c[kCapsIlp], mix_c[kCapsIlp];
+    float sw_c[kCapsIlp][6], wv_c[kCapsIlp][6], swp_c[kCapsIlp], best_c[kCapsIlp], wvp_c[kCapsIlp];
+    int widx_c[kCapsIlp];
+    float regsum = 0.0f;
+#pragma unroll
+    for (int u = 0; u < kCapsIlp; ++u) {
+      post_c[u].m = -INFINITY;
+      post_c[u].s = 0.0f;
+      mix_c[u].m = -INFINITY;
+      mix_c[u].s = 0.0f;
+      swp_c[u] = 0.0f;
+      best_c[u] = -INFINITY;
+      wvp_c[u] = 0.0f;
+      widx_c[u] = 0;
 #pragma unroll
       for (int p = 0; p < 6; ++p) {
-        const float d = x[p] - c.vt[p];
-        q = fmaf(d, d, q);
-        regsum = fmaf(c.dyn[p], c.dyn[p], regsum);
+        sw_c[u][p] = 0.0f;
+        wv_c[u][p] = 0.0f;
       }
-      // sum over the 6 pose dims of Normal(vote, sc).log_prob(x)
-      const float lp = -q * __frcp_rn(2.0f * c.sc * c.sc) - 6.0f * logf(c.sc) - 6.0f * kHalfLog2Pi;
-      const float ml = log_safe_f(c.vp);
-      const float pl = ml + lp;
-      float resc;
-      const float wn = post.push(pl, resc);
+    }
+    // the dummy component enters chain 0 first, weight 1: dummy logit + dummy log-density (object_decoder.py:273-292)
+    post_c[0].init(kDummyLog + kDummyLog);
+    mix_c[0].init(kDummyLog);
 #pragma unroll
-      for (int p = 0; p < 6; ++p) sw[p] = fmaf(sw[p], resc, wn * c.vt[p]);
-      swp = fmaf(swp, resc, wn * c.vp);
-      mix.push(ml);
-      if (pl > best) {
-        best = pl;
-        widx = oo;
-        wvp = c.vp;
+    for (int p = 0; p < 6; ++p) sw_c[0][p] = __ldg(a.dummy_vote + (size_t)v * 6 + p);
+    const float* rowb = a.all_param + (size_t)b * O * A;
+
+    for (int o0 = 0; o0 < O; o0 += kCapsIlp) {
 #pragma unroll
-        for (int p = 0; p < 6; ++p) wv[p] = c.vt[p];
+      for (int u = 0; u < kCapsIlp; ++u) {
+        const int oo = o0 + u;
+        if (oo < O) {
+          const float* r = R + ((size_t)bi * O + oo) * 8;
+          const size_t bov = ((size_t)b * O + oo) * V + v;
+          const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
+          CapsPair c;
+          caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, r, oo, v, bov, deform, learn, c);
+          float q = 0.0f;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) {
+            const float d = x[p] - c.vt[p];
+            q = fmaf(d, d, q);
+            regsum = fmaf(c.dyn[p], c.dyn[p], regsum);
+          }
+          // sum over the 6 pose dims of Normal(vote, sc).log_prob(x)
+          const float lp = -q * __frcp_rn(2.0f * c.sc * c.sc) - 6.0f * logf(c.sc) - 6.0f * kHalfLog2Pi;
+          const float ml = log_safe_f(c.vp);
+          const float pl = ml + lp;
+          float resc;
+          const float wn = post_c[u].push(pl, resc);
+#pragma unroll
+          for (int p = 0; p < 6; ++p) sw_c[u][p] = fmaf(sw_c[u][p], resc, wn * c.vt[p]);
+          swp_c[u] = fmaf(swp_c[u], resc, wn * c.vp);
+          mix_c[u].push(ml);
+          if (pl > best_c[u]) {
+            best_c[u] = pl;
+            widx_c[u] = oo;
+            wvp_c[u] = c.vp;
+#pragma unroll
+            for (int p = 0; p < 6; ++p) wv_c[u][p] = c.vt[p];
+          }
+          vp_tile[((size_t)bi * O + oo) * Vp + v] = c.vp;
+          if (o.vote) {
+#pragma unroll
+            for (int p = 0; p < 6; ++p) o.vote[bov * 6 + p] = c.vt[p];
+          }
+          if (o.scale) o.scale[bov] = c.sc;
+          if (o.vote_presence) o.vote_presence[bov] = c.vp;
+          if (o.presence_logit_per_vote) o.presence_logit_per_vote[bov] = c.lv;
+          if (o.vote_presence_binary) o.vote_presence_binary[bov] = ml > kDummyLog ? 1.0f : 0.0f;
+          if (o.posterior_mixing_prob) o.posterior_mixing_prob[bov] = pl;   // normalised below
+          if (o.mixing_logit) o.mixing_logit[bov1] = ml;
+          if (o.mixing_log_prob) o.mixing_log_prob[bov1] = ml;             // normalised below
+        }
       }
-      vp_tile[((size_t)bi * O + oo) * Vp + v] = c.vp;
-      if (o.vote) {
+    }
+    // merge the chains into chain 0 (which is never empty: it holds the dummy component)
+    Lse post = post_c[0], mix = mix_c[0];
+    float sw[6], wv[6], swp = swp_c[0], best = best_c[0], wvp = wvp_c[0];
+    int widx = widx_c[0];
 #pragma unroll
-        for (int p = 0; p < 6; ++p) o.vote[bov * 6 + p] = c.vt[p];
+    for (int p = 0; p < 6; ++p) {
+      sw[p] = sw_c[0][p];
+      wv[p] = wv_c[0][p];
+    }
+#pragma unroll
+    for (int u = 1; u < kCapsIlp; ++u) {
+      const float M = fmaxf(post.m, post_c[u].m);
+      const float ea = expf(post.m - M), eb = expf(post_c[u].m - M);      // exp(-inf) = 0 for an empty chain
+      post.s = post.s * ea + post_c[u].s * eb;
+      post.m = M;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) sw[p] = sw[p] * ea + sw_c[u][p] * eb;
+      swp = swp * ea + swp_c[u] * eb;
+      const float Mm = fmaxf(mix.m, mix_c[u].m);
+      mix.s = mix.s * expf(mix.m - Mm) + mix_c[u].s * expf(mix_c[u].m - Mm);
+      mix.m = Mm;
+      // hard winner: largest posterior logit, lowest object index on ties (torch.argmax)
+      if (best_c[u] > best || (best_c[u] == best && best_c[u] > -INFINITY && widx_c[u] < widx)) {
+        best = best_c[u];
+        widx = widx_c[u];
+        wvp = wvp_c[u];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) wv[p] = wv_c[u][p];
       }
-      if (o.scale) o.scale[bov] = c.sc;
-      if (o.vote_presence) o.vote_presence[bov] = c.vp;
-      if (o.presence_logit_per_vote) o.presence_logit_per_vote[bov] = c.lv;
-      if (o.vote_presence_binary) o.vote_presence_binary[bov] = ml > kDummyLog ? 1.0f : 0.0f;
-      if (o.posterior_mixing_prob) o.posterior_mixing_prob[bov] = pl;   // normalised below
-      if (o.mixing_logit) o.mixing_logit[bov1] = ml;
-      if (o.mixing_log_prob) o.mixing_log_prob[bov1] = ml;             // normalised below
     }
 
     const float lse = post.value();
@@ -259,7 +314,7 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
   const int nimg = min(imgs_per_cta, a.B - b0);
   float* R = smem;
   float* acc = R + (size_t)imgs_per_cta * O * 8;     // [imgs][O][8]: sum over v of (g_r[6], g_vp*pv, unused)
-  float* scr = acc + (size_t)imgs_per_cta * O * 8;   // [7][kCapsThreads+1]
+  float* scr = acc + (size_t)imgs_per_cta * O * 8;   // [kCapsIlp][7][kCapsThreads+1]
   constexpr int kScr = kCapsThreads + 1;
   const bool deform = (a.flags & SCAE_CAPS_ALLOW_DEFORM) != 0;
   const bool learn = (a.flags & SCAE_CAPS_LEARN_VOTE_SCALE) != 0;
@@ -331,91 +386,107 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
     }
 
     // ---- pass B: per-pair gradients -------------------------------------------------------------------------------
-    for (int oo = 0; oo < O; ++oo) {
-      float red7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int o0 = 0; o0 < O; o0 += kCapsIlp) {
+      // kCapsIlp objects per iteration as independent dependency chains (latency hiding at low occupancy); their
+      // per-(image, object) partial sums go through the shared-memory transpose together, one barrier pair per group
+      float red7[kCapsIlp][7];
+#pragma unroll
+      for (int u = 0; u < kCapsIlp; ++u)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) red7[u][k] = 0.0f;
       if (active) {
-        const float* r = R + ((size_t)bi * O + oo) * 8;
-        const size_t bov = ((size_t)b * O + oo) * V + v;
-        const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
-        const size_t bo = (size_t)b * O + oo;
-        CapsPair c;
-        caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, r, oo, v, bov, deform, learn, c);
-        const float post = __ldg(sv.posterior_mixing_prob + bov);
-        float h = up.g_posterior_mixing_prob ? __ldg(up.g_posterior_mixing_prob + bov) : 0.0f;
-        float diff[6], q = 0.0f;
 #pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          h = fmaf(gsw[p], c.vt[p], h);
-          diff[p] = x[p] - c.vt[p];
-          q = fmaf(diff[p], diff[p], q);
+        for (int u = 0; u < kCapsIlp; ++u) {
+          const int oo = o0 + u;
+          if (oo < O) {
+            const float* r = R + ((size_t)bi * O + oo) * 8;
+            const size_t bov = ((size_t)b * O + oo) * V + v;
+            const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
+            const size_t bo = (size_t)b * O + oo;
+            CapsPair c;
+            caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, r, oo, v, bov, deform, learn, c);
+            const float post = __ldg(sv.posterior_mixing_prob + bov);
+            float h = up.g_posterior_mixing_prob ? __ldg(up.g_posterior_mixing_prob + bov) : 0.0f;
+            float diff[6], q = 0.0f;
+    #pragma unroll
+            for (int p = 0; p < 6; ++p) {
+              h = fmaf(gsw[p], c.vt[p], h);
+              diff[p] = x[p] - c.vt[p];
+              q = fmaf(diff[p], diff[p], q);
+            }
+            h = fmaf(gswp, c.vp, h);
+            const float g_pl = post * (h - S) + gll * pres * post;
+            const bool is_win = oo == widx;
+            float g_vp = gswp * post;
+            if (up.g_vote_presence) g_vp += __ldg(up.g_vote_presence + bov);
+            if (is_win) g_vp += gwp;
+            if (up.g_caps_presence && sv.caps_presence_arg[bo] == v) g_vp += __ldg(up.g_caps_presence + bo);
+            float g_ml = g_pl;
+            if (up.g_mixing_logit) g_ml += __ldg(up.g_mixing_logit + bov1);
+            if (need_mix) g_ml += __ldg(up.g_mixing_log_prob + bov1) - expf(log_safe_f(c.vp) - mix_lse) * sum_gmlp;
+            if (!(c.vp < kLogSafeEps)) g_vp += g_ml / c.vp;
+            const float inv_sc = __frcp_rn(c.sc);
+            const float inv2 = inv_sc * inv_sc;
+            const float coef = g_pl * inv2;
+            float gv[6];
+    #pragma unroll
+            for (int p = 0; p < 6; ++p) {
+              float g = gsw[p] * post + coef * diff[p];
+              if (up.g_vote) g += __ldg(up.g_vote + bov * 6 + p);
+              if (is_win) g += gw[p];
+              gv[p] = g;
+              gx[p] = fmaf(-coef, diff[p], gx[p]);
+            }
+            float g_sc = g_pl * (q * inv2 * inv_sc - 6.0f * inv_sc);
+            if (up.g_scale) g_sc += __ldg(up.g_scale + bov);
+            const float g_u = learn ? g_sc * sigmoid_f(c.u + 0.5f) : 0.0f;
+            float g_lv = g_vp * r[6] * c.pv * (1.0f - c.pv);
+            if (up.g_presence_logit_per_vote) g_lv += __ldg(up.g_presence_logit_per_vote + bov);
+            // vote = R . A
+            const float* A_ = c.pa.a;
+            float ga[6];
+            ga[0] = r[0] * gv[0] + r[3] * gv[3];
+            ga[1] = r[0] * gv[1] + r[3] * gv[4];
+            ga[2] = r[0] * gv[2] + r[3] * gv[5];
+            ga[3] = r[1] * gv[0] + r[4] * gv[3];
+            ga[4] = r[1] * gv[1] + r[4] * gv[4];
+            ga[5] = r[1] * gv[2] + r[4] * gv[5];
+            red7[u][0] = gv[0] * A_[0] + gv[1] * A_[1] + gv[2] * A_[2];
+            red7[u][1] = gv[0] * A_[3] + gv[1] * A_[4] + gv[2] * A_[5];
+            red7[u][2] = gv[2];
+            red7[u][3] = gv[3] * A_[0] + gv[4] * A_[1] + gv[5] * A_[2];
+            red7[u][4] = gv[3] * A_[3] + gv[4] * A_[4] + gv[5] * A_[5];
+            red7[u][5] = gv[5];
+            red7[u][6] = g_vp * c.pv;
+            float gt[6];
+            pose_affine_bwd<kSim>(ga, c.pa, gt);
+            float* grow = out.g_all_param + ((size_t)b * O + oo) * A;
+    #pragma unroll
+            for (int p = 0; p < 6; ++p) grow[6 * v + p] = gt[p];
+            grow[6 * V + 7 + v] = g_lv;
+            grow[7 * V + 7 + v] = g_u;
+          }
         }
-        h = fmaf(gswp, c.vp, h);
-        const float g_pl = post * (h - S) + gll * pres * post;
-        const bool is_win = oo == widx;
-        float g_vp = gswp * post;
-        if (up.g_vote_presence) g_vp += __ldg(up.g_vote_presence + bov);
-        if (is_win) g_vp += gwp;
-        if (up.g_caps_presence && sv.caps_presence_arg[bo] == v) g_vp += __ldg(up.g_caps_presence + bo);
-        float g_ml = g_pl;
-        if (up.g_mixing_logit) g_ml += __ldg(up.g_mixing_logit + bov1);
-        if (need_mix) g_ml += __ldg(up.g_mixing_log_prob + bov1) - expf(log_safe_f(c.vp) - mix_lse) * sum_gmlp;
-        if (!(c.vp < kLogSafeEps)) g_vp += g_ml / c.vp;
-        const float inv_sc = __frcp_rn(c.sc);
-        const float inv2 = inv_sc * inv_sc;
-        const float coef = g_pl * inv2;
-        float gv[6];
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          float g = gsw[p] * post + coef * diff[p];
-          if (up.g_vote) g += __ldg(up.g_vote + bov * 6 + p);
-          if (is_win) g += gw[p];
-          gv[p] = g;
-          gx[p] = fmaf(-coef, diff[p], gx[p]);
-        }
-        float g_sc = g_pl * (q * inv2 * inv_sc - 6.0f * inv_sc);
-        if (up.g_scale) g_sc += __ldg(up.g_scale + bov);
-        const float g_u = learn ? g_sc * sigmoid_f(c.u + 0.5f) : 0.0f;
-        float g_lv = g_vp * r[6] * c.pv * (1.0f - c.pv);
-        if (up.g_presence_logit_per_vote) g_lv += __ldg(up.g_presence_logit_per_vote + bov);
-        // vote = R . A
-        const float* A_ = c.pa.a;
-        float ga[6];
-        ga[0] = r[0] * gv[0] + r[3] * gv[3];
-        ga[1] = r[0] * gv[1] + r[3] * gv[4];
-        ga[2] = r[0] * gv[2] + r[3] * gv[5];
-        ga[3] = r[1] * gv[0] + r[4] * gv[3];
-        ga[4] = r[1] * gv[1] + r[4] * gv[4];
-        ga[5] = r[1] * gv[2] + r[4] * gv[5];
-        red7[0] = gv[0] * A_[0] + gv[1] * A_[1] + gv[2] * A_[2];
-        red7[1] = gv[0] * A_[3] + gv[1] * A_[4] + gv[2] * A_[5];
-        red7[2] = gv[2];
-        red7[3] = gv[3] * A_[0] + gv[4] * A_[1] + gv[5] * A_[2];
-        red7[4] = gv[3] * A_[3] + gv[4] * A_[4] + gv[5] * A_[5];
-        red7[5] = gv[5];
-        red7[6] = g_vp * c.pv;
-        float gt[6];
-        pose_affine_bwd<kSim>(ga, c.pa, gt);
-        float* grow = out.g_all_param + ((size_t)b * O + oo) * A;
-#pragma unroll
-        for (int p = 0; p < 6; ++p) grow[6 * v + p] = gt[p];
-        grow[6 * V + 7 + v] = g_lv;
-        grow[7 * V + 7 + v] = g_u;
-        (void)greg;
       }
-      // sum over the parts of each image: transpose through shared memory, one reducer thread per (image, slot)
+      // sum over the parts of each image: transpose through shared memory, one reducer thread per (image, object, slot)
 #pragma unroll
-      for (int k = 0; k < 7; ++k) scr[k * kScr + threadIdx.x] = red7[k];
+      for (int u = 0; u < kCapsIlp; ++u)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) scr[(u * 7 + k) * kScr + threadIdx.x] = red7[u][k];
       __syncthreads();
       {
         const int img_lo = base / V;
         const int img_hi = min(nimg - 1, (base + kCapsThreads - 1) / V);
-        const int n_red = (img_hi - img_lo + 1) * 7;
+        const int n_red = (img_hi - img_lo + 1) * 7 * kCapsIlp;
         for (int t = threadIdx.x; t < n_red; t += kCapsThreads) {
-          const int rb = img_lo + t / 7, k = t % 7;
-          const int j0 = max(0, rb * V - base), j1 = min(kCapsThreads, (rb + 1) * V - base);
-          float s = 0.0f;
-          for (int j = j0; j < j1; ++j) s += scr[k * kScr + j];
-          acc[((size_t)rb * O + oo) * 8 + k] += s;
+          const int rb = img_lo + t / (7 * kCapsIlp), rem = t % (7 * kCapsIlp);
+          const int u = rem / 7, k = rem - u * 7;
+          if (o0 + u < O) {
+            const int j0 = max(0, rb * V - base), j1 = min(kCapsThreads, (rb + 1) * V - base);
+            float sum = 0.0f;
+            for (int j = j0; j < j1; ++j) sum += scr[(u * 7 + k) * kScr + j];
+            acc[((size_t)rb * O + o0 + u) * 8 + k] += sum;
+          }
         }
       }
       __syncthreads();
