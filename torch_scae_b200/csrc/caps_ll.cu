@@ -28,11 +28,45 @@ struct CapsSmem {
   float* red;     // fwd: [2][imgs*V] per-point partials; bwd: scratch [7][kCapsThreads+1]
 };
 
-__host__ __device__ inline size_t caps_fwd_smem_floats(int imgs, int O, int V) {
-  return (size_t)imgs * O * 8 + (size_t)imgs * O * (V | 1) + 2 * (size_t)imgs * V;
+// One staging buffer holds, for the current group of kCapsIlp objects, the all_param rows of the CTA's images
+// ([imgs][kCapsIlp][A]) and the matching cpr_static rows ([kCapsIlp][V*6]).  Two buffers (double buffering).
+__host__ __device__ inline size_t caps_stage_floats(int imgs, int V) {
+  return (size_t)imgs * kCapsIlp * (8 * V + 7) + (size_t)kCapsIlp * V * 6;
 }
-__host__ __device__ inline size_t caps_bwd_smem_floats(int imgs, int O) {
-  return (size_t)imgs * O * 8 * 2 + (size_t)kCapsIlp * 7 * (kCapsThreads + 1);
+__host__ __device__ inline size_t caps_fwd_smem_floats(int imgs, int O, int V) {
+  return (size_t)imgs * O * 8 + (size_t)imgs * O * (V | 1) + 2 * (size_t)imgs * V + 2 * caps_stage_floats(imgs, V);
+}
+__host__ __device__ inline size_t caps_bwd_smem_floats(int imgs, int O, int V) {
+  return (size_t)imgs * O * 8 * 2 + (size_t)kCapsIlp * 7 * (kCapsThreads + 1) + 2 * caps_stage_floats(imgs, V);
+}
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Issues the asynchronous, fully coalesced copy of one object group into a staging buffer.  The rows of objects
+// o0 .. o0+nobj-1 of one image are contiguous in all_param, so each image is one run of nobj*A floats (4-byte cp.async:
+// rows are only 4-byte aligned because A = 8V+7 is odd).  Replaces per-thread loads with a 24-byte lane stride that
+// touched 24 sectors per warp-load (profiles/r01e: 13.9 M L1 sectors for 43 MB of parameters).
+__device__ __forceinline__ void caps_stage_issue(const scae_caps_args& a, int b0, int nimg, int o0, float* stage) {
+  const int O = a.O, V = a.V, A = 8 * V + 7;
+  const int nobj = min(kCapsIlp, O - o0);
+  const int run = nobj * A;
+  for (int bi = 0; bi < nimg; ++bi) {
+    const float* src = a.all_param + ((size_t)(b0 + bi) * O + o0) * A;
+    float* dst = stage + (size_t)bi * kCapsIlp * A;
+    for (int e = threadIdx.x; e < run; e += kCapsThreads) cp_async4(dst + e, src + e);
+  }
+  const float* ssrc = a.cpr_static + (size_t)o0 * V * 6;
+  float* sdst = stage + (size_t)nimg * kCapsIlp * A;
+  for (int e = threadIdx.x; e < nobj * V * 6; e += kCapsThreads) cp_async4(sdst + e, ssrc + e);
+  cp_async_commit();
 }
 
 // ---- phase 0 (both directions): capsule-level quantities per (image, object) -------------------------------------
@@ -67,16 +101,17 @@ struct CapsPair {
   float lv, pv, vp, u, sc;
 };
 
+// row: the object's all_param row [A]; srow: the object's cpr_static row [V*6] (staged in shared memory, or global)
 template <bool kSim>
-__device__ __forceinline__ void caps_pair_fwd(const scae_caps_args& a, const float* __restrict__ row, const float* r,
+__device__ __forceinline__ void caps_pair_fwd(const scae_caps_args& a, const float* row, const float* srow, const float* r,
                                               int oo, int v, size_t bov, bool deform, bool learn, CapsPair& c) {
   const int V = a.V;
   const size_t ov = (size_t)oo * V + v;
   float t[6];
 #pragma unroll
   for (int p = 0; p < 6; ++p) {
-    c.dyn[p] = deform ? __ldg(row + 6 * v + p) : 0.0f;
-    t[p] = c.dyn[p] + __ldg(a.cpr_static + ov * 6 + p);
+    c.dyn[p] = deform ? row[6 * v + p] : 0.0f;
+    t[p] = c.dyn[p] + srow[6 * v + p];
   }
   pose_affine_fwd<kSim>(t, c.pa);
   const float* A_ = c.pa.a;
@@ -86,11 +121,11 @@ __device__ __forceinline__ void caps_pair_fwd(const scae_caps_args& a, const flo
   c.vt[3] = r[3] * A_[0] + r[4] * A_[3];
   c.vt[4] = r[3] * A_[1] + r[4] * A_[4];
   c.vt[5] = r[3] * A_[2] + r[4] * A_[5] + r[5];
-  c.lv = __ldg(row + 6 * V + 7 + v) + __ldg(a.bias_vote + ov);
+  c.lv = row[6 * V + 7 + v] + __ldg(a.bias_vote + ov);
   if (a.noise_vote) c.lv += __ldg(a.noise_vote + bov);
   c.pv = sigmoid_f(c.lv);
   c.vp = r[6] * c.pv;
-  c.u = __ldg(row + 7 * V + 7 + v) + __ldg(a.bias_scale + ov);
+  c.u = row[7 * V + 7 + v] + __ldg(a.bias_scale + ov);
   c.sc = learn ? softplus_f(c.u + 0.5f) + 1e-2f : 1.0f;
 }
 
@@ -107,6 +142,8 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
   float* R = smem;
   float* vp_tile = R + (size_t)imgs_per_cta * O * 8;
   float* red = vp_tile + (size_t)imgs_per_cta * O * Vp;
+  float* stage0 = red + 2 * (size_t)imgs_per_cta * V;                     // two staging buffers (see caps_stage_issue)
+  const size_t stage_floats = caps_stage_floats(imgs_per_cta, V);
   const bool deform = (a.flags & SCAE_CAPS_ALLOW_DEFORM) != 0;
   const bool learn = (a.flags & SCAE_CAPS_LEARN_VOTE_SCALE) != 0;
 
@@ -114,13 +151,15 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
   __syncthreads();
 
   const int n_items = nimg * V;
-  for (int i = threadIdx.x; i < n_items; i += kCapsThreads) {
-    const int bi = i / V, v = i - bi * V, b = b0 + bi;
+  for (int base = 0; base < n_items; base += kCapsThreads) {
+    const int i = base + threadIdx.x;
+    const bool active = i < n_items;
+    const int bi = active ? i / V : 0, v = active ? i - bi * V : 0, b = b0 + bi;
     const size_t bv = (size_t)b * V + v;
     float x[6];
 #pragma unroll
-    for (int p = 0; p < 6; ++p) x[p] = __ldg(a.x + bv * 6 + p);
-    const float pres = a.presence ? __ldg(a.presence + bv) : 1.0f;
+    for (int p = 0; p < 6; ++p) x[p] = active ? __ldg(a.x + bv * 6 + p) : 0.0f;
+    const float pres = (active && a.presence) ? __ldg(a.presence + bv) : 1.0f;
     // kCapsIlp independent streaming-softmax chains (objects oo, oo+1, ... of one iteration): at ~9 resident warps per
     // SM the kernel is latency bound, and the chains give the scheduler independent work; they are merged below.
     Lse post_c[kCapsIlp], mix_c[kCapsIlp];
@@ -148,18 +187,29 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
     mix_c[0].init(kDummyLog);
 #pragma unroll
     for (int p = 0; p < 6; ++p) sw_c[0][p] = __ldg(a.dummy_vote + (size_t)v * 6 + p);
-    const float* rowb = a.all_param + (size_t)b * O * A;
 
-    for (int o0 = 0; o0 < O; o0 += kCapsIlp) {
+    // object groups stream through two shared-memory staging buffers filled by coalesced cp.async copies
+    caps_stage_issue(a, b0, nimg, 0, stage0);
+    for (int o0 = 0, g = 0; o0 < O; o0 += kCapsIlp, ++g) {
+      float* stage = stage0 + (size_t)(g & 1) * stage_floats;
+      if (o0 + kCapsIlp < O) {
+        caps_stage_issue(a, b0, nimg, o0 + kCapsIlp, stage0 + (size_t)((g + 1) & 1) * stage_floats);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();                                   // this group's rows have landed for every thread
+      const float* srow0 = stage + (size_t)nimg * kCapsIlp * A;
 #pragma unroll
       for (int u = 0; u < kCapsIlp; ++u) {
         const int oo = o0 + u;
-        if (oo < O) {
+        if (active && oo < O) {
           const float* r = R + ((size_t)bi * O + oo) * 8;
           const size_t bov = ((size_t)b * O + oo) * V + v;
           const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
           CapsPair c;
-          caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, r, oo, v, bov, deform, learn, c);
+          caps_pair_fwd<kSim>(a, stage + ((size_t)bi * kCapsIlp + u) * A, srow0 + (size_t)u * V * 6, r, oo, v, bov, deform,
+                              learn, c);
           float q = 0.0f;
 #pragma unroll
           for (int p = 0; p < 6; ++p) {
@@ -198,6 +248,7 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
           if (o.mixing_log_prob) o.mixing_log_prob[bov1] = ml;             // normalised below
         }
       }
+      __syncthreads();                                   // everyone is done with this buffer before it is refilled
     }
     // merge the chains into chain 0 (which is never empty: it holds the dummy component)
     Lse post = post_c[0], mix = mix_c[0];
@@ -230,39 +281,41 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
       }
     }
 
-    const float lse = post.value();
-    const float inv_s = __frcp_rn(post.s);
-    if (o.log_prob_per_point) o.log_prob_per_point[bv] = lse;
-    if (o.soft_winner) {
-#pragma unroll
-      for (int p = 0; p < 6; ++p) o.soft_winner[bv * 6 + p] = sw[p] * inv_s;
-    }
-    if (o.soft_winner_presence) o.soft_winner_presence[bv] = swp * inv_s;
-    if (o.winner) {
-#pragma unroll
-      for (int p = 0; p < 6; ++p) o.winner[bv * 6 + p] = wv[p];
-    }
-    if (o.winner_presence) o.winner_presence[bv] = wvp;
-    if (o.winner_idx) o.winner_idx[bv] = widx;
-    if (o.is_from_capsule) o.is_from_capsule[bv] = widx / V;   // sic (object_decoder.py:334)
-    if (o.posterior_mixing_prob) {
-      for (int oo = 0; oo < O; ++oo) {
-        const size_t bov = ((size_t)b * O + oo) * V + v;
-        o.posterior_mixing_prob[bov] = expf(o.posterior_mixing_prob[bov] - lse);
+    if (active) {
+      const float lse = post.value();
+      const float inv_s = __frcp_rn(post.s);
+      if (o.log_prob_per_point) o.log_prob_per_point[bv] = lse;
+      if (o.soft_winner) {
+  #pragma unroll
+        for (int p = 0; p < 6; ++p) o.soft_winner[bv * 6 + p] = sw[p] * inv_s;
       }
-    }
-    const size_t dummy_row = ((size_t)b * (O + 1) + O) * V + v;
-    if (o.mixing_logit) o.mixing_logit[dummy_row] = kDummyLog;
-    if (o.mixing_log_prob) {
-      const float mlse = mix.value();
-      for (int oo = 0; oo < O; ++oo) {
-        const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
-        o.mixing_log_prob[bov1] -= mlse;
+      if (o.soft_winner_presence) o.soft_winner_presence[bv] = swp * inv_s;
+      if (o.winner) {
+  #pragma unroll
+        for (int p = 0; p < 6; ++p) o.winner[bv * 6 + p] = wv[p];
       }
-      o.mixing_log_prob[dummy_row] = kDummyLog - mlse;
+      if (o.winner_presence) o.winner_presence[bv] = wvp;
+      if (o.winner_idx) o.winner_idx[bv] = widx;
+      if (o.is_from_capsule) o.is_from_capsule[bv] = widx / V;   // sic (object_decoder.py:334)
+      if (o.posterior_mixing_prob) {
+        for (int oo = 0; oo < O; ++oo) {
+          const size_t bov = ((size_t)b * O + oo) * V + v;
+          o.posterior_mixing_prob[bov] = expf(o.posterior_mixing_prob[bov] - lse);
+        }
+      }
+      const size_t dummy_row = ((size_t)b * (O + 1) + O) * V + v;
+      if (o.mixing_logit) o.mixing_logit[dummy_row] = kDummyLog;
+      if (o.mixing_log_prob) {
+        const float mlse = mix.value();
+        for (int oo = 0; oo < O; ++oo) {
+          const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
+          o.mixing_log_prob[bov1] -= mlse;
+        }
+        o.mixing_log_prob[dummy_row] = kDummyLog - mlse;
+      }
+      red[i] = lse * pres;
+      red[n_items + i] = 0.5f * regsum;
     }
-    red[i] = lse * pres;
-    red[n_items + i] = 0.5f * regsum;
   }
   __syncthreads();
 
@@ -316,6 +369,8 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
   float* acc = R + (size_t)imgs_per_cta * O * 8;     // [imgs][O][8]: sum over v of (g_r[6], g_vp*pv, unused)
   float* scr = acc + (size_t)imgs_per_cta * O * 8;   // [kCapsIlp][7][kCapsThreads+1]
   constexpr int kScr = kCapsThreads + 1;
+  float* stage0 = scr + (size_t)kCapsIlp * 7 * kScr;                       // two staging buffers (see caps_stage_issue)
+  const size_t stage_floats = caps_stage_floats(imgs_per_cta, V);
   const bool deform = (a.flags & SCAE_CAPS_ALLOW_DEFORM) != 0;
   const bool learn = (a.flags & SCAE_CAPS_LEARN_VOTE_SCALE) != 0;
   const bool soft = up.g_soft_winner != nullptr || up.g_soft_winner_presence != nullptr;
@@ -358,7 +413,8 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
         for (int oo = 0; oo < O; ++oo) {
           const size_t bov = ((size_t)b * O + oo) * V + v;
           CapsPair c;
-          caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, R + ((size_t)bi * O + oo) * 8, oo, v, bov, deform, learn, c);
+          caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, a.cpr_static + (size_t)oo * V * 6, R + ((size_t)bi * O + oo) * 8, oo,
+                              v, bov, deform, learn, c);
           float h = up.g_posterior_mixing_prob ? __ldg(up.g_posterior_mixing_prob + bov) : 0.0f;
 #pragma unroll
           for (int p = 0; p < 6; ++p) h = fmaf(gsw[p], c.vt[p], h);
@@ -386,9 +442,20 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
     }
 
     // ---- pass B: per-pair gradients -------------------------------------------------------------------------------
-    for (int o0 = 0; o0 < O; o0 += kCapsIlp) {
-      // kCapsIlp objects per iteration as independent dependency chains (latency hiding at low occupancy); their
-      // per-(image, object) partial sums go through the shared-memory transpose together, one barrier pair per group
+    caps_stage_issue(a, b0, nimg, 0, stage0);
+    for (int o0 = 0, g = 0; o0 < O; o0 += kCapsIlp, ++g) {
+      // kCapsIlp objects per iteration as independent dependency chains (latency hiding at low occupancy); their rows
+      // arrive through the double-buffered staging area and their per-(image, object) partial sums go through the
+      // shared-memory transpose together, one barrier pair per group
+      float* stage = stage0 + (size_t)(g & 1) * stage_floats;
+      if (o0 + kCapsIlp < O) {
+        caps_stage_issue(a, b0, nimg, o0 + kCapsIlp, stage0 + (size_t)((g + 1) & 1) * stage_floats);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      const float* srow0 = stage + (size_t)nimg * kCapsIlp * A;
       float red7[kCapsIlp][7];
 #pragma unroll
       for (int u = 0; u < kCapsIlp; ++u)
@@ -404,7 +471,8 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
             const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
             const size_t bo = (size_t)b * O + oo;
             CapsPair c;
-            caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, r, oo, v, bov, deform, learn, c);
+            caps_pair_fwd<kSim>(a, stage + ((size_t)bi * kCapsIlp + u) * A, srow0 + (size_t)u * V * 6, r, oo, v, bov, deform,
+                                learn, c);
             const float post = __ldg(sv.posterior_mixing_prob + bov);
             float h = up.g_posterior_mixing_prob ? __ldg(up.g_posterior_mixing_prob + bov) : 0.0f;
             float diff[6], q = 0.0f;
@@ -625,7 +693,7 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_bwd(const sca
   const bool have_sw = up->g_soft_winner != nullptr;
 
   const int imgs = caps_imgs_per_cta(V);
-  const size_t smem = caps_bwd_smem_floats(imgs, O) * sizeof(float);
+  const size_t smem = caps_bwd_smem_floats(imgs, O, V) * sizeof(float);
   SCAE_REQUIRE(smem <= (size_t)max_smem_optin(), SCAE_ELIMIT, "caps bwd: O=%d needs %zu bytes of shared memory", O, smem);
   const bool sim = (a->flags & SCAE_CAPS_SIMILARITY) != 0;
   auto kern = sim ? caps_ll_bwd_kernel<true> : caps_ll_bwd_kernel<false>;

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_ll_bwd_gather_kernel(con
 constexpr int kScanThreads = 256;
 
 template <int C, bool kAlpha>
-__global__ void __launch_bounds__(kScanThreads, 3) tmpl_ll_bwd_scan_kernel(const scae_tmpl_args a,
+__global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan_kernel(const scae_tmpl_args a,
                                                                            const float* __restrict__ x,
                                                                            const float* __restrict__ gout,
                                                                            const float* __restrict__ cache,
@@ -632,7 +632,8 @@ static int tmpl_bwd_plan(const scae_tmpl_args* a, BwdPlan* p) {
   int per_sm = (int)(limit / smem);
   const int by_threads = 2048 / threads;
   if (per_sm > by_threads) per_sm = by_threads;
-  if (per_sm > 3) per_sm = 3;                      // compiled with __launch_bounds__(256, 3)
+  const int cap = a->C == 1 ? 4 : 3;               // compiled with __launch_bounds__(256, C == 1 ? 4 : 3)
+  if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   const long slots = (long)sm_count() * per_sm;
   g.grid = a->B < slots ? a->B : (int)slots;
