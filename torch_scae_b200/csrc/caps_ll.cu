@@ -28,16 +28,35 @@ struct CapsSmem {
   float* red;     // fwd: [2][imgs*V] per-point partials; bwd: scratch [7][kCapsThreads+1]
 };
 
-// One staging buffer holds, for the current group of kCapsIlp objects, the all_param rows of the CTA's images
-// ([imgs][kCapsIlp][A]) and the matching cpr_static rows ([kCapsIlp][V*6]).  Two buffers (double buffering).
-__host__ __device__ inline size_t caps_stage_floats(int imgs, int V) {
-  return (size_t)imgs * kCapsIlp * (8 * V + 7) + (size_t)kCapsIlp * V * 6;
+// One staging buffer holds, for the current group of kCapsIlp objects, every per-pair input of the CTA's images:
+//   prm   [imgs][kCapsIlp][A]   all_param rows              bv / bs [kCapsIlp][V]   bias_vote / bias_scale rows
+//   stc   [kCapsIlp][V*6]       cpr_static rows             nz      [imgs][kCapsIlp][V]  noise_vote (if given)
+//   post / gpost [imgs][kCapsIlp][V]  saved posterior and its upstream gradient (backward only)
+// Two buffers (double buffering).
+struct CapsStage {
+  const float *prm, *stc, *bv, *bs, *nz, *post, *gpost;
+};
+__host__ __device__ inline size_t caps_stage_floats(int imgs, int V, bool bwd) {
+  return (size_t)imgs * kCapsIlp * (8 * V + 7) + (size_t)kCapsIlp * V * 6 + 2 * (size_t)kCapsIlp * V +
+         (size_t)imgs * kCapsIlp * V * (bwd ? 3 : 1);
+}
+__device__ __forceinline__ CapsStage caps_stage_view(const float* stage, int imgs, int V) {
+  const int A = 8 * V + 7;
+  CapsStage s;
+  s.prm = stage;
+  s.stc = s.prm + (size_t)imgs * kCapsIlp * A;
+  s.bv = s.stc + (size_t)kCapsIlp * V * 6;
+  s.bs = s.bv + (size_t)kCapsIlp * V;
+  s.nz = s.bs + (size_t)kCapsIlp * V;
+  s.post = s.nz + (size_t)imgs * kCapsIlp * V;
+  s.gpost = s.post + (size_t)imgs * kCapsIlp * V;
+  return s;
 }
 __host__ __device__ inline size_t caps_fwd_smem_floats(int imgs, int O, int V) {
-  return (size_t)imgs * O * 8 + (size_t)imgs * O * (V | 1) + 2 * (size_t)imgs * V + 2 * caps_stage_floats(imgs, V);
+  return (size_t)imgs * O * 8 + (size_t)imgs * O * (V | 1) + 2 * (size_t)imgs * V + 2 * caps_stage_floats(imgs, V, false);
 }
 __host__ __device__ inline size_t caps_bwd_smem_floats(int imgs, int O, int V) {
-  return (size_t)imgs * O * 8 * 2 + (size_t)kCapsIlp * 7 * (kCapsThreads + 1) + 2 * caps_stage_floats(imgs, V);
+  return (size_t)imgs * O * 8 * 2 + (size_t)kCapsIlp * 7 * (kCapsThreads + 1) + 2 * caps_stage_floats(imgs, V, true);
 }
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
@@ -51,21 +70,28 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // Issues the asynchronous, fully coalesced copy of one object group into a staging buffer.  The rows of objects
-// o0 .. o0+nobj-1 of one image are contiguous in all_param, so each image is one run of nobj*A floats (4-byte cp.async:
-// rows are only 4-byte aligned because A = 8V+7 is odd).  Replaces per-thread loads with a 24-byte lane stride that
-// touched 24 sectors per warp-load (profiles/r01e: 13.9 M L1 sectors for 43 MB of parameters).
-__device__ __forceinline__ void caps_stage_issue(const scae_caps_args& a, int b0, int nimg, int o0, float* stage) {
+// o0 .. o0+nobj-1 of one image are contiguous in every source tensor, so each (tensor, image) is one run (4-byte
+// cp.async: all_param rows are only 4-byte aligned because A = 8V+7 is odd).  Replaces per-thread global loads whose
+// 24-byte lane stride touched 24 sectors per warp-load and whose latency sat on the critical path of every pair
+// (profiles/r01e: long_scoreboard 6.4 stall cycles per issue).
+__device__ __forceinline__ void caps_copy_run(float* dst, const float* src, int n) {
+  for (int e = threadIdx.x; e < n; e += kCapsThreads) cp_async4(dst + e, src + e);
+}
+__device__ __forceinline__ void caps_stage_issue(const scae_caps_args& a, const float* post, const float* gpost, int b0,
+                                                 int nimg, int imgs, int o0, float* stage) {
   const int O = a.O, V = a.V, A = 8 * V + 7;
   const int nobj = min(kCapsIlp, O - o0);
-  const int run = nobj * A;
+  const CapsStage s = caps_stage_view(stage, imgs, V);
   for (int bi = 0; bi < nimg; ++bi) {
-    const float* src = a.all_param + ((size_t)(b0 + bi) * O + o0) * A;
-    float* dst = stage + (size_t)bi * kCapsIlp * A;
-    for (int e = threadIdx.x; e < run; e += kCapsThreads) cp_async4(dst + e, src + e);
+    const size_t bo = (size_t)(b0 + bi) * O + o0;
+    caps_copy_run(const_cast<float*>(s.prm) + (size_t)bi * kCapsIlp * A, a.all_param + bo * A, nobj * A);
+    if (a.noise_vote) caps_copy_run(const_cast<float*>(s.nz) + (size_t)bi * kCapsIlp * V, a.noise_vote + bo * V, nobj * V);
+    if (post) caps_copy_run(const_cast<float*>(s.post) + (size_t)bi * kCapsIlp * V, post + bo * V, nobj * V);
+    if (gpost) caps_copy_run(const_cast<float*>(s.gpost) + (size_t)bi * kCapsIlp * V, gpost + bo * V, nobj * V);
   }
-  const float* ssrc = a.cpr_static + (size_t)o0 * V * 6;
-  float* sdst = stage + (size_t)nimg * kCapsIlp * A;
-  for (int e = threadIdx.x; e < nobj * V * 6; e += kCapsThreads) cp_async4(sdst + e, ssrc + e);
+  caps_copy_run(const_cast<float*>(s.stc), a.cpr_static + (size_t)o0 * V * 6, nobj * V * 6);
+  caps_copy_run(const_cast<float*>(s.bv), a.bias_vote + (size_t)o0 * V, nobj * V);
+  caps_copy_run(const_cast<float*>(s.bs), a.bias_scale + (size_t)o0 * V, nobj * V);
   cp_async_commit();
 }
 
@@ -101,12 +127,12 @@ struct CapsPair {
   float lv, pv, vp, u, sc;
 };
 
-// row: the object's all_param row [A]; srow: the object's cpr_static row [V*6] (staged in shared memory, or global)
+// Per-pair inputs, each pointing at the object's row (shared-memory staging buffer, or global memory):
+//   row [A] all_param, srow [V*6] cpr_static, bvote / bscale [V] biases, nvote [V] noise (nullable)
 template <bool kSim>
-__device__ __forceinline__ void caps_pair_fwd(const scae_caps_args& a, const float* row, const float* srow, const float* r,
-                                              int oo, int v, size_t bov, bool deform, bool learn, CapsPair& c) {
-  const int V = a.V;
-  const size_t ov = (size_t)oo * V + v;
+__device__ __forceinline__ void caps_pair_fwd(const float* row, const float* srow, const float* bvote, const float* bscale,
+                                              const float* nvote, const float* r, int V, int v, bool deform, bool learn,
+                                              CapsPair& c) {
   float t[6];
 #pragma unroll
   for (int p = 0; p < 6; ++p) {
@@ -121,11 +147,11 @@ __device__ __forceinline__ void caps_pair_fwd(const scae_caps_args& a, const flo
   c.vt[3] = r[3] * A_[0] + r[4] * A_[3];
   c.vt[4] = r[3] * A_[1] + r[4] * A_[4];
   c.vt[5] = r[3] * A_[2] + r[4] * A_[5] + r[5];
-  c.lv = row[6 * V + 7 + v] + __ldg(a.bias_vote + ov);
-  if (a.noise_vote) c.lv += __ldg(a.noise_vote + bov);
+  c.lv = row[6 * V + 7 + v] + bvote[v];
+  if (nvote) c.lv += nvote[v];
   c.pv = sigmoid_f(c.lv);
   c.vp = r[6] * c.pv;
-  c.u = row[7 * V + 7 + v] + __ldg(a.bias_scale + ov);
+  c.u = row[7 * V + 7 + v] + bscale[v];
   c.sc = learn ? softplus_f(c.u + 0.5f) + 1e-2f : 1.0f;
 }
 
@@ -143,7 +169,7 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
   float* vp_tile = R + (size_t)imgs_per_cta * O * 8;
   float* red = vp_tile + (size_t)imgs_per_cta * O * Vp;
   float* stage0 = red + 2 * (size_t)imgs_per_cta * V;                     // two staging buffers (see caps_stage_issue)
-  const size_t stage_floats = caps_stage_floats(imgs_per_cta, V);
+  const size_t stage_floats = caps_stage_floats(imgs_per_cta, V, true);
   const bool deform = (a.flags & SCAE_CAPS_ALLOW_DEFORM) != 0;
   const bool learn = (a.flags & SCAE_CAPS_LEARN_VOTE_SCALE) != 0;
 
@@ -189,17 +215,18 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
     for (int p = 0; p < 6; ++p) sw_c[0][p] = __ldg(a.dummy_vote + (size_t)v * 6 + p);
 
     // object groups stream through two shared-memory staging buffers filled by coalesced cp.async copies
-    caps_stage_issue(a, b0, nimg, 0, stage0);
+    caps_stage_issue(a, nullptr, nullptr, b0, nimg, imgs_per_cta, 0, stage0);
     for (int o0 = 0, g = 0; o0 < O; o0 += kCapsIlp, ++g) {
       float* stage = stage0 + (size_t)(g & 1) * stage_floats;
       if (o0 + kCapsIlp < O) {
-        caps_stage_issue(a, b0, nimg, o0 + kCapsIlp, stage0 + (size_t)((g + 1) & 1) * stage_floats);
+        caps_stage_issue(a, nullptr, nullptr, b0, nimg, imgs_per_cta, o0 + kCapsIlp,
+                         stage0 + (size_t)((g + 1) & 1) * stage_floats);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
       }
       __syncthreads();                                   // this group's rows have landed for every thread
-      const float* srow0 = stage + (size_t)nimg * kCapsIlp * A;
+      const CapsStage st = caps_stage_view(stage, imgs_per_cta, V);
 #pragma unroll
       for (int u = 0; u < kCapsIlp; ++u) {
         const int oo = o0 + u;
@@ -208,8 +235,9 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
           const size_t bov = ((size_t)b * O + oo) * V + v;
           const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
           CapsPair c;
-          caps_pair_fwd<kSim>(a, stage + ((size_t)bi * kCapsIlp + u) * A, srow0 + (size_t)u * V * 6, r, oo, v, bov, deform,
-                              learn, c);
+          caps_pair_fwd<kSim>(st.prm + ((size_t)bi * kCapsIlp + u) * A, st.stc + (size_t)u * V * 6, st.bv + (size_t)u * V,
+                              st.bs + (size_t)u * V, a.noise_vote ? st.nz + ((size_t)bi * kCapsIlp + u) * V : nullptr, r, V, v,
+                              deform, learn, c);
           float q = 0.0f;
 #pragma unroll
           for (int p = 0; p < 6; ++p) {
@@ -370,7 +398,7 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
   float* scr = acc + (size_t)imgs_per_cta * O * 8;   // [kCapsIlp][7][kCapsThreads+1]
   constexpr int kScr = kCapsThreads + 1;
   float* stage0 = scr + (size_t)kCapsIlp * 7 * kScr;                       // two staging buffers (see caps_stage_issue)
-  const size_t stage_floats = caps_stage_floats(imgs_per_cta, V);
+  const size_t stage_floats = caps_stage_floats(imgs_per_cta, V, true);
   const bool deform = (a.flags & SCAE_CAPS_ALLOW_DEFORM) != 0;
   const bool learn = (a.flags & SCAE_CAPS_LEARN_VOTE_SCALE) != 0;
   const bool soft = up.g_soft_winner != nullptr || up.g_soft_winner_presence != nullptr;
@@ -413,8 +441,10 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
         for (int oo = 0; oo < O; ++oo) {
           const size_t bov = ((size_t)b * O + oo) * V + v;
           CapsPair c;
-          caps_pair_fwd<kSim>(a, rowb + (size_t)oo * A, a.cpr_static + (size_t)oo * V * 6, R + ((size_t)bi * O + oo) * 8, oo,
-                              v, bov, deform, learn, c);
+          caps_pair_fwd<kSim>(rowb + (size_t)oo * A, a.cpr_static + (size_t)oo * V * 6, a.bias_vote + (size_t)oo * V,
+                              a.bias_scale + (size_t)oo * V,
+                              a.noise_vote ? a.noise_vote + ((size_t)b * O + oo) * V : nullptr,
+                              R + ((size_t)bi * O + oo) * 8, V, v, deform, learn, c);
           float h = up.g_posterior_mixing_prob ? __ldg(up.g_posterior_mixing_prob + bov) : 0.0f;
 #pragma unroll
           for (int p = 0; p < 6; ++p) h = fmaf(gsw[p], c.vt[p], h);
@@ -442,20 +472,21 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
     }
 
     // ---- pass B: per-pair gradients -------------------------------------------------------------------------------
-    caps_stage_issue(a, b0, nimg, 0, stage0);
+    caps_stage_issue(a, sv.posterior_mixing_prob, up.g_posterior_mixing_prob, b0, nimg, imgs_per_cta, 0, stage0);
     for (int o0 = 0, g = 0; o0 < O; o0 += kCapsIlp, ++g) {
       // kCapsIlp objects per iteration as independent dependency chains (latency hiding at low occupancy); their rows
       // arrive through the double-buffered staging area and their per-(image, object) partial sums go through the
       // shared-memory transpose together, one barrier pair per group
       float* stage = stage0 + (size_t)(g & 1) * stage_floats;
       if (o0 + kCapsIlp < O) {
-        caps_stage_issue(a, b0, nimg, o0 + kCapsIlp, stage0 + (size_t)((g + 1) & 1) * stage_floats);
+        caps_stage_issue(a, sv.posterior_mixing_prob, up.g_posterior_mixing_prob, b0, nimg, imgs_per_cta, o0 + kCapsIlp,
+                         stage0 + (size_t)((g + 1) & 1) * stage_floats);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
       }
       __syncthreads();
-      const float* srow0 = stage + (size_t)nimg * kCapsIlp * A;
+      const CapsStage st = caps_stage_view(stage, imgs_per_cta, V);
       float red7[kCapsIlp][7];
 #pragma unroll
       for (int u = 0; u < kCapsIlp; ++u)
@@ -471,10 +502,11 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_bwd_kernel(const scae_ca
             const size_t bov1 = ((size_t)b * (O + 1) + oo) * V + v;
             const size_t bo = (size_t)b * O + oo;
             CapsPair c;
-            caps_pair_fwd<kSim>(a, stage + ((size_t)bi * kCapsIlp + u) * A, srow0 + (size_t)u * V * 6, r, oo, v, bov, deform,
-                                learn, c);
-            const float post = __ldg(sv.posterior_mixing_prob + bov);
-            float h = up.g_posterior_mixing_prob ? __ldg(up.g_posterior_mixing_prob + bov) : 0.0f;
+            const size_t su = ((size_t)bi * kCapsIlp + u) * V;
+            caps_pair_fwd<kSim>(st.prm + ((size_t)bi * kCapsIlp + u) * A, st.stc + (size_t)u * V * 6, st.bv + (size_t)u * V,
+                                st.bs + (size_t)u * V, a.noise_vote ? st.nz + su : nullptr, r, V, v, deform, learn, c);
+            const float post = st.post[su + v];
+            float h = up.g_posterior_mixing_prob ? st.gpost[su + v] : 0.0f;
             float diff[6], q = 0.0f;
     #pragma unroll
             for (int p = 0; p < 6; ++p) {
