@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kCapsThreads) caps_ll_fwd_kernel(const scae_ca
   float* vp_tile = R + (size_t)imgs_per_cta * O * 8;
   float* red = vp_tile + (size_t)imgs_per_cta * O * Vp;
   float* stage0 = red + 2 * (size_t)imgs_per_cta * V;                     // two staging buffers (see caps_stage_issue)
-  const size_t stage_floats = caps_stage_floats(imgs_per_cta, V, true);
+  const size_t stage_floats = caps_stage_floats(imgs_per_cta, V, false);  // must match caps_fwd_smem_floats
   const bool deform = (a.flags & SCAE_CAPS_ALLOW_DEFORM) != 0;
   const bool learn = (a.flags & SCAE_CAPS_LEARN_VOTE_SCALE) != 0;
 
