@@ -138,16 +138,19 @@ def capsule_oracle(d, flags, which=CAPS_UP, dtype=torch.float64):
     return out
 
 
-def capsule_cuda(d, flags, which=CAPS_UP):
+def capsule_cuda(d, flags, which=CAPS_UP, part_grads=True, extra_bits=0):
+    """part_grads=False: x / presence are data (what SCAE training does: stop_grad_caps_target), which is what lets the
+    backward take the fast path (csrc/caps_ll2.cu); extra_bits: additional SCAE_CAPS_* flag bits (e.g. RELU_GRAD)."""
     from torch_scae_b200 import _lib, ops
     cast = lambda t: None if t is None else t.to(DEV, torch.float32).clone().requires_grad_(True)
+    data = lambda t: None if t is None else t.to(DEV, torch.float32).clone()
     leaf = dict(all_param=cast(d['all_param']), cpr_static=cast(d['cpr_static']), dummy_vote=cast(d['dummy_vote']),
-                x=cast(d['x']), presence=cast(d['presence']))
+                x=(cast if part_grads else data)(d['x']), presence=(cast if part_grads else data)(d['presence']))
     biases = [cast(b) for b in d['biases']]
     nz = lambda t: None if t is None else t.to(DEV, torch.float32)
     bits = (_lib.CAPS_SIMILARITY if flags['similarity'] else 0) \
         | (_lib.CAPS_LEARN_VOTE_SCALE if flags['learn_vote_scale'] else 0) \
-        | (_lib.CAPS_ALLOW_DEFORM if flags['allow_deformations'] else 0)
+        | (_lib.CAPS_ALLOW_DEFORM if flags['allow_deformations'] else 0) | extra_bits
     res = dict(zip(ops.CAPS_RETURNS, ops.CapsuleVoteLikelihood.apply(
         leaf['all_param'], leaf['cpr_static'], *biases, leaf['dummy_vote'], leaf['x'], leaf['presence'],
         nz(d['noise_caps']), nz(d['noise_vote']), bits)))

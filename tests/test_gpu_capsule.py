@@ -154,3 +154,103 @@ def test_full_size_properties():
     c = capsule_cuda(d2, DEFAULT, which)
     assert rel_err(c['g_all_param'], 2 * a['g_all_param']) < 1e-6
     assert rel_err(c['g_cpr_static'], 2 * a['g_cpr_static']) < 1e-5
+
+
+# ---- fast path (csrc/caps_ll2.cu): pair-parallel kernels, taken when x / presence are data (SCAE training) -------------
+
+FAST_UP = ('ll_per_example', 'reg_per_example', 'posterior_mixing_prob', 'caps_presence', 'vote_presence', 'scale',
+           'vote', 'presence_logit_per_caps', 'presence_logit_per_vote', 'mixing_logit')
+FAST_GRADS = ('g_all_param', 'g_cpr_static', 'g_b0', 'g_b1', 'g_b2', 'g_b3')
+
+
+@pytest.mark.parametrize('B,O,V', [(8, 32, 40),      # MNIST config, 16-byte aligned image blocks
+                                   (9, 10, 40),      # O*A*4 = 8 mod 16: blocks alternate between two alignments
+                                   (7, 35, 6),       # O*A odd: all four alignments, several objects per warp
+                                   (3, 5, 7),        # odd pair count: vote block leaves through the copy loop
+                                   (330, 10, 40),    # more images than SMs: persistent backward, double-buffered prefetch
+                                   (4, 32, 64),      # likelihood-stress config: single-stage backward (shared memory)
+                                   (2, 3, 130), (1, 1, 1)])
+def test_fast_path_vs_fp64_oracle(B, O, V):
+    d = _f32(make_capsule_inputs(B, O, V, seed=B * 1000 + O * 10 + V))
+    ref = capsule_oracle(d, DEFAULT, FAST_UP)
+    got = capsule_cuda(d, DEFAULT, FAST_UP, part_grads=False)
+    _compare(got, ref, FWD_KEYS, TOL_OUT, (B, O, V))
+    _compare(got, ref, FAST_GRADS, TOL_GRAD, (B, O, V))
+    assert float(got['g_dummy_vote'].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('flags', [dict(similarity=True, learn_vote_scale=False, allow_deformations=False),
+                                   dict(similarity=True, learn_vote_scale=True, allow_deformations=True),
+                                   dict(similarity=False, learn_vote_scale=False, allow_deformations=True)])
+@pytest.mark.parametrize('presence,noise', [(True, True), (False, False)])
+def test_fast_path_flag_and_optional_input_combinations(flags, presence, noise):
+    d = _f32(make_capsule_inputs(4, 7, 9, presence=presence, noise=noise, seed=7))
+    which = ('ll_per_example', 'reg_per_example', 'posterior_mixing_prob', 'caps_presence')
+    ref = capsule_oracle(d, flags, which)
+    got = capsule_cuda(d, flags, which, part_grads=False)
+    _compare(got, ref, FWD_KEYS, TOL_OUT, flags)
+    _compare(got, ref, FAST_GRADS, TOL_GRAD, flags)
+
+
+def test_fast_path_many_images_single_stage():
+    """stress shape with several images per persistent CTA: the single-stage refill path of the backward kernel"""
+    which = ('ll_per_example', 'reg_per_example', 'posterior_mixing_prob', 'caps_presence')
+    d = _f32(make_capsule_inputs(300, 32, 64, seed=5))
+    ref = capsule_oracle(d, DEFAULT, which)
+    got = capsule_cuda(d, DEFAULT, which, part_grads=False)
+    _compare(got, ref, ('ll_per_example', 'posterior_mixing_prob', 'caps_presence', 'vote'), TOL_OUT, 'stress')
+    _compare(got, ref, FAST_GRADS, TOL_GRAD, 'stress')
+
+
+def test_fast_path_fused_relu_mask():
+    """SCAE_CAPS_RELU_GRAD: g_all_param is masked by (all_param > 0) (the MLP's final ReLU, nn_ext.py:19-31) while the
+    gradients of cpr_static / biases still see the unmasked pre-activation gradient."""
+    from torch_scae_b200 import _lib
+    which = ('ll_per_example', 'reg_per_example', 'posterior_mixing_prob', 'caps_presence')
+    d = _f32(make_capsule_inputs(6, 10, 40, seed=21))
+    ref = capsule_oracle(d, DEFAULT, which)
+    got = capsule_cuda(d, DEFAULT, which, part_grads=False, extra_bits=_lib.CAPS_RELU_GRAD)
+    mask = (d['all_param'] > 0).double()
+    assert rel_err(got['g_all_param'], ref['g_all_param'] * mask) < TOL_GRAD
+    _compare(got, ref, ('g_cpr_static', 'g_b0', 'g_b1', 'g_b2', 'g_b3'), TOL_GRAD, 'relu')
+
+
+def test_fast_and_general_paths_agree(monkeypatch):
+    which = ('ll_per_example', 'reg_per_example', 'posterior_mixing_prob', 'caps_presence')
+    d = make_capsule_inputs(200, 32, 40, seed=9, dtype=torch.float32)
+    fast = capsule_cuda(d, DEFAULT, which, part_grads=False)
+    again = capsule_cuda(d, DEFAULT, which, part_grads=False)
+    for k in fast:                                           # deterministic: bit-identical reruns
+        assert torch.equal(fast[k], again[k]), k
+    monkeypatch.setenv('SCAE_CAPS_IMPL', 'v1')
+    general = capsule_cuda(d, DEFAULT, which, part_grads=False)
+    for k in FWD_KEYS:
+        assert rel_err(fast[k], general[k]) < 2e-5, k
+    for k in ('winner_idx', 'is_from_capsule') if 'winner_idx' in fast else ('is_from_capsule',):
+        assert torch.equal(fast[k], general[k]), k
+    for k in FAST_GRADS:
+        assert rel_err(fast[k], general[k]) < 2e-4, k
+
+
+def test_parameter_head_writes_kernel_layout():
+    """PerCapsuleMLP.forward_contiguous (strided-output batched GEMM + in-place ReLU) equals the plain bmm chain, values
+    and gradients, and yields the contiguous (B, O, A) block the fused kernel stages with bulk copies."""
+    from torch_scae_b200.object_decoder import PerCapsuleMLP
+    strict_fp32()
+    torch.manual_seed(0)
+    mlp = PerCapsuleMLP(10, [33, 128, 327], bias=False).to(DEV)
+    x = torch.randn(64, 10, 33, device=DEV, requires_grad=True)
+    w = torch.randn(64, 10, 327, device=DEV)
+    ref = mlp(x)
+    g_ref = torch.autograd.grad((ref * w).sum(), [x, mlp.w0, mlp.w1])
+    out = mlp.forward_contiguous(x)
+    assert out.is_contiguous() and out.shape == (64, 10, 327)
+    assert rel_err(out, ref) < 1e-6
+    g = torch.autograd.grad((out * w).sum(), [x, mlp.w0, mlp.w1])
+    for a_, b_ in zip(g, g_ref):
+        assert rel_err(a_, b_) < 1e-5
+    # gradient already masked by the consumer (what the fused kernel does with SCAE_CAPS_RELU_GRAD)
+    out2 = mlp.forward_contiguous(x, grad_is_masked=True)
+    g2 = torch.autograd.grad(out2, [x, mlp.w0, mlp.w1], grad_outputs=w * (out2 > 0))
+    for a_, b_ in zip(g2, g_ref):
+        assert rel_err(a_, b_) < 1e-5

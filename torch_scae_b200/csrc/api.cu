@@ -43,26 +43,40 @@ int max_smem_optin() {
   return n > 0 ? n : 48 * 1024;
 }
 
-// out[i] = sum_p partials[p][i], p ascending: deterministic.  One thread per column, coalesced across columns.
-__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partials, float* __restrict__ out,
-                                                          int n_parts, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-  int p = 0;
-  for (; p + 4 <= n_parts; p += 4) {
-    acc0 += partials[(size_t)(p + 0) * n + i];
-    acc1 += partials[(size_t)(p + 1) * n + i];
-    acc2 += partials[(size_t)(p + 2) * n + i];
-    acc3 += partials[(size_t)(p + 3) * n + i];
+// out[i] = sum_p partials[p][i] in a fixed order: deterministic.  A CTA owns 32 columns; its 16 warps take the rows
+// p = w, w+16, w+32, ... with eight independent accumulators (eight loads in flight per thread: the kernel is pure
+// latency), and the per-warp sums are combined in warp order.  Lanes are consecutive columns, so every row read is one
+// 128-byte line per warp.
+constexpr int kReduceWarps = 16;
+__global__ void __launch_bounds__(32 * kReduceWarps) reduce_rows_kernel(const float* __restrict__ partials,
+                                                                        float* __restrict__ out, int n_parts, int n) {
+  __shared__ float part[kReduceWarps][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (i < n) {
+    int p = w;
+    for (; p + 7 * kReduceWarps < n_parts; p += 8 * kReduceWarps) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += partials[(size_t)(p + k * kReduceWarps) * n + i];
+    }
+    for (; p < n_parts; p += kReduceWarps) acc[0] += partials[(size_t)p * n + i];
   }
-  for (; p < n_parts; ++p) acc0 += partials[(size_t)p * n + i];
-  out[i] = (acc0 + acc1) + (acc2 + acc3);
+  part[w][lane] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  __syncthreads();
+  if (w == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kReduceWarps; ++k) t += part[k][lane];
+    out[i] = t;
+  }
 }
 
 int launch_reduce_rows(const float* partials, float* out, int n_parts, int n, cudaStream_t stream) {
   if (n <= 0) return SCAE_OK;
-  reduce_rows_kernel<<<(n + 255) / 256, 256, 0, stream>>>(partials, out, n_parts, n);
+  reduce_rows_kernel<<<(n + 31) / 32, 32 * kReduceWarps, 0, stream>>>(partials, out, n_parts, n);
   SCAE_CUDA_TRY(cudaGetLastError());
   return SCAE_OK;
 }

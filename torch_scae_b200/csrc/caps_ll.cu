@@ -13,7 +13,7 @@
 // A CTA covers floor(128 / V) whole images.
 //
 // Per-image algorithmic HBM traffic and the roofline are in DESIGN.md section 5.
-#include "common.cuh"
+#include "caps_common.cuh"
 
 namespace scae {
 
@@ -118,14 +118,6 @@ __device__ __forceinline__ void caps_phase0(const scae_caps_args& a, int b0, int
     if (logit_out) logit_out[(size_t)b * O + oo] = lc;
   }
 }
-
-// everything the forward computes for one (b, o, v) pair
-struct CapsPair {
-  PoseAffine pa;   // object-part transform (cpr) with its intermediates
-  float dyn[6];    // cpr_dynamic as used (zeros when deformations are disabled)
-  float vt[6];     // vote
-  float lv, pv, vp, u, sc;
-};
 
 // Per-pair inputs, each pointing at the object's row (shared-memory staging buffer, or global memory):
 //   row [A] all_param, srow [V*6] cpr_static, bvote / bscale [V] biases, nvote [V] noise (nullable)
@@ -683,6 +675,11 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_fwd(const sca
   if (rc != SCAE_OK) return rc;
   SCAE_REQUIRE(out != nullptr, SCAE_EINVAL, "caps fwd: outputs is NULL");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!caps_force_v1()) {   // fast path (caps_ll2.cu) when the image's working set fits in shared memory
+    bool handled = false;
+    rc = caps2_fwd(a, out, stream, &handled);
+    if (rc != SCAE_OK || handled) return rc;
+  }
   const int imgs = caps_imgs_per_cta(a->V);
   const size_t smem = caps_fwd_smem_floats(imgs, a->O, a->V) * sizeof(float);
   SCAE_REQUIRE(smem <= (size_t)max_smem_optin(), SCAE_ELIMIT, "caps fwd: O=%d, V=%d need %zu bytes of shared memory",
@@ -699,7 +696,9 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_fwd(const sca
 extern "C" __attribute__((visibility("default"))) size_t scae_caps_ll_bwd_workspace_bytes(const scae_caps_args* a) {
   if (a == nullptr || a->B <= 0 || a->O <= 0 || a->V <= 0) return 0;
   const size_t n = (size_t)a->O * (8 * a->V + 7);
-  return (caps_split(a->B) * n + (size_t)a->B * a->V * 6) * sizeof(float);
+  const size_t general = (caps_split(a->B) * n + (size_t)a->B * a->V * 6) * sizeof(float);
+  const size_t fast = caps2_bwd_workspace_bytes(a);
+  return general > fast ? general : fast;
 }
 
 extern "C" __attribute__((visibility("default"))) int scae_caps_ll_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_caps_upstream* up,
@@ -717,6 +716,12 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_bwd(const sca
   SCAE_REQUIRE(workspace && workspace_bytes >= scae_caps_ll_bwd_workspace_bytes(a), SCAE_EINVAL,
                "caps bwd: workspace too small (%zu < %zu)", workspace_bytes, scae_caps_ll_bwd_workspace_bytes(a));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!caps_force_v1()) {   // fast path (caps_ll2.cu): training-step upstream set, working set fits in shared memory
+    bool handled = false;
+    rc = caps2_bwd(a, saved, up, g_all_param, g_shared, g_dummy_vote, g_x, g_presence, workspace, workspace_bytes, stream,
+                   &handled);
+    if (rc != SCAE_OK || handled) return rc;
+  }
   const int B = a->B, O = a->O, V = a->V, A = 8 * V + 7, n = O * A;
   const int nsplit = caps_split(B);
   float* partials = static_cast<float*>(workspace);

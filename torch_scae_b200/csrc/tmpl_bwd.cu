@@ -378,6 +378,11 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
   float* red = smem + (size_t)nwarps * 2 * atlas_floats;  // [64] block-reduction scratch
   float* xs = red + 64;                                   // [W] affine_grid base coordinates
   float* ys = xs + a.W;                                   // [H]
+  // [C][H*W] records {x, upstream gradient, cached numerator lse, cached denominator lse} of the current image: every
+  // warp of the CTA works on the same image, so the four global loads (and their 64-bit address arithmetic) that each
+  // (template, pass) used to repeat are paid once per image
+  const bool staged = g.pix_floats > 0;
+  float4* PIX = reinterpret_cast<float4*>(smem + (((size_t)nwarps * 2 * atlas_floats + 64 + a.W + a.H + 3) & ~(size_t)3));
   for (int e = lane; e < 2 * atlas_floats; e += 32) atlas[e] = 0.0f;
   for (int e = threadIdx.x; e < a.W; e += blockDim.x) xs[e] = base_coord(e, a.W);
   for (int e = threadIdx.x; e < a.H; e += blockDim.x) ys[e] = base_coord(e, a.H);
@@ -395,9 +400,11 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
   __syncthreads();   // partial row zeroed before any warp accumulates into it
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-    // background component: once per pixel, by warp 0
-    if (warp == 0) {
-      for (int p = lane; p < HW; p += 32) {
+    // background component, once per pixel -- spread over the whole CTA -- and the pixel records
+    if (staged) __syncthreads();                       // the previous image's records are no longer read
+    if (staged || warp == 0) {
+      const int p_first = staged ? (int)threadIdx.x : lane, p_step = staged ? (int)blockDim.x : 32;
+      for (int p = p_first; p < HW; p += p_step) {
         float xv[C], G[C], Nc[C], Dc[C];
         const size_t px0 = (size_t)b * C * HW + p;
 #pragma unroll
@@ -407,10 +414,12 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
           G[c] = __ldg(gout + px0 + (size_t)c * HW);
           Nc[c] = __ldg(cache + cx);
           Dc[c] = __ldg(cache + cx + (size_t)C * HW);
+          if (staged) PIX[c * HW + p] = make_float4(xv[c], G[c], Nc[c], Dc[c]);
         }
         bwd_background<C, kAlpha>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
       }
     }
+    if (staged) __syncthreads();
     for (int m = warp; m < a.M; m += nwarps) {
       // ---- per-template setup (all lanes compute the same coefficients) -----------------------------------------
       const float* pp = a.pose + ((size_t)b * a.M + m) * 6;
@@ -439,14 +448,25 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
         const int p = p0 + lane;
         const bool valid = p < HW;
         float xv[C], G[C], Nc[C], Dc[C];
+        if (staged) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const size_t px = (size_t)b * C * HW + (size_t)c * HW + p;
-          const size_t cx = (size_t)b * 2 * C * HW + (size_t)c * HW + p;
-          xv[c] = valid ? __ldg(x + px) : 0.0f;
-          G[c] = valid ? __ldg(gout + px) : 0.0f;        // G = 0 switches a dead lane off
-          Nc[c] = valid ? __ldg(cache + cx) : 0.0f;
-          Dc[c] = valid ? __ldg(cache + cx + (size_t)C * HW) : 0.0f;
+          for (int c = 0; c < C; ++c) {
+            const float4 r4 = valid ? PIX[c * HW + p] : make_float4(0.f, 0.f, 0.f, 0.f);   // G = 0 switches a dead lane off
+            xv[c] = r4.x;
+            G[c] = r4.y;
+            Nc[c] = r4.z;
+            Dc[c] = r4.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const size_t px = (size_t)b * C * HW + (size_t)c * HW + p;
+            const size_t cx = (size_t)b * 2 * C * HW + (size_t)c * HW + p;
+            xv[c] = valid ? __ldg(x + px) : 0.0f;
+            G[c] = valid ? __ldg(gout + px) : 0.0f;
+            Nc[c] = valid ? __ldg(cache + cx) : 0.0f;
+            Dc[c] = valid ? __ldg(cache + cx + (size_t)C * HW) : 0.0f;
+          }
         }
         const float X = xs[valid ? j : 0], Y = ys[valid ? i : 0];
         Tap t;
@@ -627,6 +647,16 @@ static int tmpl_bwd_plan(const scae_tmpl_args* a, BwdPlan* p) {
     threads /= 2;                                   // very large templates: fewer warps per CTA
   }
   SCAE_REQUIRE(smem <= limit, SCAE_ELIMIT, "tmpl bwd: a %dx%d template does not fit in shared memory", a->h, a->w);
+  // per-image pixel records in shared memory when at least two CTAs per SM still fit (each CTA also pays 1 KB reserved)
+  {
+    const size_t pix_bytes = (size_t)4 * a->C * a->H * a->W * sizeof(float) + 16;
+    const char* e = getenv("SCAE_TMPL_BWD_STAGE");
+    const bool allow = e == nullptr || strcmp(e, "0") != 0;
+    if (allow && 2 * (smem + pix_bytes + 1024) <= limit + 1024) {
+      g.pix_floats = 4 * a->C * a->H * a->W;
+      smem += pix_bytes;
+    }
+  }
   g.threads = threads;
   g.smem_bytes = smem;
   int per_sm = (int)(limit / smem);

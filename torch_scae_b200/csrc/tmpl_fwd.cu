@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_ll_fwd_kernel(const scae
   constexpr int kPad = TT::kPad, PIX = TT::kPixMax, ND = kAlpha ? 1 : C;
   extern __shared__ __align__(16) float smem[];
   const TmplSmem s = tmpl_carve(smem, a, g, 0);
+  int* tab = reinterpret_cast<int*>(s.red + 64);   // [C*h*w] staging table
   tmpl_prologue(s, a, g, 0);
+  build_stage_table(tab, C, a.h, a.w, g.pw, kPad);
   const TmplScalars sc = tmpl_scalars(a);
   const int HW = a.H * a.W;
   const int col = threadIdx.x % g.tw, rg = threadIdx.x / g.tw;
@@ -122,6 +124,10 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_ll_fwd_kernel(const scae
   const float lim_x = (float)a.w + 2.5f, lim_y = (float)a.h + 2.5f;
   const unsigned row = (unsigned)(g.pw * kPad), tex_stride = (unsigned)(g.ph * g.pw * kPad);
   const unsigned base0 = 0u - kMagicBits * (row + (unsigned)kPad);
+  // all templates in one chunk: the alpha logits (shared by the whole batch) are staged once per CTA, not per image
+  const bool one_chunk = g.mc >= a.M;
+  __syncthreads();                                  // atlas zeroed, table built
+  if (kAlpha && one_chunk) stage_alpha_tab<C>(s.atlas, tab, a, 0, a.M, (int)tex_stride);
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     __syncthreads();
@@ -157,7 +163,8 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_ll_fwd_kernel(const scae
         for (int m0 = 0; m0 < a.M; m0 += g.mc) {
           const int mc = min(g.mc, a.M - m0);
           __syncthreads();
-          stage_atlas<C, kAlpha>(s.atlas, a, b, m0, mc, g.pw, g.ph);
+          stage_templates_tab<C>(s.atlas, tab, a, b, m0, mc, (int)tex_stride);
+          if (kAlpha && !one_chunk) stage_alpha_tab<C>(s.atlas, tab, a, m0, mc, (int)tex_stride);
           __syncthreads();
           for (int mm = 0; mm < mc; ++mm) {
             const float* t8 = s.tp + (size_t)(m0 + mm) * 8;
@@ -351,7 +358,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_fwd(const sca
   if (rc != SCAE_OK) return rc;
   SCAE_REQUIRE(x && log_prob, SCAE_EINVAL, "tmpl fwd: x and log_prob are required");
   TmplGeom g;
-  rc = tmpl_geometry(a, 0, 0, kFwdSmemBudget, &g);
+  rc = tmpl_geometry(a, 0, (size_t)a->C * a->h * a->w * sizeof(int), kFwdSmemBudget, &g);   // + the staging table
   if (rc != SCAE_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool alpha = a->mode == SCAE_TMPL_MODE_ALPHA;

@@ -20,6 +20,38 @@ from .attrdict import AttrDict
 from .general_utils import prod
 
 
+class _ParamHead(torch.autograd.Function):
+    """Last Linear + ReLU of the per-capsule parameter MLPs, producing ``all_param`` directly in the contiguous
+    (B, O, A) layout the fused kernel stages with bulk copies.
+
+    The batched GEMM writes through a strided (O, B, A) view of the output buffer (row stride O*A, batch stride A), so
+    the (O,B,A)->(B,O,A) transpose copy of the plain bmm chain disappears; the backward feeds the kernel's (B,O,A)
+    gradient to the two GEMMs through the same strided view.  With ``grad_is_masked`` the caller promises that the
+    incoming gradient already carries the ReLU mask (the kernel applies it, SCAE_CAPS_RELU_GRAD), so no separate
+    threshold pass runs.
+    """
+
+    @staticmethod
+    def forward(ctx, h, w, grad_is_masked):
+        n, B, _ = h.shape                              # h (O, B, H), w (O, A, H)
+        out = h.new_empty(B, n, w.shape[1])
+        torch.bmm(h, w.transpose(1, 2), out=out.transpose(0, 1))
+        torch.relu_(out)
+        ctx.save_for_backward(h, w, out)
+        ctx.grad_is_masked = grad_is_masked
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w, out = ctx.saved_tensors
+        if not ctx.grad_is_masked:
+            g = g * (out > 0)
+        gt = g.transpose(0, 1)                         # (O, B, A) view, unit stride in A: a legal GEMM operand
+        gh = torch.bmm(gt, w) if ctx.needs_input_grad[0] else None
+        gw = torch.bmm(gt.transpose(1, 2), h) if ctx.needs_input_grad[1] else None
+        return gh, gw, None
+
+
 class PerCapsuleMLP(nn.Module):
     """``n`` independent Linear/ReLU chains (final ReLU included, like nn_ext.MLP) as batched matmuls.
 
@@ -38,17 +70,26 @@ class PerCapsuleMLP(nn.Module):
             if bias:
                 self.register_parameter(f'b{j}', nn.Parameter(torch.empty(n, fan_out).uniform_(-bound, bound)))
 
-    def forward(self, x):
-        """x (B, n, in) -> (B, n, out)."""
+    def _hidden(self, x, n_layers):
         h = x.transpose(0, 1)                         # (n, B, in)
-        for j in range(self.n_layers):
+        for j in range(n_layers):
             w = getattr(self, f'w{j}')
             if self.has_bias:
                 h = torch.baddbmm(getattr(self, f'b{j}').unsqueeze(1), h, w.transpose(1, 2))
             else:
                 h = torch.bmm(h, w.transpose(1, 2))
             h = torch.relu(h)
-        return h.transpose(0, 1)
+        return h
+
+    def forward(self, x):
+        """x (B, n, in) -> (B, n, out)."""
+        return self._hidden(x, self.n_layers).transpose(0, 1)
+
+    def forward_contiguous(self, x, grad_is_masked=False):
+        """Same values as ``forward`` for a bias-free last layer, as a contiguous (B, n, out) tensor (see _ParamHead)."""
+        assert not self.has_bias
+        h = self._hidden(x, self.n_layers - 1).contiguous()
+        return _ParamHead.apply(h, getattr(self, f'w{self.n_layers - 1}'), grad_is_masked)
 
     # ---- reference-compatible (de)serialisation ---------------------------------------------------------------------
     def _named(self):
@@ -117,18 +158,23 @@ class CapsuleLayer(nn.Module):
         self.cpr_static = nn.Parameter(torch.zeros(1, n_caps, n_votes, P))
 
     def kernel_flags(self):
+        """Flag word for the fused kernel.  RELU_GRAD: the backward kernel masks g_all_param with (all_param > 0), the
+        backward of the final ReLU of ``caps_mlps`` (nn_ext.py:19-31), which ``predict_all_param`` then skips."""
         return (_lib.CAPS_SIMILARITY if self.similarity_transform else 0) \
             | (_lib.CAPS_LEARN_VOTE_SCALE if self.learn_vote_scale else 0) \
-            | (_lib.CAPS_ALLOW_DEFORM if self.allow_deformations else 0)
+            | (_lib.CAPS_ALLOW_DEFORM if self.allow_deformations else 0) | _lib.CAPS_RELU_GRAD
 
-    def predict_all_param(self, feature):
-        """(B,O,F) -> all_param (B,O,A): the per-capsule MLP half of the reference's forward (:137-158)."""
+    def predict_all_param(self, feature, grad_is_masked=False):
+        """(B,O,F) -> all_param (B,O,A), contiguous: the per-capsule MLP half of the reference's forward (:137-158).
+
+        ``grad_is_masked=True`` is for callers that hand all_param to the fused kernel with ``kernel_flags()`` (and to
+        nothing else): the kernel's gradient then already contains the final ReLU's mask."""
         if self.caps_dropout_rate != 0.0:
             # the reference deletes `caps_exist` before using it (object_decoder.py:152,:196): unsupported there too
             raise NameError("name 'caps_exist' is not defined")
         raw = self.mlps(feature)
         ones = raw.new_ones(*raw.shape[:2], 1)
-        return self.caps_mlps(torch.cat([raw, ones], -1))
+        return self.caps_mlps.forward_contiguous(torch.cat([raw, ones], -1), grad_is_masked)
 
     def draw_noise(self, all_param):
         """The two presence-logit noises, drawn like the reference (always on, also in eval mode; :198-212)."""
@@ -149,7 +195,7 @@ class CapsuleLayer(nn.Module):
         """Stand-alone use (no likelihood).  Returns the reference's keys, with ``vote`` as (B,O,V,3,3)."""
         if parent_transform is not None or parent_presence is not None:
             raise NotImplementedError('hierarchical parent_transform / parent_presence are not supported')
-        all_param = self.predict_all_param(feature)
+        all_param = self.predict_all_param(feature, grad_is_masked=True)
         B, O, _ = all_param.shape
         V = self.n_votes
         noise_caps, noise_vote = self.draw_noise(all_param)
@@ -231,7 +277,7 @@ class CapsuleObjectDecoder(nn.Module):
         noise (used by parity tests to inject the reference's draws).
         """
         layer = self.capsule_layer
-        all_param = layer.predict_all_param(obj_encoding)
+        all_param = layer.predict_all_param(obj_encoding, grad_is_masked=True)
         noise_caps, noise_vote = noise if noise is not None else layer.draw_noise(all_param)
         out = dict(zip(ops.CAPS_RETURNS, ops.CapsuleVoteLikelihood.apply(
             all_param, layer.cpr_static, *layer.caps_bias_list, self.dummy_vote, part_pose, part_presence,
