@@ -48,9 +48,9 @@ def algorithmic_bytes(M=40, C=1, h=11, w=11, H=40, W=40, O=32):
     caps_in = 4 * O * A + 4 * O * (V + 1) + 4 * 7 * V                     # all_param, noises, x + presence
     # API-complete forward: every tensor of the reference's result dict
     f2 = caps_in + 4 * (O * V * (6 + 7) + 2 * (O + 1) * V + 2 * O + O + V * (6 + 1 + 6 + 1 + 1) + 2) + 8 * 2 * V
-    # backward: inputs + saved posterior/lse + upstream (posterior, caps_presence, ll, reg) + g_all_param (written by the
-    # kernel, re-read and re-written by the finalisation pass)
-    b2 = caps_in + 4 * (O * V + V) + 4 * (O * V + O + 2) + 4 * O * A * 3
+    # backward: inputs + saved posterior/lse + upstream (posterior, caps_presence, ll, reg) + g_all_param, written once
+    # (ReLU mask, regulariser and the batch sums for cpr_static / biases are fused into the kernel)
+    b2 = caps_in + 4 * (O * V + V) + 4 * (O * V + O + 2) + 4 * O * A
     return dict(scae_tmpl_ll_fwd=f1, scae_tmpl_ll_bwd=b1, scae_caps_ll_fwd=f2, scae_caps_ll_bwd=b2)
 
 
@@ -275,14 +275,19 @@ def run_gpu(args):
     peak, peak_src = measured_peaks()
     bytes_per_image = algorithmic_bytes(O=args.n_obj_caps)
     kernels = {}
+    plumbing = {}
     launches = 0
     for name, (calls, n_launch, total_ms) in kstats.items():
         avg_ms = total_ms / calls
+        launches += n_launch
+        if name not in bytes_per_image:        # small kernels serving the callers of the hot paths (e.g. scae_colsum)
+            plumbing[name] = dict(calls_per_step=calls // steps, launches_per_step=n_launch // steps,
+                                  ms_per_step=round(total_ms / steps, 4))
+            continue
         gbs = bytes_per_image[name] * B / (avg_ms * 1e-3) / 1e9
         kernels[name] = dict(ms=round(avg_ms, 4), launches_per_call=n_launch // calls,
                              algorithmic_bytes=bytes_per_image[name] * B, achieved_gbs=round(gbs, 1),
                              frac_of_hbm_peak=round(gbs / peak, 4), share_of_step=round(avg_ms / ms_step, 4))
-        launches += n_launch
     dominant = max(kernels, key=lambda k: kernels[k]['ms'])
     traffic = ncu_traffic().get(dominant)
     roofline = dict(kernel=dominant, bound='hbm', achieved=kernels[dominant]['achieved_gbs'], peak=peak, unit='GB/s',
@@ -310,7 +315,8 @@ def run_gpu(args):
                 e2e=dict(value=round(e2e_value, 1), unit=UNIT, ms_per_step=round(ms_e2e, 4),
                          h2d_bytes_per_step=int(host_image.numel() * 4 + host_label.numel() * 8) * world,
                          d2h_bytes_per_step=4 * world),
-                gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu, clocks=clocks, extra=extra)
+                gpu_launches=launches, roofline=roofline, kernels=kernels, plumbing_kernels=plumbing, cpu_baseline=cpu,
+                clocks=clocks, extra=extra)
     print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -42,6 +42,9 @@ int scae_abi_version(void);
 const char* scae_last_error(void);
 /* Compiled-for architecture string, e.g. "sm_100a". */
 const char* scae_build_arch(void);
+/* Number of CUDA kernels this library has launched from the calling thread so far (monotonic; bench.py's launch
+ * accounting reads it before and after each entry point). */
+unsigned long long scae_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Hot path 1: template warp + per-pixel template-mixture Gaussian log-likelihood
@@ -183,6 +186,17 @@ size_t scae_caps_ll_bwd_workspace_bytes(const scae_caps_args* a);
 int scae_caps_ll_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_caps_upstream* up,
                      float* g_all_param, float* g_shared, float* g_dummy_vote, float* g_x, float* g_presence,
                      void* workspace, size_t workspace_bytes, scae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Plumbing for the callers of hot path 2: column sums of a tall-skinny matrix.
+ * out[cols] = sum over rows of x[rows, cols] (row-major), deterministic (two fixed-order stages).  This is the bias
+ * gradient of the set transformer's 16- and 256-wide linear layers applied to B*M rows (reference
+ * set_transformer.py:24-223; autograd computes it with a generic reduction there), which a generic reduction
+ * kernel runs 5-8x below the HBM rate for such shapes.  cols must divide 256 or be a multiple of 256.
+ * ------------------------------------------------------------------------------------------------------------ */
+size_t scae_colsum_workspace_bytes(long rows, int cols); /* 0 when the shape is not supported */
+int scae_colsum(const float* x, long rows, int cols, float* out, void* workspace, size_t workspace_bytes,
+                scae_stream_t stream);
 
 #ifdef __cplusplus
 }

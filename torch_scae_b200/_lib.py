@@ -5,7 +5,7 @@ is built in-tree by ``torch_scae_b200.build`` (``__graft_entry__.build()``); on 
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_int, c_size_t, c_uint, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_int, c_long, c_size_t, c_uint, c_ulonglong, c_void_p
 
 from .build import LIB_PATH
 
@@ -64,6 +64,7 @@ SYMBOLS = {
     'scae_abi_version': (c_int, []),
     'scae_last_error': (c_char_p, []),
     'scae_build_arch': (c_char_p, []),
+    'scae_launch_count': (c_ulonglong, []),
     'scae_tmpl_ll_fwd': (c_int, [POINTER(TmplArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'scae_tmpl_ll_bwd_workspace_bytes': (c_size_t, [POINTER(TmplArgs)]),
     'scae_tmpl_ll_bwd': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 10 + [c_size_t, c_void_p]),
@@ -72,6 +73,8 @@ SYMBOLS = {
     'scae_caps_ll_bwd_workspace_bytes': (c_size_t, [POINTER(CapsArgs)]),
     'scae_caps_ll_bwd': (c_int, [POINTER(CapsArgs), POINTER(CapsSaved), POINTER(CapsUpstream)] + [c_void_p] * 6 +
                          [c_size_t, c_void_p]),
+    'scae_colsum_workspace_bytes': (c_size_t, [c_long, c_int]),
+    'scae_colsum': (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -7,6 +7,9 @@
 namespace scae {
 
 static thread_local char g_error[512] = "";
+static thread_local unsigned long long g_launches = 0;
+
+void note_launch() { ++g_launches; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -57,12 +60,13 @@ __global__ void __launch_bounds__(32 * kReduceWarps) reduce_rows_kernel(const fl
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (i < n) {
-    int p = w;
-    for (; p + 7 * kReduceWarps < n_parts; p += 8 * kReduceWarps) {
+    for (int p = w; p < n_parts; p += 8 * kReduceWarps) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += partials[(size_t)(p + k * kReduceWarps) * n + i];
+      for (int k = 0; k < 8; ++k) {   // predicated, so the last round also keeps all of its loads in flight
+        const int q = p + k * kReduceWarps;
+        acc[k] += q < n_parts ? partials[(size_t)q * n + i] : 0.0f;
+      }
     }
-    for (; p < n_parts; p += kReduceWarps) acc[0] += partials[(size_t)p * n + i];
   }
   part[w][lane] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
   __syncthreads();
@@ -77,8 +81,52 @@ __global__ void __launch_bounds__(32 * kReduceWarps) reduce_rows_kernel(const fl
 int launch_reduce_rows(const float* partials, float* out, int n_parts, int n, cudaStream_t stream) {
   if (n <= 0) return SCAE_OK;
   reduce_rows_kernel<<<(n + 31) / 32, 32 * kReduceWarps, 0, stream>>>(partials, out, n_parts, n);
+  note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   return SCAE_OK;
+}
+
+// ---- column sums of a tall-skinny matrix --------------------------------------------------------------------------
+// x [rows, cols] row-major -> partial[split][cols]; a second reduce_rows pass sums the splits (fixed order).
+// A CTA of 256 threads owns a tile of W = min(cols, 256) columns and a slab of rows; thread t sits on column t % W and
+// walks rows t / W, t / W + 256 / W, ...: for cols <= 256 the CTA reads its slab as one contiguous stream.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ partial, long rows,
+                                                     int cols, int W, long rows_per_split) {
+  __shared__ float part[256];
+  const int t = threadIdx.x;
+  const int rpi = 256 / W;                              // rows per iteration
+  const int col = blockIdx.x * W + (t % W);
+  const long r0 = (long)blockIdx.y * rows_per_split, r1 = min(rows, r0 + rows_per_split);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (long r = r0 + t / W; r < r1; r += 8L * rpi) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long q = r + (long)k * rpi;
+      acc[k] += q < r1 ? __ldg(x + q * cols + col) : 0.0f;
+    }
+  }
+  part[t] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  __syncthreads();
+  if (t < W) {
+    float s = 0.f;
+    for (int k = 0; k < rpi; ++k) s += part[t + k * W];
+    partial[(size_t)blockIdx.y * cols + col] = s;
+  }
+}
+
+static bool colsum_shape_ok(long rows, int cols) {
+  return rows > 0 && cols > 0 && ((cols <= 256 && 256 % cols == 0) || cols % 256 == 0);
+}
+static int colsum_splits(long rows, int cols) {
+  const int tiles = cols <= 256 ? 1 : cols / 256;
+  const int rpi = cols <= 256 ? 256 / cols : 1;
+  long s = (4L * sm_count() + tiles - 1) / tiles;       // about four CTAs per SM
+  const long max_s = (rows + 8L * rpi - 1) / (8L * rpi); // at least one full round of loads per CTA
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  return (int)s;
 }
 
 }  // namespace scae
@@ -91,5 +139,31 @@ SCAE_EXPORT int scae_abi_version(void) { return SCAE_B200_ABI_VERSION; }
 SCAE_EXPORT const char* scae_last_error(void) { return scae::g_error; }
 
 SCAE_EXPORT const char* scae_build_arch(void) { return "sm_100a"; }
+
+SCAE_EXPORT unsigned long long scae_launch_count(void) { return scae::g_launches; }
+
+SCAE_EXPORT size_t scae_colsum_workspace_bytes(long rows, int cols) {
+  if (!scae::colsum_shape_ok(rows, cols)) return 0;
+  return (size_t)scae::colsum_splits(rows, cols) * cols * sizeof(float);
+}
+
+SCAE_EXPORT int scae_colsum(const float* x, long rows, int cols, float* out, void* workspace, size_t workspace_bytes,
+                            scae_stream_t stream_) {
+  using namespace scae;
+  SCAE_REQUIRE(x && out, SCAE_EINVAL, "colsum: x and out are required");
+  SCAE_REQUIRE(colsum_shape_ok(rows, cols), SCAE_ELIMIT,
+               "colsum: cols=%d must divide 256 or be a multiple of 256 (rows=%ld)", cols, rows);
+  const int splits = colsum_splits(rows, cols);
+  SCAE_REQUIRE(workspace && workspace_bytes >= (size_t)splits * cols * sizeof(float), SCAE_EINVAL,
+               "colsum: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int W = cols <= 256 ? cols : 256;
+  const long rows_per_split = (rows + splits - 1) / splits;
+  dim3 grid(cols <= 256 ? 1 : cols / 256, splits);
+  colsum_kernel<<<grid, 256, 0, stream>>>(x, static_cast<float*>(workspace), rows, cols, W, rows_per_split);
+  note_launch();
+  SCAE_CUDA_TRY(cudaGetLastError());
+  return launch_reduce_rows(static_cast<const float*>(workspace), out, splits, cols, stream);
+}
 
 }  // extern "C"

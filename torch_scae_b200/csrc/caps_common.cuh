@@ -61,16 +61,18 @@ __device__ __forceinline__ float softplus_fast(float x) {
 
 __device__ __forceinline__ float log_safe_fast(float p) { return p < kLogSafeEps ? kLogSafeFloor : __logf(p); }
 
-// pose_affine_fwd with the fast sigmoid / tanh (sincosf stays: theta = 2 pi t reaches tens of radians)
+// pose_affine_fwd with the fast sigmoid / tanh.  The rotation angle is theta = 2 pi t (cv_ops.py:45), so
+// sin / cos (theta) = sinpi / cospi (2 t): sincospif reduces its argument exactly (2 t is exact in fp32), has no slow
+// path and no stack frame, and is closer to the fp64 value than sincosf(fl(t * fl(2 pi))) -- the difference to the
+// latter is the reference's own rounding of theta, about |theta| * 9e-8.
 template <bool kSimilarity>
 __device__ __forceinline__ void pose_affine_fast(const float t[6], PoseAffine& o) {
   o.sx = sigmoid_fast(t[0]) + 1e-2f;
   o.sy = sigmoid_fast(t[1]) + 1e-2f;
-  const float theta = t[2] * kTwoPi;
   o.sh = tanh5_fast(t[3]);
   o.tx = tanh5_fast(t[4]);
   o.ty = tanh5_fast(t[5]);
-  sincosf(theta, &o.s, &o.c);
+  sincospif(2.0f * t[2], &o.s, &o.c);
   if (kSimilarity) {
     o.a[0] = o.sx * o.c;
     o.a[1] = -o.sx * o.s;

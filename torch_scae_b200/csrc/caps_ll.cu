@@ -689,6 +689,7 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_fwd(const sca
   auto kern = sim ? caps_ll_fwd_kernel<true> : caps_ll_fwd_kernel<false>;
   if (smem > 48 * 1024) SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kCapsThreads, smem, stream>>>(*a, *out, imgs);
+  note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   return SCAE_OK;
 }
@@ -737,12 +738,14 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_bwd(const sca
   if (smem > 48 * 1024) SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CapsBwdOut out{g_all_param, g_x, g_presence, (want_dummy && have_sw) ? dummy_rows : nullptr};
   kern<<<(B + imgs - 1) / imgs, kCapsThreads, smem, stream>>>(*a, *saved, *up, out, imgs);
+  note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
 
   const int rows_per_split = (B + nsplit - 1) / nsplit;
   dim3 grid((n + 255) / 256, nsplit);
   caps_bwd_finalize_kernel<<<grid, 256, 0, stream>>>(g_all_param, a->all_param, up->g_reg_per_example, partials, B, O, V,
                                                      a->flags, rows_per_split);
+  note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   rc = launch_reduce_rows(partials, g_shared, nsplit, n, stream);
   if (rc != SCAE_OK) return rc;

@@ -27,7 +27,7 @@
 namespace scae {
 
 constexpr int kF2MaxThreads = 512;   // forward: 2 CTAs per SM (<= 64 registers per thread)
-constexpr int kB2MaxThreads = 512;   // backward: 1 persistent CTA per SM
+constexpr int kB2MaxThreads = 640;   // backward: 1 persistent CTA per SM (<= 102 registers per thread)
 constexpr int kIntMax = 0x7fffffff;
 
 __host__ __device__ inline int round_up4(int n) { return (n + 3) & ~3; }
@@ -834,19 +834,20 @@ static int carveout_percent(size_t smem_bytes, int ctas) {
   return pct > 100 ? 100 : pct;
 }
 
-// largest multiple of 32 in [lo, hi] that wastes the fewest thread slots over ceil(n / T) passes; ties -> larger T
+// Threads per CTA for a loop of n pairs: the largest multiple of 32 in [lo, hi] whose thread-slot efficiency
+// n / (ceil(n / T) * T) is within 6 % of the best one -- these kernels are latency bound, so warps count for more than
+// the last few percent of lane utilisation.
 static int pick_threads(int n, int lo, int hi) {
-  int best = hi;
   double best_eff = -1.0;
   for (int t = hi; t >= lo; t -= 32) {
-    const int passes = (n + t - 1) / t;
-    const double eff = (double)n / ((double)passes * t);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = t;
-    }
+    const double eff = (double)n / ((double)((n + t - 1) / t) * t);
+    if (eff > best_eff) best_eff = eff;
   }
-  return best;
+  for (int t = hi; t >= lo; t -= 32) {
+    const double eff = (double)n / ((double)((n + t - 1) / t) * t);
+    if (eff >= 0.94 * best_eff) return t;
+  }
+  return hi;
 }
 
 static bool caps2_shape_ok(const scae_caps_args* a) {
@@ -868,6 +869,7 @@ int caps2_fwd(const scae_caps_args* a, const scae_caps_outputs* out, cudaStream_
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent(smem, 2)));
   kern<<<a->B, threads, smem, stream>>>(*a, *out, L);
+  note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   *handled = true;
   return SCAE_OK;
@@ -896,7 +898,7 @@ int caps2_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_
       (up->g_posterior_mixing_prob && !aligned16(up->g_posterior_mixing_prob)))
     return SCAE_OK;
   const int O = a->O, V = a->V, A = 8 * V + 7, n = O * A;
-  const int threads = pick_threads(O * V, 384, kB2MaxThreads);
+  const int threads = pick_threads(O * V, 384, kB2MaxThreads);   // e.g. 640 for 1280 pairs: two full passes
   if (V * 8 + O * 4 > kSmallMax * threads) return SCAE_OK;
   const bool noise = a->noise_vote != nullptr, have_gpost = up->g_posterior_mixing_prob != nullptr;
   Caps2BwdLayout L = caps2_bwd_layout(O, V, noise, have_gpost, 2);
@@ -912,6 +914,7 @@ int caps2_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_
   float* partials = static_cast<float*>(workspace);
   Caps2BwdOut out{g_all_param, g_presence, partials};
   kern<<<grid, threads, smem, stream>>>(*a, *saved, *up, out, L);
+  note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   int rc = launch_reduce_rows(partials, g_shared, grid, n, stream);
   if (rc != SCAE_OK) return rc;

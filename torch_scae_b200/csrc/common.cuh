@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);   // records the message, returns SCAE_ECUDA
 int sm_count();                                   // SM count of the current device (cached per device)
 int max_smem_optin();                             // max dynamic shared memory per block (opt-in) of the device
+void note_launch();                               // counts one kernel launch of this library (scae_launch_count())
 
 #define SCAE_CUDA_TRY(expr)                                        \
   do {                                                             \

@@ -712,11 +712,13 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_bwd(
       rc = tmpl_prepare_kernel(kern, g.smem_bytes);
       if (rc != SCAE_OK) return rc;
       kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, x, grad_log_prob, cache, out, g);
+      note_launch();
     } else {
       auto kern = tmpl_ll_bwd_scan_kernel<kC, kA>;
       rc = tmpl_prepare_kernel(kern, g.smem_bytes);
       if (rc != SCAE_OK) return rc;
       kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, x, grad_log_prob, cache, out, g);
+      note_launch();
     }
   });
   SCAE_CUDA_TRY(cudaGetLastError());

@@ -367,6 +367,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_fwd(const sca
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
     if (rc != SCAE_OK) return rc;
     kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, x, log_prob, ll, cache, g);
+    note_launch();
   });
   SCAE_CUDA_TRY(cudaGetLastError());
   return SCAE_OK;
@@ -388,6 +389,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_render(const sca
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
     if (rc != SCAE_OK) return rc;
     kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, transformed_templates, mixing_logits, mode, mean, g);
+    note_launch();
   });
   SCAE_CUDA_TRY(cudaGetLastError());
   return SCAE_OK;

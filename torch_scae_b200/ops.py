@@ -42,16 +42,19 @@ class KernelTimer:
         return out
 
 
-def _timed(name, launches, fn, *args):
-    """Calls a C-ABI entry point, bracketing it with CUDA events when a KernelTimer is active."""
+def _timed(name, fn, *args):
+    """Calls a C-ABI entry point, bracketing it with CUDA events when a KernelTimer is active; the number of kernels
+    the call launched comes from the library's own counter (scae_launch_count)."""
     t = KernelTimer.active
     if t is None:
         return fn(*args)
+    lib = _lib.load()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    before = lib.scae_launch_count()
     start.record()
     rc = fn(*args)
     end.record()
-    t.records.setdefault(name, []).append((start, end, launches))
+    t.records.setdefault(name, []).append((start, end, lib.scae_launch_count() - before))
     return rc
 
 
@@ -64,6 +67,23 @@ def _f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+def colsum(x2d):
+    """Sum over the rows of a contiguous fp32 CUDA matrix (rows, cols) -> (cols,) through scae_colsum: the bias gradient
+    of the set transformer's tall-skinny linear layers.  Shapes the kernel does not cover use torch.sum (same values up
+    to summation order; this is host-side plumbing, not one of the two hot paths)."""
+    lib = _lib.load()
+    rows, cols = x2d.shape
+    ws_bytes = lib.scae_colsum_workspace_bytes(rows, cols) if x2d.is_cuda and x2d.dtype == torch.float32 else 0
+    if ws_bytes == 0:
+        return x2d.sum(0)
+    x2d = x2d.contiguous()
+    out = torch.empty(cols, device=x2d.device, dtype=torch.float32)
+    ws = torch.empty(ws_bytes, device=x2d.device, dtype=torch.uint8)
+    check(_timed('scae_colsum', lib.scae_colsum, ptr(x2d), rows, cols, ptr(out), ptr(ws), ws_bytes, _stream()),
+          'scae_colsum')
+    return out
 
 
 # =================================================================================================================
@@ -108,7 +128,7 @@ class TemplateMixtureLogProb(torch.autograd.Function):
         log_prob = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
         ll = torch.empty(B, device=x.device, dtype=torch.float32)
         cache = torch.empty(B, 2, C, H, W, device=x.device, dtype=torch.float32)
-        check(_timed('scae_tmpl_ll_fwd', 1, lib.scae_tmpl_ll_fwd, ctypes.byref(args), ptr(x), ptr(log_prob), ptr(ll),
+        check(_timed('scae_tmpl_ll_fwd', lib.scae_tmpl_ll_fwd, ctypes.byref(args), ptr(x), ptr(log_prob), ptr(ll),
                      ptr(cache), _stream()), 'scae_tmpl_ll_fwd')
         ctx.save_for_backward(*[t for t in tensors if t is not None], cache)
         ctx.present = [t is not None for t in tensors]
@@ -146,7 +166,7 @@ class TemplateMixtureLogProb(torch.autograd.Function):
         ws_bytes = lib.scae_tmpl_ll_bwd_workspace_bytes(ctypes.byref(args))
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         # kernel launches: the backward kernel + the partial-sum reductions (alpha gradient, scalar gradients)
-        check(_timed('scae_tmpl_ll_bwd', 3 if g_alpha is not None else 2, lib.scae_tmpl_ll_bwd, ctypes.byref(args),
+        check(_timed('scae_tmpl_ll_bwd', lib.scae_tmpl_ll_bwd, ctypes.byref(args),
                      ptr(x), ptr(g), ptr(cache), ptr(g_templates), ptr(g_pose), ptr(g_presence), ptr(g_bg_image),
                      ptr(g_alpha), ptr(g_scalars), ptr(ws), ws_bytes, _stream()), 'scae_tmpl_ll_bwd')
 
@@ -226,7 +246,7 @@ class CapsuleVoteLikelihood(torch.autograd.Function):
         args = _caps_args(all_param, cpr_static, (b0, b1, b2, b3), noise_caps, noise_vote, x, presence, dummy_vote,
                           flags)
         outs = CapsOutputs(*[ptr(out[k]) for k in CAPS_OUTPUT_FIELDS])
-        check(_timed('scae_caps_ll_fwd', 1, lib.scae_caps_ll_fwd, ctypes.byref(args), ctypes.byref(outs), _stream()),
+        check(_timed('scae_caps_ll_fwd', lib.scae_caps_ll_fwd, ctypes.byref(args), ctypes.byref(outs), _stream()),
               'scae_caps_ll_fwd')
         inputs = (all_param, cpr_static, b0, b1, b2, b3, dummy_vote, x, presence, noise_caps, noise_vote)
         ctx.present = [t is not None for t in inputs]
@@ -264,7 +284,7 @@ class CapsuleVoteLikelihood(torch.autograd.Function):
         ws_bytes = lib.scae_caps_ll_bwd_workspace_bytes(ctypes.byref(args))
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         # kernel launches: backward kernel + finalize + reduction of the shared-parameter partials (+ dummy-vote sum)
-        check(_timed('scae_caps_ll_bwd', 3 + (1 if g_dummy is not None else 0), lib.scae_caps_ll_bwd,
+        check(_timed('scae_caps_ll_bwd', lib.scae_caps_ll_bwd,
                      ctypes.byref(args), ctypes.byref(sv), ctypes.byref(up), ptr(g_all), ptr(g_shared), ptr(g_dummy),
                      ptr(g_x), ptr(g_presence), ptr(ws), ws_bytes, _stream()), 'scae_caps_ll_bwd')
         g_static = g_shared[:, :6 * V].reshape(cpr_static.shape)

@@ -43,7 +43,8 @@ class _SplitKLinear(torch.autograd.Function):
             else:
                 gw = g2.t() @ x2
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0)
+            from . import ops                      # column sums at the HBM rate (csrc/api.cu::colsum_kernel)
+            gb = ops.colsum(g2)
         return gx, gw, gb
 
 
