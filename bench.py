@@ -166,7 +166,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import torch.distributed as dist
-    from torch_scae_b200 import ddp, factory, ops
+    from torch_scae_b200 import ddp, factory, graph, ops
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -189,7 +189,9 @@ def run_gpu(args):
     model = factory.make_scae(model_params(args.n_obj_caps)).to(dev).train()
     ddp.broadcast_parameters(model)
     bucket = ddp.FlatGradBucket(model)
-    opt = torch.optim.RMSprop(model.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2, foreach=True)
+    # capturable: the optimizer step is part of the captured CUDA graph (no host-side step counters)
+    opt = torch.optim.RMSprop(model.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2, foreach=True,
+                              capturable=True)
     torch.manual_seed(42 + rank)                            # different synthetic shard per rank
     host_image = torch.rand(B, 1, 40, 40).pin_memory()
     host_label = torch.randint(0, 10, (B,)).pin_memory()
@@ -227,19 +229,37 @@ def run_gpu(args):
         step(image, label)
     assert bucket.check_views(), 'gradient views were replaced; flat bucket all-reduce would be stale'
 
+    # The whole step (zero, forward, loss, backward, optimizer; the all-reduce stays eager between two graphs when
+    # world > 1) replayed as a CUDA graph: torch_scae_b200/graph.py.  --no-graph keeps the eager launches.
+    graphed, graph_note = None, 'disabled (--no-graph)'
+    if not args.no_graph:
+        try:
+            graphed = graph.GraphedTrainStep(model, opt, bucket, image, label)
+            graph_note = 'whole step captured' if world == 1 else 'fwd+bwd graph, eager NCCL all-reduce, optimizer graph'
+        except Exception as exc:                            # noqa: BLE001 - report and fall back to eager launches
+            graphed, graph_note = None, f'capture failed, eager launches: {type(exc).__name__}: {exc}'[:300]
+            torch.cuda.synchronize()
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # (1) device-resident throughput, with per-entry-point kernel timing
+    # (1) device-resident throughput.  The per-entry-point kernel timing brackets every C-ABI call with CUDA events on
+    # the launching stream, which only exists for eager launches: with a captured step the headline is the graph replay
+    # and the kernel durations come from an eager pass over the same step right after it.
     with ops.KernelTimer() as timer:
-        ms_step = timed(lambda: step(image, label), steps)
+        ms_eager = timed(lambda: step(image, label), steps if graphed is None else min(steps, 20))
     kstats = timer.summary()
+    eager_steps = steps if graphed is None else min(steps, 20)
+    ms_step = timed(lambda: graphed(), steps) if graphed is not None else ms_eager
 
     # (2) end to end: pinned host batch -> device every step, loss read back to the host every step
     def e2e_step():
-        img = host_image.to(dev, non_blocking=True)
-        lab = host_label.to(dev, non_blocking=True)
-        loss = step(img, lab)
+        if graphed is not None:
+            loss = graphed(host_image, host_label, non_blocking=True)
+        else:
+            img = host_image.to(dev, non_blocking=True)
+            lab = host_label.to(dev, non_blocking=True)
+            loss = step(img, lab)
         host_loss.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()           # the user reads the loss every step
 
@@ -252,6 +272,7 @@ def run_gpu(args):
     extra = {}
     if rank == 0 and not args.no_extra and world == 1:
         del opt, bucket
+        graphed = None                                      # releases the captured graphs and their pool
         m2 = factory.make_scae(model_params(10)).to(dev).train()
         b2 = ddp.FlatGradBucket(m2)
         o2 = torch.optim.RMSprop(m2.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2, foreach=True)
@@ -279,15 +300,15 @@ def run_gpu(args):
     launches = 0
     for name, (calls, n_launch, total_ms) in kstats.items():
         avg_ms = total_ms / calls
-        launches += n_launch
+        launches += (n_launch // eager_steps) * steps      # launches of OUR kernels inside the timed region of `value`
         if name not in bytes_per_image:        # small kernels serving the callers of the hot paths (e.g. scae_colsum)
-            plumbing[name] = dict(calls_per_step=calls // steps, launches_per_step=n_launch // steps,
-                                  ms_per_step=round(total_ms / steps, 4))
+            plumbing[name] = dict(calls_per_step=calls // eager_steps, launches_per_step=n_launch // eager_steps,
+                                  ms_per_step=round(total_ms / eager_steps, 4))
             continue
         gbs = bytes_per_image[name] * B / (avg_ms * 1e-3) / 1e9
         kernels[name] = dict(ms=round(avg_ms, 4), launches_per_call=n_launch // calls,
                              algorithmic_bytes=bytes_per_image[name] * B, achieved_gbs=round(gbs, 1),
-                             frac_of_hbm_peak=round(gbs / peak, 4), share_of_step=round(avg_ms / ms_step, 4))
+                             frac_of_hbm_peak=round(gbs / peak, 4), share_of_step=round(avg_ms / ms_eager, 4))
     dominant = max(kernels, key=lambda k: kernels[k]['ms'])
     traffic = ncu_traffic().get(dominant)
     roofline = dict(kernel=dominant, bound='hbm', achieved=kernels[dominant]['achieved_gbs'], peak=peak, unit='GB/s',
@@ -308,7 +329,8 @@ def run_gpu(args):
                 ms_per_step=round(ms_step, 4), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
                 data='synthetic',
                 config=dict(workload=workload_name(args.n_obj_caps, B), n_obj_caps=args.n_obj_caps,
-                            global_batch=B * world, parallelism=f'dp{world}', tf32=False,
+                            global_batch=B * world, parallelism=f'dp{world}', tf32=False, cuda_graph=graph_note,
+                            ms_per_step_eager=round(ms_eager, 4),
                             l2_policy='per-step working set (>190 MB of activations per 1024 images) exceeds the 126 MB L2',
                             note="BASELINE.json's parenthetical says 10 obj caps; the reference's mnist.yaml:4 says 32 "
                                  "(used here); the 10-capsule variant is under extra.n_obj_caps_10"),
@@ -347,6 +369,7 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=128, help='batch of the bounded CPU sample (BASELINE configs[0])')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -1,0 +1,84 @@
+"""CUDA-graph replay of the train step (torch_scae_b200/graph.py) against the same steps launched eagerly."""
+import copy
+
+import pytest
+import torch
+
+from gpu_util import DEV, strict_fp32
+
+pytestmark = pytest.mark.gpu
+
+
+def _model():
+    from torch_scae_b200 import factory
+    torch.manual_seed(7)
+    model = factory.make_scae(dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=32,
+                                   scae_params=dict(reconstruct_alternatives=False)))
+    # no random draws inside the step, so that eager launches and graph replays can be compared exactly
+    model.part_encoder.noise_scale = 0.
+    model.obj_decoder.capsule_layer.noise_type = None
+    return model.to(DEV).train()
+
+
+def test_graph_replay_matches_eager_steps():
+    from torch_scae_b200 import ddp, graph
+    strict_fp32()
+    B, n_steps = 64, 3
+    g = torch.Generator().manual_seed(3)
+    images = [torch.rand(B, 1, 40, 40, generator=g).to(DEV) for _ in range(n_steps)]
+    labels = [torch.randint(0, 10, (B,), generator=g).to(DEV) for _ in range(n_steps)]
+
+    init = None
+
+    def make():
+        model = _model()
+        if init is not None:
+            model.load_state_dict(init)      # (the template initialiser draws from numpy's RNG)
+        bucket = ddp.FlatGradBucket(model)
+        opt = torch.optim.RMSprop(model.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / B ** 2, foreach=True,
+                                  capturable=True)
+        return model, bucket, opt
+
+    # eager
+    model_e, bucket_e, opt_e = make()
+    init = copy.deepcopy(model_e.state_dict())
+    losses_e = []
+    for img, lab in zip(images, labels):
+        bucket_e.zero()
+        res = model_e(img)
+        loss, _ = model_e.loss(res, img, lab)
+        loss.backward()
+        opt_e.step()
+        losses_e.append(float(loss.detach()))
+
+    # graph: construction warms up with real steps, then must hand the model back untouched
+    model_g, bucket_g, opt_g = make()
+    step = graph.GraphedTrainStep(model_g, opt_g, bucket_g, images[0], labels[0])
+    for k, v in model_g.state_dict().items():
+        assert torch.equal(v, init[k]), f'{k} was changed by the graph warm-up'
+    losses_g = [float(step(img, lab)) for img, lab in zip(images, labels)]
+    assert bucket_g.check_views()
+
+    for le, lg in zip(losses_e, losses_g):
+        assert abs(le - lg) <= 1e-5 * abs(le), (losses_e, losses_g)
+    moved = 0.0
+    for (k, pe), pg in zip(model_e.state_dict().items(), model_g.state_dict().values()):
+        assert torch.allclose(pe, pg, rtol=0, atol=2e-6), k
+        moved = max(moved, float((pe - init[k]).abs().max()))
+    assert moved > 1e-5          # the steps did train
+
+
+def test_graph_step_draws_fresh_noise_on_every_replay():
+    from torch_scae_b200 import ddp, factory, graph
+    torch.manual_seed(11)
+    model = factory.make_scae(dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=32,
+                                   scae_params=dict(reconstruct_alternatives=False))).to(DEV).train()
+    bucket = ddp.FlatGradBucket(model)
+    opt = torch.optim.RMSprop(model.parameters(), lr=0.0, momentum=0.9, eps=1e-6, foreach=True, capturable=True)
+    image = torch.rand(32, 1, 40, 40, device=DEV)
+    label = torch.randint(0, 10, (32,), device=DEV)
+    step = graph.GraphedTrainStep(model, opt, bucket, image, label)
+    a = float(step(image, label))
+    b = float(step(image, label))
+    assert a == a and b == b
+    assert a != b                # lr = 0: only the presence noises differ between the two replays
