@@ -30,12 +30,11 @@ struct TexTraits {
 struct TmplGeom {
   int tw, k, ppt, threads;
   int tiles_x, tiles_y;
-  int mc;             // templates per shared-memory chunk
+  int mc;             // forward: templates per shared-memory chunk; backward: templates per warp per work unit
   int pw, ph;         // padded atlas width / height
   int atlas_floats;   // floats of one atlas (mc templates), rounded up to a multiple of 4 to keep 16-byte alignment
-  int gbuf_floats;    // backward (gather): floats of the per-pixel gradient buffer, mc * H * W * kPad (multiple of 4)
-  int split;          // backward (gather): lanes cooperating on one texel
-  int pix_floats;     // backward (scan): floats of the per-image pixel record tile (0 = read x / grad / cache from global)
+  int pix_floats;     // backward: floats of the per-image pixel record tile (0 = read x / grad / cache from global)
+  int groups;         // backward: template groups per image (work unit = image x group of `warps per CTA` templates)
   int grid;
   size_t smem_bytes;
 };

@@ -74,8 +74,8 @@ int tmpl_geometry(const scae_tmpl_args* a, size_t per_tmpl_extra_bytes, size_t f
   g->tiles_x = (a->W + tw - 1) / tw;
   g->pw = a->w + 4;
   g->ph = a->h + 4;
-  g->gbuf_floats = 0;
-  g->split = 1;
+  g->pix_floats = 0;
+  g->groups = 1;
 
   const size_t atlas_tmpl = (size_t)g->pw * g->ph * tmpl_texel_floats(a) * sizeof(float);
   const size_t per_tmpl = atlas_tmpl + per_tmpl_extra_bytes;
