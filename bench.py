@@ -54,6 +54,19 @@ def algorithmic_bytes(M=40, C=1, h=11, w=11, H=40, W=40, O=32):
     return dict(scae_tmpl_ll_fwd=f1, scae_tmpl_ll_bwd=b1, scae_caps_ll_fwd=f2, scae_caps_ll_bwd=b2)
 
 
+# Path 1 is bound by the SM issue rate, not by HBM: work units = (M+1) * H * W (pixel, component)
+# pairs per image and an ALGORITHMIC lane-instruction count per unit -- 50 for the forward (coordinates, floor/weights,
+# four taps, two bilinear blends, two streaming-logsumexp updates; SURVEY's figure) and 120 for the backward (the
+# forward recomputation + responsibilities + coordinate/texel gradients + the 8-way transposed-bilinear scatter).
+# t_issue = units * instr / (SMs * 128 lanes * f_clk) is the time at a perfect issue rate.
+ISSUE_LANE_INSTR = dict(scae_tmpl_ll_fwd=50, scae_tmpl_ll_bwd=120)
+
+
+def issue_roof_ms(name, batch, sm_mhz, M=40, H=40, W=40, sms=148):
+    units = (M + 1) * H * W * batch
+    return units * ISSUE_LANE_INSTR[name] / (sms * 128 * sm_mhz * 1e6) * 1e3
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -308,7 +321,13 @@ def run_gpu(args):
         gbs = bytes_per_image[name] * B / (avg_ms * 1e-3) / 1e9
         kernels[name] = dict(ms=round(avg_ms, 4), launches_per_call=n_launch // calls,
                              algorithmic_bytes=bytes_per_image[name] * B, achieved_gbs=round(gbs, 1),
-                             frac_of_hbm_peak=round(gbs / peak, 4), share_of_step=round(avg_ms / ms_eager, 4))
+                             frac_of_hbm_peak=round(gbs / peak, 4), share_of_step=round(avg_ms / ms_step, 4))
+        if name in ISSUE_LANE_INSTR:
+            t_issue = issue_roof_ms(name, B, (clocks or {}).get('sm_mhz') or 1965)
+            kernels[name].update(binding_roof='sm issue rate', issue_roof_ms=round(t_issue, 4),
+                                 frac_of_issue_roof=round(t_issue / avg_ms, 3))
+        else:
+            kernels[name].update(binding_roof='hbm')
     dominant = max(kernels, key=lambda k: kernels[k]['ms'])
     traffic = ncu_traffic().get(dominant)
     roofline = dict(kernel=dominant, bound='hbm', achieved=kernels[dominant]['achieved_gbs'], peak=peak, unit='GB/s',

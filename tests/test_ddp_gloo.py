@@ -63,3 +63,50 @@ def test_flat_bucket_allreduce_world2(tmp_path):
     res = torch.load(out)
     assert res['same'], 'ranks diverged'
     assert res['err'] < 1e-6, res
+
+
+# ---- batch-global sparsity statistics: sync_batch_stats=True == single process, global batch ----
+def _sparsity_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from torch_scae_b200 import object_decoder as od
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(5)
+    full = torch.rand(12, 7, dtype=torch.float64)                  # caps_presence of the global batch (B=12, O=7)
+    weights = torch.rand(4, dtype=torch.float64)
+    results = {}
+    for kind in ('l2', 'entropy', 'kl'):
+        # sharded: each rank sees 6 examples; losses weighted like SCAE.loss, gradients averaged like FlatGradBucket
+        local = full[rank * 6:(rank + 1) * 6].clone().requires_grad_(True)
+        within, between = od.sparsity_loss(kind, local, n_classes=3, sync_batch_stats=True)
+        (weights[0] * within + weights[1] * between).backward()
+        grad = local.grad / world                                  # all_reduce_mean of parameter gradients
+        parts = [torch.zeros_like(grad) for _ in range(world)]
+        dist.all_gather(parts, grad)
+        stats = torch.stack([within.detach(), between.detach()])
+        dist.all_reduce(stats)                                     # within: mean of shard means; between: same on all ranks
+        if rank == 0:
+            ref_in = full.clone().requires_grad_(True)
+            rw, rb = od.sparsity_loss(kind, ref_in, n_classes=3)
+            (weights[0] * rw + weights[1] * rb).backward()
+            results[kind] = dict(
+                grad_err=float((torch.cat(parts) - ref_in.grad).abs().max() / ref_in.grad.abs().max()),
+                within_err=float((stats[0] / world - rw).abs()), between_err=float((stats[1] / world - rb).abs()))
+    # and the default (per-shard statistics, the reference's behaviour under Lightning DDP) stays collective-free
+    local = full[rank * 6:(rank + 1) * 6].clone()
+    _, b_local = od.sparsity_loss('l2', local, n_classes=3)
+    if rank == 0:
+        results['local_between'] = float(b_local)
+        results['expected_local_between'] = float(torch.mean((local.sum(0) - 6 / 3) ** 2))
+        torch.save(results, out)
+    dist.destroy_process_group()
+
+
+def test_sync_batch_stats_world2(tmp_path):
+    out = str(tmp_path / 'sparsity.pt')
+    mp.spawn(_sparsity_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    for kind in ('l2', 'entropy', 'kl'):
+        assert res[kind]['grad_err'] < 1e-12, (kind, res[kind])
+        assert res[kind]['within_err'] < 1e-12 and res[kind]['between_err'] < 1e-12, (kind, res[kind])
+    assert abs(res['local_between'] - res['expected_local_between']) < 1e-12

@@ -41,3 +41,47 @@ def broadcast_parameters(module, src=0, process_group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
         for t in list(module.parameters()) + list(module.buffers()):
             dist.broadcast(t.data, src, group=process_group)
+
+
+# ---- batch-global statistics under data parallelism ---------------------------------------------
+class _AllReduceSum(torch.autograd.Function):
+    """sum over ranks, differentiable: d(total)/d(local) = 1, and every rank holds the same upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, local, group):
+        total = local.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        return total
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class _ScaleGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, factor):
+        ctx.factor = factor
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.factor, None
+
+
+def world_size(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def global_sum(local, group=None):
+    """``local`` summed over all ranks (a no-op on one rank); gradients flow back to the local term."""
+    return _AllReduceSum.apply(local, group) if world_size(group) > 1 else local
+
+
+def global_stat_loss(term, group=None):
+    """A loss term computed from ``global_sum`` statistics is the SAME number on every rank; averaging the parameter
+    gradients over ranks (FlatGradBucket.all_reduce_mean) would therefore weigh it 1/world.  This keeps the value and
+    multiplies its gradient by the world size, so that the averaged gradients equal the single-process gradients of
+    the global-batch loss."""
+    w = world_size(group)
+    return _ScaleGrad.apply(term, float(w)) if w > 1 else term

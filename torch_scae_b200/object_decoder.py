@@ -297,28 +297,46 @@ class CapsuleObjectDecoder(nn.Module):
 
 # ---- capsule sparsity losses: (B,O)-sized, stay in PyTorch (object_decoder.py:431-493) ------------------------------
 
-def capsule_l2_loss(caps_presence, n_classes: int, within_example_constant=None, **unused_kwargs):
+def _batch_stats(caps_presence, sync_batch_stats):
+    """(sum over the batch (O,), batch size): of the local shard like the reference under Lightning DDP, or -- with
+    ``sync_batch_stats`` -- of the global batch, summed over the data-parallel ranks."""
+    from . import ddp
+    total, batch_size = caps_presence.sum(0), caps_presence.shape[0]
+    if sync_batch_stats:
+        total, batch_size = ddp.global_sum(total), batch_size * ddp.world_size()
+    return total, batch_size
+
+
+def _between(term, sync_batch_stats):
+    from . import ddp
+    return ddp.global_stat_loss(term) if sync_batch_stats else term
+
+
+def capsule_l2_loss(caps_presence, n_classes: int, within_example_constant=None, sync_batch_stats=False,
+                    **unused_kwargs):
     del unused_kwargs
-    batch_size, num_caps = caps_presence.shape
+    num_caps = caps_presence.shape[1]
     if within_example_constant is None:
         within_example_constant = float(num_caps) / n_classes
     within_example = torch.mean((caps_presence.sum(1) - within_example_constant) ** 2)
-    between_example = torch.mean((caps_presence.sum(0) - float(batch_size) / n_classes) ** 2)
-    return within_example, between_example
+    total, batch_size = _batch_stats(caps_presence, sync_batch_stats)
+    between_example = torch.mean((total - float(batch_size) / n_classes) ** 2)
+    return within_example, _between(between_example, sync_batch_stats)
 
 
-def capsule_entropy_loss(caps_presence, k=1, **unused_kwargs):
+def capsule_entropy_loss(caps_presence, k=1, sync_batch_stats=False, **unused_kwargs):
     del unused_kwargs
     within_prob = math_ops.normalize(caps_presence, 1)
     within_example = math_ops.cross_entropy_safe(within_prob, within_prob * k)
-    between_prob = math_ops.normalize(torch.sum(caps_presence, 0), 0)
+    total, _ = _batch_stats(caps_presence, sync_batch_stats)
+    between_prob = math_ops.normalize(total, 0)
     between_example = math_ops.cross_entropy_safe(between_prob, between_prob * k)
-    return within_example, -between_example          # negated: between-example entropy is to be increased
+    return within_example, _between(-between_example, sync_batch_stats)   # negated: this entropy is to be increased
 
 
-def neg_capsule_kl(caps_presence, **unused_kwargs):
+def neg_capsule_kl(caps_presence, sync_batch_stats=False, **unused_kwargs):
     del unused_kwargs
-    return capsule_entropy_loss(caps_presence, k=int(caps_presence.shape[-1]))
+    return capsule_entropy_loss(caps_presence, k=int(caps_presence.shape[-1]), sync_batch_stats=sync_batch_stats)
 
 
 def sparsity_loss(loss_type, *args, **kwargs):

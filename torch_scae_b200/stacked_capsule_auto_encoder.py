@@ -25,7 +25,8 @@ class SCAE(nn.Module):
                  prior_sparsity_loss_type='l2', prior_within_example_sparsity_weight=0.,
                  prior_between_example_sparsity_weight=0., prior_within_example_constant=None,
                  posterior_sparsity_loss_type='entropy', posterior_within_example_sparsity_weight=0.,
-                 posterior_between_example_sparsity_weight=0., reconstruct_alternatives=True):
+                 posterior_between_example_sparsity_weight=0., reconstruct_alternatives=True,
+                 sync_batch_stats=False):
         super().__init__()
         self.part_encoder = part_encoder
         self.template_generator = template_generator
@@ -56,6 +57,10 @@ class SCAE(nn.Module):
         self.posterior_between_example_sparsity_weight = posterior_between_example_sparsity_weight
         self.part_caps_sparsity_weight = part_caps_sparsity_weight
         self.reconstruct_alternatives = reconstruct_alternatives
+        # Extension (not in the reference's signature): under data parallelism the between-example sparsity statistics
+        # are batch-GLOBAL sums; False = per-shard statistics, what the reference computes under Lightning DDP; True =
+        # statistics of the global batch (two O-float all-reduces per step), for N-GPU == 1-GPU equivalence.
+        self.sync_batch_stats = sync_batch_stats
 
     def forward(self, image, noise=None):
         """``noise``: optional dict(part_presence, caps, vote) of pre-scaled noises replacing the internal draws."""
@@ -147,7 +152,8 @@ class SCAE(nn.Module):
         if self.prior_within_example_sparsity_weight > 0 or self.prior_between_example_sparsity_weight > 0:
             within, between = sparsity_loss(self.prior_sparsity_loss_type, res.caps_presence,
                                             n_classes=self.n_classes,
-                                            within_example_constant=self.prior_within_example_constant)
+                                            within_example_constant=self.prior_within_example_constant,
+                                            sync_batch_stats=self.sync_batch_stats)
             loss = loss + self.prior_within_example_sparsity_weight * within \
                 + self.prior_between_example_sparsity_weight * between
             log.update(prior_within_sparsity_loss=within, prior_between_sparsity_loss=between)
@@ -155,7 +161,7 @@ class SCAE(nn.Module):
             n_points = res.posterior_mixing_prob.shape[-1]
             mass = res.posterior_mixing_prob.sum(-1)
             within, between = sparsity_loss(self.posterior_sparsity_loss_type, mass / n_points,
-                                            n_classes=self.n_classes)
+                                            n_classes=self.n_classes, sync_batch_stats=self.sync_batch_stats)
             loss = loss + self.posterior_within_example_sparsity_weight * within \
                 + self.posterior_between_example_sparsity_weight * between
             log.update(posterior_within_sparsity_loss=within, posterior_between_sparsity_loss=between)
