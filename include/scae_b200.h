@@ -198,6 +198,36 @@ size_t scae_colsum_workspace_bytes(long rows, int cols); /* 0 when the shape is 
 int scae_colsum(const float* x, long rows, int cols, float* out, void* workspace, size_t workspace_bytes,
                 scae_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Plumbing for the callers of the hot paths: fused elementwise / reduction kernels (csrc/support.cu).  None of these
+ * is on a likelihood path; each replaces a string of small stock-PyTorch launches around it.  Deterministic.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* LayerNorm over a short last dimension d in {8, 16, 32, 64} (nn.LayerNorm in the set transformer's MAB blocks,
+ * reference set_transformer.py:104-116).  y = (x - mean) * rstd * gamma + beta; gamma / beta nullable (1 / 0);
+ * stats[rows, 2] = {mean, rstd} (nullable, needed by the backward). */
+int scae_layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, long rows, int d, float* y,
+                       float* stats, scae_stream_t stream);
+size_t scae_layernorm_bwd_workspace_bytes(long rows, int d); /* 0 when d is not supported */
+/* gx[rows, d]; g_gamma_beta[2 d] = [sum_rows g * xhat | sum_rows g]. */
+int scae_layernorm_bwd(const float* g, const float* x, const float* gamma, const float* stats, long rows, int d,
+                       float* gx, float* g_gamma_beta, void* workspace, size_t workspace_bytes, scae_stream_t stream);
+
+/* Per-channel bias and optional ReLU on an NCHW tensor y[N, C, HW], in place (nn.Conv2d bias + nn.ReLU of the part
+ * encoder's Conv2dStack, reference nn_ext.py:34-59; part_encoder.py:95 att_conv bias with relu = 0). */
+int scae_bias_act_fwd(float* y, const float* bias, int N, int C, int HW, int relu, scae_stream_t stream);
+size_t scae_bias_act_bwd_workspace_bytes(int N, int C, int HW);
+/* relu != 0: gx = g * (y > 0) (gx may alias g), g_bias[C] = sum over (N, HW) of gx.  relu == 0: only g_bias is
+ * produced (the input gradient is g itself; y and gx may be NULL). */
+int scae_bias_act_bwd(const float* g, const float* y, float* gx, float* g_bias, int N, int C, int HW, int relu,
+                      void* workspace, size_t workspace_bytes, scae_stream_t stream);
+
+/* multiple_attention_pooling_2d (reference nn_ext.py:76-101): h[groups, D + 1, S] -> out[groups, D], the softmax over
+ * the S <= 64 positions of every group's last channel pools the group's other D channels. */
+int scae_attnpool_fwd(const float* h, float* out, long groups, int D, int S, scae_stream_t stream);
+/* gh[groups, D + 1, S] from g[groups, D] (recomputes the softmax from h). */
+int scae_attnpool_bwd(const float* h, const float* g, float* gh, long groups, int D, int S, scae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

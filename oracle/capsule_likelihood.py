@@ -69,7 +69,7 @@ def capsule_likelihood(vote, scale, vote_presence, dummy_vote, x, presence=None)
     B, O, V, P = vote.shape
     s = scale.unsqueeze(-1)
     lp = (-((x.unsqueeze(1) - vote) ** 2) / (2 * s ** 2) - torch.log(s) - HALF_LOG_2PI).sum(-1)   # :263-269
-    f32 = dict(dtype=torch.float32)
+    f32 = dict(dtype=torch.float32, device=x.device)
     dummy_lp = torch.zeros(B, 1, V, **f32) + np.log(0.01)                            # :273-274
     lp = torch.cat([lp, dummy_lp], 1)
     dummy_logit = torch.full((B, 1, V), fill_value=np.log(0.01), **f32)             # :281-282
@@ -88,7 +88,7 @@ def capsule_likelihood(vote, scale, vote_presence, dummy_vote, x, presence=None)
     is_from_capsule = win // V                                                      # :334 (sic)
     post = F.softmax(post_logit, 1)                                                 # :338
     votes_ext = torch.cat([vote, dummy_vote.expand(B, 1, V, P)], 1)                 # :341-344
-    pres_ext = torch.cat([vote_presence, torch.zeros(B, 1, V, dtype=vote_presence.dtype)], 1)
+    pres_ext = torch.cat([vote_presence, torch.zeros(B, 1, V, dtype=vote_presence.dtype, device=vote_presence.device)], 1)
     soft_winner = torch.sum(post.unsqueeze(-1) * votes_ext, 1)                      # :350
     soft_winner_presence = torch.sum(post * pres_ext, 1)                            # :354
     return dict(log_prob=log_prob, vote_presence_binary=binary, winner=winner, winner_presence=winner_presence,

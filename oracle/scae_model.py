@@ -152,7 +152,7 @@ def capsule_mlps(sd, cfg, obj_encoding):
     B = obj_encoding.shape[0]
     p = 'obj_decoder.capsule_layer'
     raw = torch.stack([_mlp(sd, f'{p}.mlps.{i}', obj_encoding[:, i]) for i in range(O)], 1)
-    ext = torch.cat([raw, torch.ones(B, O, 1, dtype=raw.dtype)], -1)
+    ext = torch.cat([raw, torch.ones(B, O, 1, dtype=raw.dtype, device=raw.device)], -1)
     return torch.stack([_mlp(sd, f'{p}.caps_mlps.{i}', ext[:, i]) for i in range(O)], 1)
 
 
@@ -171,9 +171,9 @@ def object_decoder(sd, cfg, obj_encoding, part_pose, part_presence, noise=None):
         n_caps = noise.get('caps') if noise else None
         n_vote = noise.get('vote') if noise else None
         if n_caps is None:
-            n_caps = (torch.rand(B, O, 1, dtype=all_param.dtype) - .5) * ns
+            n_caps = (torch.rand(B, O, 1, dtype=all_param.dtype, device=all_param.device) - .5) * ns
         if n_vote is None:
-            n_vote = (torch.rand(B, O, V, dtype=all_param.dtype) - .5) * ns
+            n_vote = (torch.rand(B, O, V, dtype=all_param.dtype, device=all_param.device) - .5) * ns
     elif nt:
         raise ValueError(f'Invalid noise type: {nt}')
     return cl.object_decoder_post_mlp(

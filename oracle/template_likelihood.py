@@ -53,7 +53,7 @@ def decode(templates, pose, output_size, presence=None, bg_image=None, *, templa
     if scale is not None:
         sigma = F.softplus(scale) + 1e-4
     else:
-        sigma = torch.ones(1, dtype=templates.dtype)
+        sigma = torch.ones(1, dtype=templates.dtype, device=templates.device)
     if presence is not None:                                                            # :225-231
         full = torch.cat([presence, presence.new_ones(B, 1)], 1)
         logits = logits + log_safe(full).view(B, M + 1, 1, 1, 1)

@@ -38,3 +38,69 @@ def test_skinny_linear_gradients():
     x64 = x.detach().double().cpu().requires_grad_(True)
     rx, rw, rb = torch.autograd.grad((lin64(x64) * w.double().cpu()).sum(), [x64, lin64.weight, lin64.bias])
     assert rel_err(gx, rx) < 1e-5 and rel_err(gw, rw) < 1e-5 and rel_err(gb, rb) < 1e-5
+
+
+# ---- fused plumbing kernels (csrc/support.cu) vs the plain PyTorch ops in fp64 -------------------------------------------
+@pytest.mark.parametrize('shape', [(1024, 40, 16), (7, 3, 16), (129, 32), (5, 64), (1000, 8)])
+@pytest.mark.parametrize('affine', [True, False])
+def test_layer_norm_matches_torch(shape, affine):
+    from torch_scae_b200 import ops
+    d = shape[-1]
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(*shape, generator=g) * 3 + 1).cuda().requires_grad_(True)
+    w = (torch.rand(d, generator=g) + 0.5).cuda().requires_grad_(True) if affine else None
+    b = torch.randn(d, generator=g).cuda().requires_grad_(True) if affine else None
+    up = torch.randn(*shape, generator=g).cuda()
+    y = ops.layer_norm(x, w, b, 1e-5)
+    grads = torch.autograd.grad((y * up).sum(), [x] + ([w, b] if affine else []))
+    x64 = x.detach().double().cpu().requires_grad_(True)
+    w64 = w.detach().double().cpu().requires_grad_(True) if affine else None
+    b64 = b.detach().double().cpu().requires_grad_(True) if affine else None
+    y64 = torch.nn.functional.layer_norm(x64, (d,), w64, b64, 1e-5)
+    ref = torch.autograd.grad((y64 * up.double().cpu()).sum(), [x64] + ([w64, b64] if affine else []))
+    assert rel_err(y, y64) < 1e-5
+    for got, want in zip(grads, ref):
+        assert rel_err(got, want) < 1e-5
+    y2 = ops.layer_norm(x, w, b, 1e-5)
+    assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize('N,cin,cout,hw,k,stride,relu', [(64, 1, 128, 40, 3, 2, True), (64, 128, 128, 19, 3, 2, True),
+                                                         (33, 16, 24, 7, 3, 1, True), (64, 128, 960, 5, 1, 1, False),
+                                                         (3, 4, 5, 6, 3, 1, False)])
+def test_conv_bias_act_matches_torch(N, cin, cout, hw, k, stride, relu):
+    from torch_scae_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(N + cout)
+    conv = torch.nn.Conv2d(cin, cout, k, stride).cuda()
+    x = torch.randn(N, cin, hw, hw, device='cuda', requires_grad=True)
+    y = ops.conv_bias_act(x, conv, relu)
+    up = torch.randn_like(y)
+    gx, gw, gb = torch.autograd.grad((y * up).sum(), [x, conv.weight, conv.bias])
+    conv64 = torch.nn.Conv2d(cin, cout, k, stride).double()
+    conv64.load_state_dict({n: v.double().cpu() for n, v in conv.state_dict().items()})
+    x64 = x.detach().double().cpu().requires_grad_(True)
+    y64 = conv64(x64)
+    if relu:
+        y64 = torch.relu(y64)
+    rx, rw, rb = torch.autograd.grad((y64 * up.double().cpu()).sum(), [x64, conv64.weight, conv64.bias])
+    assert rel_err(y, y64) < 1e-5
+    # a ReLU mask can flip where the fp32 pre-activation is within rounding of zero: compare in the l2 norm
+    from conftest import l2_rel_err
+    assert l2_rel_err(gx, rx) < 1e-4 and l2_rel_err(gw, rw) < 1e-4 and l2_rel_err(gb, rb) < 1e-4
+
+
+@pytest.mark.parametrize('B,n,D,G', [(64, 40, 24, 5), (5, 3, 7, 8), (2, 1, 1, 1), (3, 2, 40, 6)])
+def test_attention_pool_matches_reference_formula(B, n, D, G):
+    from torch_scae_b200 import nn_ext
+    g = torch.Generator().manual_seed(B * n + D)
+    h = torch.randn(B, n * (D + 1), G, G, generator=g).cuda().requires_grad_(True)
+    out = nn_ext.multiple_attention_pooling_2d(h, n)
+    up = torch.randn(out.shape, generator=g).cuda()
+    (gh,) = torch.autograd.grad((out * up).sum(), [h])
+    h64 = h.detach().double().cpu().requires_grad_(True)
+    grouped = h64.view(B, n, D + 1, G * G)                      # the reference formula (nn_ext.py:76-101)
+    ref = (grouped[:, :, :-1] * torch.softmax(grouped[:, :, -1:], -1)).sum(-1).reshape(B, n * D, 1, 1)
+    (rh,) = torch.autograd.grad((ref * up.double().cpu()).sum(), [h64])
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 1e-5 and rel_err(gh, rh) < 1e-5

@@ -5,7 +5,7 @@ is built in-tree by ``torch_scae_b200.build`` (``__graft_entry__.build()``); on 
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_int, c_long, c_size_t, c_uint, c_ulonglong, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_size_t, c_uint, c_ulonglong, c_void_p
 
 from .build import LIB_PATH
 
@@ -75,6 +75,16 @@ SYMBOLS = {
                          [c_size_t, c_void_p]),
     'scae_colsum_workspace_bytes': (c_size_t, [c_long, c_int]),
     'scae_colsum': (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'scae_layernorm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_long, c_int, c_void_p, c_void_p, c_void_p]),
+    'scae_layernorm_bwd_workspace_bytes': (c_size_t, [c_long, c_int]),
+    'scae_layernorm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
+    'scae_bias_act_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'scae_bias_act_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'scae_bias_act_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_size_t, c_void_p]),
+    'scae_attnpool_fwd': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
+    'scae_attnpool_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -87,6 +87,132 @@ def colsum(x2d):
 
 
 # =================================================================================================================
+# fused plumbing kernels for the callers of the hot paths (csrc/support.cu)
+# =================================================================================================================
+# These are NOT likelihood paths: each falls back to the stock PyTorch op when the kernel does not cover the input
+# (CPU tensors, other dtypes / shapes), with identical semantics.
+
+def _workspace(n_bytes, device):
+    return torch.empty(max(int(n_bytes), 16), device=device, dtype=torch.uint8)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        lib = _lib.load()
+        x = x.contiguous()
+        d = x.shape[-1]
+        rows = x.numel() // d
+        y = torch.empty_like(x)
+        stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32)
+        check(_timed('scae_layernorm_fwd', lib.scae_layernorm_fwd, ptr(x), ptr(weight), ptr(bias), eps, rows, d,
+                     ptr(y), ptr(stats), _stream()), 'scae_layernorm_fwd')
+        ctx.save_for_backward(x, weight, stats)
+        ctx.has = (weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, weight, stats = ctx.saved_tensors
+        g = g.contiguous()
+        d = x.shape[-1]
+        rows = x.numel() // d
+        gx = torch.empty_like(x)
+        ggb = torch.empty(2 * d, device=x.device, dtype=torch.float32)
+        ws_bytes = lib.scae_layernorm_bwd_workspace_bytes(rows, d)
+        ws = _workspace(ws_bytes, x.device)
+        check(_timed('scae_layernorm_bwd', lib.scae_layernorm_bwd, ptr(g), ptr(x), ptr(weight), ptr(stats), rows, d,
+                     ptr(gx), ptr(ggb), ptr(ws), ws_bytes, _stream()), 'scae_layernorm_bwd')
+        return gx, ggb[:d] if ctx.has[0] else None, ggb[d:] if ctx.has[1] else None, None
+
+
+def layer_norm(x, weight, bias, eps):
+    """F.layer_norm over the last dimension."""
+    d = x.shape[-1]
+    if x.is_cuda and x.dtype == torch.float32 and d in (8, 16, 32, 64) and x.numel() > 0 \
+            and (weight is None or weight.dtype == torch.float32):
+        return _LayerNorm.apply(x, weight, bias, float(eps))
+    return torch.nn.functional.layer_norm(x, (d,), weight, bias, eps)
+
+
+class _ConvBiasAct(torch.autograd.Function):
+    """cuDNN convolution (no padding / dilation / groups) + per-channel bias + optional ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, relu):
+        lib = _lib.load()
+        y = torch.nn.functional.conv2d(x, weight, None, stride).contiguous()
+        N, C, H, W = y.shape
+        check(_timed('scae_bias_act_fwd', lib.scae_bias_act_fwd, ptr(y), ptr(bias), N, C, H * W, int(relu), _stream()),
+              'scae_bias_act_fwd')
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.stride, ctx.relu = stride, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, weight, y = ctx.saved_tensors
+        g = g.contiguous()
+        N, C, H, W = g.shape
+        g_bias = torch.empty(C, device=g.device, dtype=torch.float32)
+        gx_pre = torch.empty_like(g) if ctx.relu else g
+        ws_bytes = lib.scae_bias_act_bwd_workspace_bytes(N, C, H * W)
+        ws = _workspace(ws_bytes, g.device)
+        check(_timed('scae_bias_act_bwd', lib.scae_bias_act_bwd, ptr(g), ptr(y), ptr(gx_pre) if ctx.relu else None,
+                     ptr(g_bias), N, C, H * W, int(ctx.relu), ptr(ws), ws_bytes, _stream()), 'scae_bias_act_bwd')
+        gx, gw, _ = torch.ops.aten.convolution_backward(
+            gx_pre, x, weight, None, ctx.stride, (0, 0), (1, 1), False, (0, 0), 1,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        return gx, gw, g_bias if ctx.needs_input_grad[2] else None, None, None
+
+
+def conv_bias_act(x, conv, relu):
+    """``relu(conv(x))`` / ``conv(x)`` for an nn.Conv2d; the bias add, the ReLU and (backward) the ReLU mask + bias
+    gradient run as one pass each instead of four."""
+    ok = (x.is_cuda and x.dtype == torch.float32 and conv.bias is not None and conv.padding == (0, 0)
+          and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == 'zeros' and x.dim() == 4
+          and conv.weight.dtype == torch.float32)
+    if not ok:
+        y = conv(x)
+        return torch.relu(y) if relu else y
+    return _ConvBiasAct.apply(x.contiguous(), conv.weight, conv.bias, tuple(conv.stride), bool(relu))
+
+
+class _AttentionPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, groups, D, S):
+        lib = _lib.load()
+        h = h.contiguous()
+        out = torch.empty(groups, D, device=h.device, dtype=torch.float32)
+        check(_timed('scae_attnpool_fwd', lib.scae_attnpool_fwd, ptr(h), ptr(out), groups, D, S, _stream()),
+              'scae_attnpool_fwd')
+        ctx.save_for_backward(h)
+        ctx.dims = (groups, D, S)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (h,) = ctx.saved_tensors
+        groups, D, S = ctx.dims
+        gh = torch.empty_like(h)
+        check(_timed('scae_attnpool_bwd', lib.scae_attnpool_bwd, ptr(h), ptr(g.contiguous()), ptr(gh), groups, D, S,
+                     _stream()), 'scae_attnpool_bwd')
+        return gh, None, None, None
+
+
+def attention_pool(feature_map, n_attention_map):
+    """nn_ext.multiple_attention_pooling_2d on a CUDA fp32 map with at most 64 positions; None when not covered."""
+    B, C, H, W = feature_map.shape
+    S, D = H * W, C // n_attention_map - 1
+    if not (feature_map.is_cuda and feature_map.dtype == torch.float32 and S <= 64 and 0 < D <= 1024):
+        return None
+    return _AttentionPool.apply(feature_map, B * n_attention_map, D, S).view(B, C - n_attention_map, 1, 1)
+
+
+# =================================================================================================================
 # hot path 1
 # =================================================================================================================
 

@@ -47,7 +47,8 @@ class CapsuleImageEncoder(nn.Module):
         """``presence_noise`` (B,M), already scaled, replaces the internally drawn training noise
         (part_encoder.py:105-107); used by parity tests to inject the reference's noise."""
         B = image.shape[0]
-        h = self.att_conv(self.encoder(image) + self.img_embedding_bias.unsqueeze(0))
+        from . import ops
+        h = ops.conv_bias_act(self.encoder(image) + self.img_embedding_bias.unsqueeze(0), self.att_conv, relu=False)
         h = multiple_attention_pooling_2d(h, self.n_caps).view(B, self.n_caps, self.n_total_caps_dims)
         pose, presence_logit, feature = torch.split(h, self.caps_dim_splits, -1)
         presence_logit = presence_logit.squeeze(-1)

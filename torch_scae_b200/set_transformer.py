@@ -14,13 +14,13 @@ from . import skinny
 
 
 def _layer_norm(x, ln):
-    """nn.LayerNorm's arithmetic with the affine part as plain elementwise ops.
-
-    For the tiny feature width used here (d=16) ATen's fused LayerNorm backward spends 0.24 ms per call in its
-    gamma/beta reduction kernel (profiles/r01a); normalising without affine parameters and applying weight/bias
-    separately gives the same values and lets the parameter gradients come from ordinary column reductions.
-    """
-    return F.layer_norm(x, ln.normalized_shape, None, None, ln.eps) * ln.weight + ln.bias
+    """nn.LayerNorm through ``ops.layer_norm``: for the tiny feature width used here (d = 16) ATen's kernels spend
+    60 us forward and 0.24 ms backward per call on 2.6 MB of data (profiles/r01a, r01p); the thread-per-row kernel in
+    csrc/support.cu does either direction, affine part and parameter gradients included, in one pass."""
+    from . import ops
+    if len(ln.normalized_shape) == 1 and ln.elementwise_affine:
+        return ops.layer_norm(x, ln.weight, ln.bias, ln.eps)
+    return ln(x)
 
 
 def qkv_attention(queries, keys, values, presence=None):
