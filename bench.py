@@ -201,10 +201,11 @@ def run_gpu(args):
     torch.manual_seed(42)                                   # identical initial weights on every rank
     model = factory.make_scae(model_params(args.n_obj_caps)).to(dev).train()
     ddp.broadcast_parameters(model)
-    bucket = ddp.FlatGradBucket(model)
-    # capturable: the optimizer step is part of the captured CUDA graph (no host-side step counters)
-    opt = torch.optim.RMSprop(model.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2, foreach=True,
-                              capturable=True)
+    # parameters, gradients and optimizer state live in flat buffers: gradients are assigned (not accumulated) and
+    # copied into the bucket by one multi-tensor launch, the all-reduce is one NCCL call on the bucket, and the
+    # RMSprop update (the reference's optimizer and hyper-parameters, base_experiment.py:47-53) is one kernel
+    bucket = ddp.FlatGradBucket(model, assign=True, flat_params=True)
+    opt = ddp.FlatRMSprop(bucket, lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2)
     torch.manual_seed(42 + rank)                            # different synthetic shard per rank
     host_image = torch.rand(B, 1, 40, 40).pin_memory()
     host_label = torch.randint(0, 10, (B,)).pin_memory()
@@ -216,6 +217,7 @@ def run_gpu(args):
         res = model(img)
         loss, _ = model.loss(res, img, lab)
         loss.backward()
+        bucket.collect()
         bucket.all_reduce_mean()
         opt.step()
         return loss
@@ -287,14 +289,15 @@ def run_gpu(args):
         del opt, bucket
         graphed = None                                      # releases the captured graphs and their pool
         m2 = factory.make_scae(model_params(10)).to(dev).train()
-        b2 = ddp.FlatGradBucket(m2)
-        o2 = torch.optim.RMSprop(m2.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2, foreach=True)
+        b2 = ddp.FlatGradBucket(m2, assign=True, flat_params=True)
+        o2 = ddp.FlatRMSprop(b2, lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2)
 
         def step2():
             b2.zero()
             r = m2(image)
             l, _ = m2.loss(r, image, label)
             l.backward()
+            b2.collect()
             o2.step()
         for _ in range(5):
             step2()

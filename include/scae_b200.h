@@ -228,6 +228,12 @@ int scae_attnpool_fwd(const float* h, float* out, long groups, int D, int S, sca
 /* gh[groups, D + 1, S] from g[groups, D] (recomputes the softmax from h). */
 int scae_attnpool_bwd(const float* h, const float* g, float* gh, long groups, int D, int S, scae_stream_t stream);
 
+/* torch.optim.RMSprop (centered = False, weight_decay = 0; the reference's optimizer, base_experiment.py:47-53) over
+ * FLAT buffers of n floats, one pass: square_avg = alpha square_avg + (1 - alpha) g^2; step = g / (sqrt(square_avg) +
+ * eps); with momentum_buf: buf = momentum buf + step, param -= lr buf; without (NULL): param -= lr step. */
+int scae_rmsprop_step(float* param, const float* grad, float* square_avg, float* momentum_buf, long n, float lr,
+                      float alpha, float eps, float momentum, scae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

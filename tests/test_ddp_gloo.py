@@ -110,3 +110,35 @@ def test_sync_batch_stats_world2(tmp_path):
         assert res[kind]['grad_err'] < 1e-12, (kind, res[kind])
         assert res[kind]['within_err'] < 1e-12 and res[kind]['between_err'] < 1e-12, (kind, res[kind])
     assert abs(res['local_between'] - res['expected_local_between']) < 1e-12
+
+
+# ---- flat parameter / gradient / optimizer-state buffers (single process, CPU arithmetic path) --------------------------
+def test_flat_rmsprop_assign_mode_matches_torch_rmsprop():
+    from torch_scae_b200 import ddp
+    torch.manual_seed(3)
+    ref = nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 3), nn.Linear(3, 2))
+    model = nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 3), nn.Linear(3, 2))
+    model.load_state_dict(ref.state_dict())
+    for m in (ref, model):
+        m[3].weight.requires_grad_(True)
+    ropt = torch.optim.RMSprop(ref.parameters(), lr=1e-2, momentum=0.9, eps=1e-3)
+    bucket = ddp.FlatGradBucket(model, assign=True, flat_params=True)
+    opt = ddp.FlatRMSprop(bucket, lr=1e-2, momentum=0.9, eps=1e-3)
+    data, target = torch.randn(8, 6), torch.randn(8, 3)
+    for _ in range(4):
+        ropt.zero_grad()
+        ((ref[:3](data) - target) ** 2).mean().backward()        # the last Linear gets no gradient at all
+        ropt.step()
+        bucket.zero()
+        ((model[:3](data) - target) ** 2).mean().backward()
+        bucket.collect()
+        assert bucket.check_views()
+        bucket.all_reduce_mean()
+        opt.step()
+    for (k, a), b in zip(ref.state_dict().items(), model.state_dict().values()):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), k
+    # parameters are views of one flat buffer, state_dict round-trips through them
+    base = bucket.flat_param.untyped_storage().data_ptr()
+    assert all(p.untyped_storage().data_ptr() == base for p in model.parameters())
+    model.load_state_dict(ref.state_dict())
+    assert all(p.untyped_storage().data_ptr() == base for p in model.parameters())

@@ -104,3 +104,47 @@ def test_attention_pool_matches_reference_formula(B, n, D, G):
     (rh,) = torch.autograd.grad((ref * up.double().cpu()).sum(), [h64])
     assert out.shape == ref.shape
     assert rel_err(out, ref) < 1e-5 and rel_err(gh, rh) < 1e-5
+
+
+def test_flat_rmsprop_kernel_matches_torch_rmsprop():
+    from torch_scae_b200 import ddp
+    torch.manual_seed(5)
+    ref = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Tanh(), torch.nn.Linear(17, 5)).cuda()
+    model = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Tanh(), torch.nn.Linear(17, 5)).cuda()
+    model.load_state_dict(ref.state_dict())
+    for momentum in (0.9, 0.0):
+        ropt = torch.optim.RMSprop(ref.parameters(), lr=3e-3, momentum=momentum, eps=1e-4)
+        bucket = ddp.FlatGradBucket(model, assign=True, flat_params=True)
+        opt = ddp.FlatRMSprop(bucket, lr=3e-3, momentum=momentum, eps=1e-4)
+        data, target = torch.randn(64, 33, device='cuda'), torch.randn(64, 5, device='cuda')
+        for _ in range(5):
+            ropt.zero_grad()
+            ((ref(data) - target) ** 2).mean().backward()
+            ropt.step()
+            bucket.zero()
+            ((model(data) - target) ** 2).mean().backward()
+            bucket.collect()
+            opt.step()
+        for (k, a), b in zip(ref.state_dict().items(), model.state_dict().values()):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (momentum, k)
+
+
+def test_shared_query_attention_matches_expanded_queries():
+    """MultiHeadQKVAttention with batch-shared queries (seeds.expand) projects them once; same result and gradients as
+    the reference's per-image evaluation (set_transformer.py:24-71)."""
+    from torch_scae_b200 import set_transformer as st
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(2)
+    att = st.MultiHeadQKVAttention(d_k=32, d_v=32, n_heads=1).cuda()
+    seeds = torch.randn(1, 6, 32, device='cuda', requires_grad=True)
+    z = torch.randn(9, 11, 32, device='cuda', requires_grad=True)
+    presence = torch.rand(9, 11, device='cuda')
+    up = torch.randn(9, 6, 32, device='cuda')
+    params = [seeds, z] + list(att.parameters())
+    out = att(seeds.expand(9, -1, -1), z, z, presence)
+    got = torch.autograd.grad((out * up).sum(), params)
+    out_ref = att(seeds.expand(9, -1, -1).contiguous(), z, z, presence)
+    ref = torch.autograd.grad((out_ref * up).sum(), params)
+    assert rel_err(out, out_ref) < 1e-5
+    for a, b in zip(got, ref):
+        assert rel_err(a, b) < 1e-5

@@ -27,8 +27,8 @@ torch.backends.cudnn.benchmark = True
 dev = torch.device('cuda', 0)
 torch.manual_seed(42)
 model = factory.make_scae(model_params(args.n_obj_caps)).to(dev).train()
-bucket = ddp.FlatGradBucket(model)
-opt = torch.optim.RMSprop(model.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(args.batch) ** 2, foreach=True)
+bucket = ddp.FlatGradBucket(model, assign=True, flat_params=True)
+opt = ddp.FlatRMSprop(bucket, lr=3e-5, momentum=0.9, eps=1e-2 / float(args.batch) ** 2)
 image = torch.rand(args.batch, 1, 40, 40, device=dev)
 label = torch.randint(0, 10, (args.batch,), device=dev)
 
@@ -38,6 +38,7 @@ def step():
     res = model(image)
     loss, _ = model.loss(res, image, label)
     loss.backward()
+    bucket.collect()
     opt.step()
 
 

@@ -83,6 +83,8 @@ SYMBOLS = {
     'scae_bias_act_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'scae_bias_act_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                   c_size_t, c_void_p]),
+    'scae_rmsprop_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
+                                  c_void_p]),
     'scae_attnpool_fwd': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
     'scae_attnpool_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),
 }

@@ -155,11 +155,22 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(float* __restrict__ y
   const long plane = (long)C * HW;
   const int total = (n1 - n0) * HW;
   const float inv_hw = 1.0f / (float)HW;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int dn = (int)(((float)e + 0.5f) * inv_hw), s = e - dn * HW;
-    float* p = y + (long)(n0 + dn) * plane + (long)c * HW + s;
-    const float v = *p + b;
-    *p = relu ? fmaxf(v, 0.0f) : v;
+  // four independent elements per thread and iteration: enough loads in flight to cover the HBM latency
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+    float* p[4];
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      const int dn = (int)(((float)e + 0.5f) * inv_hw), s = e - dn * HW;
+      p[u] = y + (long)(n0 + dn) * plane + (long)c * HW + s;
+      v[u] = e < total ? *p[u] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = v[u] + b;
+      if (e0 + u * (int)blockDim.x < total) *p[u] = relu ? fmaxf(t, 0.0f) : t;
+    }
   }
 }
 
@@ -174,15 +185,24 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* __restri
   const int total = (n1 - n0) * HW;
   const float inv_hw = 1.0f / (float)HW;
   float acc = 0.0f;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
-    const int dn = (int)(((float)e + 0.5f) * inv_hw), s = e - dn * HW;
-    const long off = (long)(n0 + dn) * plane + (long)c * HW + s;
-    float v = g[off];
-    if (relu) {
-      v = y[off] > 0.0f ? v : 0.0f;
-      gx[off] = v;
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
+    long off[4];
+    float v[4], yv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * blockDim.x;
+      const int dn = (int)(((float)e + 0.5f) * inv_hw), s = e - dn * HW;
+      off[u] = (long)(n0 + dn) * plane + (long)c * HW + s;
+      const bool ok = e < total;
+      v[u] = ok ? g[off[u]] : 0.0f;
+      yv[u] = (ok && relu) ? y[off[u]] : 1.0f;
     }
-    acc += v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = yv[u] > 0.0f ? v[u] : 0.0f;
+      if (relu && e0 + u * (int)blockDim.x < total) gx[off[u]] = t;
+      acc += t;
+    }
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -281,6 +301,52 @@ __global__ void __launch_bounds__(256) attnpool_bwd_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// RMSprop with momentum over flat parameter / gradient / state buffers: one pass instead of seven foreach launches
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                      float* __restrict__ sq, float* __restrict__ buf, long n, float lr,
+                                                      float alpha, float eps, float momentum) {
+  const long stride = (long)gridDim.x * blockDim.x * 4;
+  for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      const float4 gv = *reinterpret_cast<const float4*>(g + i);
+      float4 sv = *reinterpret_cast<float4*>(sq + i), pv = *reinterpret_cast<float4*>(p + i);
+      float4 bv = buf ? *reinterpret_cast<float4*>(buf + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+      float ss[4] = {sv.x, sv.y, sv.z, sv.w}, pp[4] = {pv.x, pv.y, pv.z, pv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ss[k] = fmaf(1.0f - alpha, gg[k] * gg[k], ss[k] * alpha);
+        const float step = __fdiv_rn(gg[k], sqrtf(ss[k]) + eps);
+        if (buf) {
+          bb[k] = fmaf(bb[k], momentum, step);
+          pp[k] = fmaf(-lr, bb[k], pp[k]);
+        } else {
+          pp[k] = fmaf(-lr, step, pp[k]);
+        }
+      }
+      *reinterpret_cast<float4*>(sq + i) = make_float4(ss[0], ss[1], ss[2], ss[3]);
+      *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      if (buf) *reinterpret_cast<float4*>(buf + i) = make_float4(bb[0], bb[1], bb[2], bb[3]);
+    } else {
+      for (long j = i; j < n; ++j) {
+        const float gj = g[j];
+        const float s = fmaf(1.0f - alpha, gj * gj, sq[j] * alpha);
+        sq[j] = s;
+        const float step = __fdiv_rn(gj, sqrtf(s) + eps);
+        if (buf) {
+          const float b = fmaf(buf[j], momentum, step);
+          buf[j] = b;
+          p[j] = fmaf(-lr, b, p[j]);
+        } else {
+          p[j] = fmaf(-lr, step, p[j]);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace scae
 
 using namespace scae;
@@ -361,6 +427,23 @@ SCAE_EXPORT int scae_bias_act_bwd(const float* g, const float* y, float* gx, flo
   note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   return launch_reduce_rows(partial, g_bias, slabs, C, stream);
+}
+
+SCAE_EXPORT int scae_rmsprop_step(float* param, const float* grad, float* square_avg, float* momentum_buf, long n,
+                                  float lr, float alpha, float eps, float momentum, scae_stream_t stream_) {
+  SCAE_REQUIRE(param && grad && square_avg, SCAE_EINVAL, "rmsprop: param, grad and square_avg are required");
+  SCAE_REQUIRE(n > 0, SCAE_EINVAL, "rmsprop: n must be positive");
+  SCAE_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(square_avg) && (!momentum_buf || aligned16(momentum_buf)),
+               SCAE_EINVAL, "rmsprop: pointers must be 16-byte aligned");
+  long grid = (n / 4 + 255) / 256;
+  const long cap = 8L * sm_count();
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  rmsprop_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(param, grad, square_avg, momentum_buf, n, lr,
+                                                                           alpha, eps, momentum);
+  note_launch();
+  SCAE_CUDA_TRY(cudaGetLastError());
+  return SCAE_OK;
 }
 
 SCAE_EXPORT int scae_attnpool_fwd(const float* h, float* out, long groups, int D, int S, scae_stream_t stream_) {

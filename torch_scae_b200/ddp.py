@@ -10,20 +10,66 @@ import torch.distributed as dist
 
 
 class FlatGradBucket:
-    def __init__(self, module, process_group=None):
+    """All parameter gradients of ``module`` in ONE flat fp32 buffer (what the all-reduce and the optimizer work on).
+
+    ``assign=False`` (default): every ``p.grad`` is a view into the buffer; ``zero()`` clears it and autograd
+    accumulates into the views in place -- one small add kernel per parameter (276 per step for the MNIST model).
+
+    ``assign=True``: ``zero()`` only drops the ``.grad`` references (no kernel), so autograd hands every parameter its
+    freshly computed gradient tensor without an add; ``collect()`` then copies them into the flat buffer with one
+    multi-tensor launch and re-points ``p.grad`` at the views.  Parameters that received no gradient keep zeros.
+
+    ``flat_params=True`` additionally re-homes every parameter as a view into one flat buffer (``flat_param``), which is
+    what ``FlatRMSprop`` updates in a single kernel.  Build the bucket AFTER moving the module to its device.
+    """
+
+    def __init__(self, module, process_group=None, assign=False, flat_params=False):
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = process_group
+        self.assign = assign
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, device=ref.device, dtype=ref.dtype)
+        self.flat_param = None
+        if flat_params:
+            self.flat_param = torch.empty(n, device=ref.device, dtype=ref.dtype)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)      # autograd accumulates into these views in place
+            # every segment starts on a 16-byte boundary relative to the buffer only if all sizes are multiples of 4;
+            # the flat kernels work on the whole buffer, so per-parameter alignment does not matter
+            view = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(view)
+            if flat_params:
+                with torch.no_grad():
+                    home = self.flat_param[off:off + p.numel()].view_as(p)
+                    home.copy_(p)
+                    p.data = home
+            p.grad = None if assign else view      # autograd accumulates into the views in place
             off += p.numel()
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
 
     def zero(self):
-        self.flat.zero_()
+        if self.assign:
+            for p in self.params:
+                p.grad = None
+        else:
+            self.flat.zero_()
+
+    def collect(self):
+        """assign mode: gradients -> flat buffer (one multi-tensor copy); no-op otherwise."""
+        if not self.assign:
+            return
+        src, dst = [], []
+        for p, view in zip(self.params, self.views):
+            if p.grad is not None and p.grad is not view:
+                src.append(p.grad)
+                dst.append(view)
+        if src:
+            torch._foreach_copy_(dst, src)
+        for p, view in zip(self.params, self.views):
+            if p.grad is not None:
+                p.grad = view                      # readers of .grad see the (reduced) bucket contents
 
     def all_reduce_mean(self):
         """Averages gradients across ranks (what Lightning's DDP does for the reference, train.py:40)."""
@@ -32,9 +78,51 @@ class FlatGradBucket:
             self.flat.div_(self.world)
 
     def check_views(self):
-        """True iff every .grad still aliases the bucket (autograd kept accumulating in place)."""
+        """True iff every existing .grad aliases the bucket (accumulate mode: autograd kept accumulating in place;
+        assign mode: ``collect`` ran after the last backward)."""
         base = self.flat.untyped_storage().data_ptr()
+        if self.assign:
+            return all(p.grad is None or p.grad.untyped_storage().data_ptr() == base for p in self.params)
         return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for p in self.params)
+
+
+class FlatRMSprop:
+    """``torch.optim.RMSprop(lr, alpha, eps, momentum)`` (centered = False, weight_decay = 0 -- the reference's
+    optimizer, base_experiment.py:47-53) over a ``FlatGradBucket(flat_params=True)``: parameters, gradients and both
+    state buffers are flat, so a step is ONE kernel (csrc/support.cu::rmsprop_kernel) instead of seven multi-tensor
+    launches over 276 tensors.  Graph-capturable (no host-side state).
+    """
+
+    def __init__(self, bucket, lr=1e-2, alpha=0.99, eps=1e-8, momentum=0.0):
+        if bucket.flat_param is None:
+            raise ValueError('FlatRMSprop needs FlatGradBucket(..., flat_params=True)')
+        self.bucket = bucket
+        self.lr, self.alpha, self.eps, self.momentum = float(lr), float(alpha), float(eps), float(momentum)
+        self.square_avg = torch.zeros_like(bucket.flat)
+        self.momentum_buffer = torch.zeros_like(bucket.flat) if momentum > 0 else None
+        # same attribute torch optimizers expose; GraphedTrainStep snapshots / restores these tensors around warm-up
+        self.state = {0: dict(square_avg=self.square_avg, **(
+            dict(momentum_buffer=self.momentum_buffer) if self.momentum_buffer is not None else {}))}
+
+    def step(self):
+        from . import _lib, ops
+        lib = _lib.load()
+        b = self.bucket
+        if not b.flat.is_cuda:
+            # host-side logic tests (gloo): the same arithmetic with torch ops
+            self.square_avg.mul_(self.alpha).addcmul_(b.flat, b.flat, value=1 - self.alpha)
+            step = b.flat / (self.square_avg.sqrt() + self.eps)
+            if self.momentum_buffer is not None:
+                self.momentum_buffer.mul_(self.momentum).add_(step)
+                step = self.momentum_buffer
+            b.flat_param.add_(step, alpha=-self.lr)
+            return
+        _lib.check(ops._timed('scae_rmsprop_step', lib.scae_rmsprop_step, _lib.ptr(b.flat_param), _lib.ptr(b.flat),
+                              _lib.ptr(self.square_avg), _lib.ptr(self.momentum_buffer), b.flat.numel(), self.lr,
+                              self.alpha, self.eps, self.momentum, ops._stream()), 'scae_rmsprop_step')
+
+    def zero_grad(self, set_to_none=True):
+        self.bucket.zero()
 
 
 def broadcast_parameters(module, src=0, process_group=None):

@@ -42,6 +42,7 @@ class GraphedTrainStep:
         res = self.model(self.static_image)
         loss, _ = self.model.loss(res, self.static_image, self.static_label)
         loss.backward()
+        self.bucket.collect()
         return loss.detach()
 
     # ---- warm-up must not train: parameters and optimizer state are put back in place afterwards ----------------------

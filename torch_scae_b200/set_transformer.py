@@ -24,7 +24,11 @@ def _layer_norm(x, ln):
 
 
 def qkv_attention(queries, keys, values, presence=None):
-    logits = torch.matmul(queries, keys.transpose(1, 2))
+    if queries.dim() == 3 and queries.shape[0] > 1 and queries.stride(0) == 0:
+        # batch-shared queries: one (B*M, d) x (d, N) GEMM instead of B small ones
+        logits = torch.matmul(keys, queries[0].t()).transpose(1, 2)
+    else:
+        logits = torch.matmul(queries, keys.transpose(1, 2))
     if presence is not None:
         logits = logits - (1. - presence.unsqueeze(-2)) * 1e32
     weights = F.softmax(logits / math.sqrt(queries.shape[-1]), -1)
@@ -54,7 +58,13 @@ class MultiHeadQKVAttention(nn.Module):
             assert values.shape[:2] == presence.shape
         B, N, _ = queries.shape
         H = self.n_heads
-        q = self._split_heads(skinny.linear(queries, self.q_projector))
+        if B > 1 and queries.stride(0) == 0:
+            # batch-shared queries (the learnt seeds / inducing points, ``S.expand(B, -1, -1)``): project them once
+            # instead of B times -- same values; the backward sums the batch before the (now tiny) weight-gradient GEMM
+            q = self.q_projector(queries[:1]).expand(B, -1, -1)
+        else:
+            q = skinny.linear(queries, self.q_projector)
+        q = self._split_heads(q)
         k = self._split_heads(skinny.linear(keys, self.k_projector))
         v = self._split_heads(skinny.linear(values, self.v_projector))
         if presence is not None and H > 1:
