@@ -148,3 +148,31 @@ def test_shared_query_attention_matches_expanded_queries():
     assert rel_err(out, out_ref) < 1e-5
     for a, b in zip(got, ref):
         assert rel_err(a, b) < 1e-5
+
+
+def test_set_transformer_pooled_output_matches_unfused_attention():
+    """SetTransformer's re-associated output attention (no z / keys / values) vs the reference's op order
+    (fc2 -> k/v projections -> attention -> output projection) on the same module: values and every gradient."""
+    from torch_scae_b200 import set_transformer as st
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(4)
+    net = st.SetTransformer(dim_in=24, dim_hidden=16, dim_out=64, n_outputs=8, n_layers=2, n_heads=1,
+                            layer_norm=True).cuda()
+    x = torch.randn(12, 10, 24, device='cuda', requires_grad=True)
+    presence = torch.rand(12, 10, device='cuda')
+    up = torch.randn(12, 8, 64, device='cuda')
+    params = [x] + list(net.parameters())
+    out = net(x, presence)
+    got = torch.autograd.grad((out * up).sum(), params)
+
+    def unfused(x, presence):
+        h = net.fc1(x)
+        for block in net.sabs:
+            h = block(h, presence)
+        z = net.fc2(h)
+        return net.multi_head_attention(net.seeds.expand(x.shape[0], -1, -1).contiguous(), z, z, presence)
+    out_ref = unfused(x, presence)
+    ref = torch.autograd.grad((out_ref * up).sum(), params)
+    assert rel_err(out, out_ref) < 1e-5
+    for (name, _), a, b in zip([('x', None)] + list(net.named_parameters()), got, ref):
+        assert rel_err(a, b) < 5e-5, name

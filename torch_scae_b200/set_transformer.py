@@ -150,5 +150,38 @@ class SetTransformer(nn.Module):
         h = skinny.linear(x, self.fc1)
         for block in self.sabs:
             h = block(h, presence)
+        att = self.multi_head_attention
+        if att.n_heads == 1 and h.shape[0] > 1:
+            return self._pooled_output(h, presence)
         z = skinny.linear(h, self.fc2)
-        return self.multi_head_attention(self.seeds.expand(x.shape[0], -1, -1), z, z, presence)
+        return att(self.seeds.expand(x.shape[0], -1, -1), z, z, presence)
+
+    def _pooled_output(self, h, presence):
+        """``multi_head_attention(seeds, z, z)`` with ``z = fc2(h)`` (set_transformer.py:218-223) evaluated WITHOUT ever
+        forming z, the keys or the values -- the same function of the same parameters, re-associated:
+
+          keys   = z Wk^T + bk = h (Wk W2)^T + (Wk b2 + bk)            (fc2 and the projector are both affine)
+          logits = q keys^T   = (q Wk W2) h^T + q (Wk b2 + bk)          -> a d_hidden-wide contraction
+          out    = (A values) Wo^T + bo = (A h) (Wo Wv W2)^T + (Wo (Wv b2 + bv) + bo)   (rows of A = softmax sum to 1)
+
+        The reference spends four (B*M, 256) x (256, 256) GEMMs here forward (and eight backward) on activations that
+        have rank d_hidden = 16; composing the weights first -- three 256x256x16 products -- leaves (B*M, 16)-sized
+        work and one (B*n_outputs, 16) x (16, 256) GEMM.  Parameters, state_dict and gradients are unchanged (autograd
+        differentiates through the composed weights); values agree to fp32 rounding (tests/test_gpu_plumbing.py).
+        """
+        att = self.multi_head_attention
+        w2, b2 = self.fc2.weight, self.fc2.bias                                   # (D, d), (D,)
+        wk, bk = att.k_projector.weight, att.k_projector.bias
+        wv, bv = att.v_projector.weight, att.v_projector.bias
+        wo, bo = att.o_projector.weight, att.o_projector.bias
+        q = att.q_projector(self.seeds[0])                                       # (N, D), batch-shared
+        qk = q @ (wk @ w2)                                                       # (N, d)
+        qb = q @ (wk @ b2 + bk)                                                  # (N,)
+        logits = torch.matmul(h, qk.t()).transpose(1, 2) + qb.unsqueeze(-1)      # (B, N, M)
+        if presence is not None:
+            logits = logits - (1. - presence.unsqueeze(-2)) * 1e32
+        weights = F.softmax(logits / math.sqrt(q.shape[-1]), -1)
+        pooled = torch.matmul(weights, h)                                        # (B, N, d)
+        wov = wo @ (wv @ w2)                                                     # (D, d)
+        bov = wo @ (wv @ b2 + bv) + bo                                           # (D,)
+        return torch.matmul(pooled, wov.t()) + bov
