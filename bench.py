@@ -40,11 +40,15 @@ def workload_name(n_obj_caps, batch):
 # ---------------------------------------------------------------------------------------------------------------------
 # algorithmic HBM bytes per image (SURVEY.md section 8d / DESIGN.md section 5)
 # ---------------------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(M=40, C=1, h=11, w=11, H=40, W=40, O=32):
+def algorithmic_bytes(M=40, C=1, h=11, w=11, H=40, W=40, O=32, fused_color=False):
+    """``fused_color``: the train step passes (raw templates, colours) to path 1: per image
+    the kernels then read M*C colours instead of M*C*h*w coloured texels and write M*C colour gradients instead of the
+    (M,C,h,w) template gradient (the batch-shared raw templates and their gradient are L2-resident, like alpha)."""
     V, A = M, 8 * M + 7
-    tmpl_in = 4 * (M * C * h * w + 6 * M + M + C * H * W)                 # templates, pose, presence, x
+    tex = M * C if fused_color else M * C * h * w
+    tmpl_in = 4 * (tex + 6 * M + M + C * H * W)                           # templates | colours, pose, presence, x
     f1 = tmpl_in + 4 * C * H * W + 4 * 2 * C * H * W + 4                  # + log_prob, lse cache, ll
-    b1 = tmpl_in + 4 * C * H * W + 4 * 2 * C * H * W + 4 * (M * C * h * w + 7 * M)   # + grad_out, cache, g_templates/pose/presence
+    b1 = tmpl_in + 4 * C * H * W + 4 * 2 * C * H * W + 4 * (tex + 7 * M)  # + grad_out, cache, g_templates|g_color/pose/presence
     caps_in = 4 * O * A + 4 * O * (V + 1) + 4 * 7 * V                     # all_param, noises, x + presence
     # API-complete forward: every tensor of the reference's result dict
     f2 = caps_in + 4 * (O * V * (6 + 7) + 2 * (O + 1) * V + 2 * O + O + V * (6 + 1 + 6 + 1 + 1) + 2) + 8 * 2 * V
@@ -310,7 +314,7 @@ def run_gpu(args):
         return
 
     peak, peak_src = measured_peaks()
-    bytes_per_image = algorithmic_bytes(O=args.n_obj_caps)
+    bytes_per_image = algorithmic_bytes(O=args.n_obj_caps, fused_color=True)   # SCAE.forward colours in-kernel
     kernels = {}
     plumbing = {}
     launches = 0

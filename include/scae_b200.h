@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SCAE_B200_ABI_VERSION 1
+#define SCAE_B200_ABI_VERSION 2
 
 #define SCAE_OK 0
 #define SCAE_EINVAL (-1)   /* bad shape / flag / NULL where a pointer is required / misaligned pointer */
@@ -59,7 +59,7 @@ unsigned long long scae_launch_count(void);
 /* The learnt scalars are passed RAW (as stored in the reference's state_dict) as device pointers so that no host
  * synchronisation is needed; the kernels apply sigmoid / softplus themselves (part_decoder.py:192,:210,:216,:221). */
 typedef struct scae_tmpl_args {
-  const float* templates;         /* [B,M,C,h,w]                                                          */
+  const float* templates;         /* [B,M,C,h,w]; or, with template_color, the batch-shared raw templates [M,C,h,w] */
   const float* templates_alpha;   /* [M,h,w]      alpha mode; NULL in temperature mode                    */
   const float* pose;              /* [B,M,6]      used directly as the 2x3 affine_grid theta              */
   const float* presence;          /* [B,M]        nullable                                                */
@@ -68,6 +68,9 @@ typedef struct scae_tmpl_args {
   const float* bg_mixing_logit;   /* [1] raw      alpha mode                                              */
   const float* temperature_logit; /* [1] raw      temperature mode                                        */
   const float* scale;             /* [1] raw learnt output scale; NULL => sigma = 1                       */
+  const float* template_color;    /* [B,M,C] nullable: fused colourisation (TemplateGenerator.forward,
+                                     part_decoder.py:90-105): template[b,m,c] = templates[m,c] * template_color[b,m,c],
+                                     so the (B,M,C,h,w) tensor of coloured templates is never formed              */
   int B, M, C, h, w, H, W;
   int mode;                       /* SCAE_TMPL_MODE_*                                                     */
 } scae_tmpl_args;
@@ -83,10 +86,12 @@ size_t scae_tmpl_ll_bwd_workspace_bytes(const scae_tmpl_args* a);
 /* Gradients of  sum(grad_log_prob * log_prob)  w.r.t. every differentiable input:
  *   g_templates[B,M,C,h,w], g_pose[B,M,6] (required); g_presence[B,M], g_bg_image[B,C,H,W], g_alpha[M,h,w]
  *   (nullable); g_scalars[4] = d/d raw {bg_value, bg_mixing_logit, temperature_logit, scale} (required; entries
- *   for absent parameters are written as 0).  Deterministic: batch-reduced gradients are summed in a fixed order. */
+ *   for absent parameters are written as 0).  With template_color: g_templates is the batch-reduced [M,C,h,w]
+ *   gradient of the raw templates and g_color[B,M,C] (required then, ignored otherwise) the colour gradient.
+ *   Deterministic: batch-reduced gradients are summed in a fixed order. */
 int scae_tmpl_ll_bwd(const scae_tmpl_args* a, const float* x, const float* grad_log_prob, const float* cache,
-                     float* g_templates, float* g_pose, float* g_presence, float* g_bg_image, float* g_alpha,
-                     float* g_scalars, void* workspace, size_t workspace_bytes, scae_stream_t stream);
+                     float* g_templates, float* g_color, float* g_pose, float* g_presence, float* g_bg_image,
+                     float* g_alpha, float* g_scalars, void* workspace, size_t workspace_bytes, scae_stream_t stream);
 
 /* Materialises what the reference's decoder returns eagerly (part_decoder.py:239-243) and the mixture's point
  * estimates (distributions.py:37-39, :50-77 with straight_through_gradient=False); every output nullable:

@@ -212,3 +212,67 @@ def test_full_size_properties():
     assert rel_err(c['g_templates_alpha'], 2 * a['g_templates_alpha']) < 1e-5
     # templates with zero presence get no template gradient and -inf-like logits do not produce NaNs
     assert bool(torch.isfinite(a['g_templates']).all()) and bool(torch.isfinite(a['g_pose']).all())
+
+
+# ---- fused colourisation: raw templates x per-image colours inside the kernels ---------------
+@pytest.mark.parametrize('cfg', [dict(B=5, M=40, C=1, h=11, w=11, H=40, W=40, alpha=True),
+                                 dict(B=4, M=24, C=3, h=11, w=11, H=32, W=32, alpha=True),
+                                 dict(B=3, M=6, C=2, h=7, w=9, H=12, W=10, alpha=False)])
+def test_fused_colourisation_matches_materialised_templates(cfg):
+    """log_prob(raw, colour) == log_prob(raw * colour) and the raw / colour gradients equal autograd's through the
+    materialised product (TemplateGenerator.forward, part_decoder.py:90-105)."""
+    from torch_scae_b200 import ops
+    B, M, C, h, w, H, W = (cfg[k] for k in ('B', 'M', 'C', 'h', 'w', 'H', 'W'))
+    d = make_template_inputs(B, M, C, h, w, H, W, alpha=cfg['alpha'], seed=11)
+    f32 = lambda t: None if t is None else t.to(DEV, torch.float32)
+    g = torch.Generator().manual_seed(12)
+    raw0 = torch.rand(1, M, C, h, w, generator=g)
+    col0 = torch.rand(B, M, C, generator=g) * 0.5 + 0.5
+    params = {k: f32(v).clone().requires_grad_(True) for k, v in d['params'].items()}
+    x, weight = f32(d['x']), f32(d['weight'])
+
+    def run(fused):
+        raw = f32(raw0).clone().requires_grad_(True)
+        col = f32(col0).clone().requires_grad_(True)
+        pose = f32(d['pose']).clone().requires_grad_(True)
+        pres = f32(d['presence']).clone().requires_grad_(True) if d['presence'] is not None else None
+        for p in params.values():
+            p.grad = None
+        args = (pose, pres, f32(d['bg_image']), x, params.get('templates_alpha'), params.get('bg_value'),
+                params.get('bg_mixing_logit'), params.get('temperature_logit'), params.get('scale'), (H, W))
+        if fused:
+            lp, ll = ops.TemplateMixtureLogProb.apply(raw, *args, col)
+        else:
+            lp, ll = ops.TemplateMixtureLogProb.apply(raw * col[:, :, :, None, None], *args)
+        (lp * weight).sum().backward()
+        out = dict(lp=lp.detach(), ll=ll.detach(), g_raw=raw.grad, g_col=col.grad, g_pose=pose.grad)
+        if pres is not None:
+            out['g_pres'] = pres.grad
+        for k, p in params.items():
+            if p.grad is not None:
+                out['g_' + k] = p.grad.clone()
+        return out
+    a, b = run(True), run(False)
+    assert torch.equal(a['lp'], b['lp'])              # same fp32 product, same kernel arithmetic
+    for k in b:
+        if k.startswith('g_'):
+            assert rel_err(a[k], b[k]) < 2e-5, k
+    assert a['g_raw'].shape == raw0.shape and a['g_col'].shape == col0.shape
+
+
+def test_fused_colourisation_render_and_module_api():
+    from torch_scae_b200.part_decoder import TemplateBasedImageDecoder
+    torch.manual_seed(0)
+    dec = TemplateBasedImageDecoder(n_templates=8, template_size=(7, 7), output_size=(16, 16),
+                                    use_alpha_channel=True).to(DEV)
+    raw = torch.rand(1, 8, 1, 7, 7, device=DEV)
+    col = torch.rand(3, 8, 1, device=DEV) + 0.5
+    pose = torch.randn(3, 8, 6, device=DEV) * 0.3 + torch.tensor([1., 0, 0, 0, 1., 0], device=DEV)
+    pres = torch.rand(3, 8, device=DEV)
+    x = torch.rand(3, 1, 16, 16, device=DEV)
+    with torch.no_grad():
+        fused = dec(raw, pose, pres, template_color=col)
+        plain = dec(raw * col[:, :, :, None, None], pose, pres)
+        assert torch.equal(fused.pdf.log_prob(x), plain.pdf.log_prob(x))
+        assert torch.equal(fused.transformed_templates, plain.transformed_templates)
+        assert torch.equal(fused.pdf.mode(), plain.pdf.mode())

@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_size_
 
 from .build import LIB_PATH
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 TMPL_MODE_ALPHA = 0
 TMPL_MODE_TEMPERATURE = 1
@@ -25,7 +25,7 @@ class ScaeError(RuntimeError):
 
 class TmplArgs(Structure):
     _fields_ = [(n, c_void_p) for n in ('templates', 'templates_alpha', 'pose', 'presence', 'bg_image', 'bg_value',
-                                        'bg_mixing_logit', 'temperature_logit', 'scale')] + \
+                                        'bg_mixing_logit', 'temperature_logit', 'scale', 'template_color')] + \
                [(n, c_int) for n in ('B', 'M', 'C', 'h', 'w', 'H', 'W', 'mode')]
 
 
@@ -67,7 +67,7 @@ SYMBOLS = {
     'scae_launch_count': (c_ulonglong, []),
     'scae_tmpl_ll_fwd': (c_int, [POINTER(TmplArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'scae_tmpl_ll_bwd_workspace_bytes': (c_size_t, [POINTER(TmplArgs)]),
-    'scae_tmpl_ll_bwd': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 10 + [c_size_t, c_void_p]),
+    'scae_tmpl_ll_bwd': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 11 + [c_size_t, c_void_p]),
     'scae_tmpl_render': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 5),
     'scae_caps_ll_fwd': (c_int, [POINTER(CapsArgs), POINTER(CapsOutputs), c_void_p]),
     'scae_caps_ll_bwd_workspace_bytes': (c_size_t, [POINTER(CapsArgs)]),

@@ -28,7 +28,9 @@
 namespace scae {
 
 struct TmplBwdOut {
-  float* g_templates;
+  float* g_templates;       // [B,M,C,h,w]; unused with template_color (see raw_partials)
+  float* g_color;           // [B,M,C]           (template_color only)
+  float* raw_partials;      // [grid][M*C*h*w]   (template_color only): per-CTA sums of colour * texel gradient
   float* g_pose;
   float* g_presence;
   float* g_bg_image;
@@ -216,6 +218,11 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
   float* my_alpha_partial = (kAlpha && out.alpha_partials) ? out.alpha_partials + (size_t)blockIdx.x * a.M * hw : nullptr;
   if (my_alpha_partial)
     for (int e = threadIdx.x; e < a.M * hw; e += blockDim.x) my_alpha_partial[e] = 0.0f;
+  // fused colourisation: the batch-shared raw templates get a per-CTA partial row like the alpha logits
+  const bool colored = a.template_color != nullptr;
+  float* my_raw_partial = colored ? out.raw_partials + (size_t)blockIdx.x * a.M * C * hw : nullptr;
+  if (my_raw_partial)
+    for (int e = threadIdx.x; e < a.M * C * hw; e += blockDim.x) my_raw_partial[e] = 0.0f;
   ScalarAcc acc;
   __syncthreads();   // partial row zeroed before any warp accumulates into it; xs / ys complete
   // row / column of this lane's pixel in the first pass, and its advance per pass
@@ -255,14 +262,17 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
       const float Ay = __ldg(pp + 3) * hw_y, By = __ldg(pp + 4) * hw_y, Cy = (__ldg(pp + 5) + 1.0f) * hw_y + 1.5f;
       const float pres = a.presence ? __ldg(a.presence + (size_t)b * a.M + m) : 1.0f;
       const float lpres = a.presence ? log_safe_f(pres) : 0.0f;
+      const float* src = a.templates + ((colored ? (size_t)0 : (size_t)b * a.M) + m) * C * hw;
+      float colv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) colv[c] = colored ? __ldg(a.template_color + ((size_t)b * a.M + m) * C + c) : 1.0f;
       {
-        const float* src = a.templates + ((size_t)b * a.M + m) * C * hw;
         const float inv_w = 1.0f / (float)a.w;
         for (int e = lane; e < hw; e += 32) {
           const int y = (int)(((float)e + 0.5f) * inv_w), xx = e - y * a.w;
           float* q = atlas + ((size_t)(y + 2) * pw + (xx + 2)) * kPad;
 #pragma unroll
-          for (int c = 0; c < C; ++c) q[c] = __ldg(src + (size_t)c * hw + e);
+          for (int c = 0; c < C; ++c) q[c] = __ldg(src + (size_t)c * hw + e) * colv[c];
           if (kAlpha) q[C] = __ldg(a.templates_alpha + (size_t)m * hw + e);
         }
       }
@@ -403,18 +413,37 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
       __syncwarp();
       // ---- flush + clear the gradient atlas ----------------------------------------------------------------------
       {
-        float* dst = out.g_templates + ((size_t)b * a.M + m) * C * hw;
+        float* dst = colored ? my_raw_partial + (size_t)m * C * hw : out.g_templates + ((size_t)b * a.M + m) * C * hw;
+        float gcol[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) gcol[c] = 0.0f;
         for (int e = lane; e < pw * ph; e += 32) {
           const int yy = (int)(((float)e + 0.5f) * inv_pw), xx = e - yy * pw;
           float* q = gatlas + (size_t)e * kPad;
           if (yy >= 2 && yy < ph - 2 && xx >= 2 && xx < pw - 2) {
             const int te = (yy - 2) * a.w + (xx - 2);
+            if (colored) {
+              // template = raw * colour: d/d raw = colour * g (summed over the batch), d/d colour = sum_texels raw * g
 #pragma unroll
-            for (int c = 0; c < C; ++c) dst[(size_t)c * hw + te] = q[c];
+              for (int c = 0; c < C; ++c) {
+                dst[(size_t)c * hw + te] += colv[c] * q[c];
+                gcol[c] = fmaf(__ldg(src + (size_t)c * hw + te), q[c], gcol[c]);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < C; ++c) dst[(size_t)c * hw + te] = q[c];
+            }
             if (kAlpha && my_alpha_partial) my_alpha_partial[(size_t)m * hw + te] += q[C];
           }
 #pragma unroll
           for (int c = 0; c < kPad; ++c) q[c] = 0.0f;
+        }
+        if (colored) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float t = warp_sum(gcol[c]);
+            if (lane == 0) out.g_color[((size_t)b * a.M + m) * C + c] = t;
+          }
         }
       }
       __syncwarp();
@@ -476,6 +505,9 @@ static int tmpl_bwd_plan(const scae_tmpl_args* a, TmplGeom* gp) {
 static size_t tmpl_ws_alpha_floats(const scae_tmpl_args* a, int grid) {
   return a->mode == SCAE_TMPL_MODE_ALPHA ? (size_t)grid * a->M * a->h * a->w : 0;
 }
+static size_t tmpl_ws_raw_floats(const scae_tmpl_args* a, int grid) {
+  return a->template_color ? (size_t)grid * a->M * a->C * a->h * a->w : 0;
+}
 
 }  // namespace scae
 
@@ -485,29 +517,32 @@ extern "C" __attribute__((visibility("default"))) size_t scae_tmpl_ll_bwd_worksp
   if (tmpl_validate(a) != SCAE_OK) return 0;
   TmplGeom g;
   if (tmpl_bwd_plan(a, &g) != SCAE_OK) return 0;
-  return (tmpl_ws_alpha_floats(a, g.grid) + (size_t)g.grid * 4) * sizeof(float);
+  return (tmpl_ws_alpha_floats(a, g.grid) + tmpl_ws_raw_floats(a, g.grid) + (size_t)g.grid * 4) * sizeof(float);
 }
 
 extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_bwd(
     const scae_tmpl_args* a, const float* x, const float* grad_log_prob, const float* cache, float* g_templates,
-    float* g_pose, float* g_presence, float* g_bg_image, float* g_alpha, float* g_scalars, void* workspace,
-    size_t workspace_bytes, scae_stream_t stream_) {
+    float* g_color, float* g_pose, float* g_presence, float* g_bg_image, float* g_alpha, float* g_scalars,
+    void* workspace, size_t workspace_bytes, scae_stream_t stream_) {
   int rc = tmpl_validate(a);
   if (rc != SCAE_OK) return rc;
   SCAE_REQUIRE(x && grad_log_prob && cache && g_templates && g_pose && g_scalars, SCAE_EINVAL,
                "tmpl bwd: a required pointer is NULL");
+  SCAE_REQUIRE(!a->template_color || g_color, SCAE_EINVAL, "tmpl bwd: g_color is required with template_color");
   TmplGeom g;
   rc = tmpl_bwd_plan(a, &g);
   if (rc != SCAE_OK) return rc;
-  const size_t need = (tmpl_ws_alpha_floats(a, g.grid) + (size_t)g.grid * 4) * sizeof(float);
+  const size_t need =
+      (tmpl_ws_alpha_floats(a, g.grid) + tmpl_ws_raw_floats(a, g.grid) + (size_t)g.grid * 4) * sizeof(float);
   SCAE_REQUIRE(workspace && workspace_bytes >= need, SCAE_EINVAL, "tmpl bwd: workspace too small (%zu < %zu)",
                workspace_bytes, need);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool alpha = a->mode == SCAE_TMPL_MODE_ALPHA;
   float* alpha_partials = static_cast<float*>(workspace);
-  float* scalar_partials = alpha_partials + tmpl_ws_alpha_floats(a, g.grid);
-  TmplBwdOut out{g_templates, g_pose, g_presence, g_bg_image, (alpha && g_alpha) ? alpha_partials : nullptr,
-                 scalar_partials};
+  float* raw_partials = alpha_partials + tmpl_ws_alpha_floats(a, g.grid);
+  float* scalar_partials = raw_partials + tmpl_ws_raw_floats(a, g.grid);
+  TmplBwdOut out{g_templates, g_color, a->template_color ? raw_partials : nullptr, g_pose, g_presence, g_bg_image,
+                 (alpha && g_alpha) ? alpha_partials : nullptr, scalar_partials};
   SCAE_TMPL_DISPATCH(a->C, alpha, {
     auto kern = tmpl_ll_bwd_scan_kernel<kC, kA>;
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
@@ -518,6 +553,10 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_bwd(
   SCAE_CUDA_TRY(cudaGetLastError());
   if (alpha && g_alpha) {
     rc = launch_reduce_rows(alpha_partials, g_alpha, g.grid, a->M * a->h * a->w, stream);
+    if (rc != SCAE_OK) return rc;
+  }
+  if (a->template_color) {
+    rc = launch_reduce_rows(raw_partials, g_templates, g.grid, a->M * a->C * a->h * a->w, stream);
     if (rc != SCAE_OK) return rc;
   }
   return launch_reduce_rows(scalar_partials, g_scalars, g.grid, 4, stream);

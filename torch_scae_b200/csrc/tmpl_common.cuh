@@ -160,7 +160,8 @@ __device__ __forceinline__ void stage_atlas(float* atlas, const scae_tmpl_args& 
   constexpr int kPad = TexTraits<C, kAlpha>::kPad;
   const int hw = a.h * a.w;
   const float inv_w = 1.0f / (float)a.w, inv_hw = 1.0f / (float)hw;
-  const float* src = a.templates + ((size_t)b * a.M + m0) * C * hw;
+  const float* col = a.template_color ? a.template_color + ((size_t)b * a.M + m0) * C : nullptr;   // [mc][C]
+  const float* src = a.templates + ((col ? (size_t)0 : (size_t)b * a.M) + m0) * C * hw;
   const int n = mc * C * hw;
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
     const int plane = (int)(((float)e + 0.5f) * inv_hw);            // (m, c)
@@ -168,7 +169,8 @@ __device__ __forceinline__ void stage_atlas(float* atlas, const scae_tmpl_args& 
     const int y = (int)(((float)rem + 0.5f) * inv_w);
     const int x = rem - y * a.w;
     const int m = plane / C, c = plane - m * C;
-    atlas[(((size_t)m * ph + (y + 2)) * pw + (x + 2)) * kPad + c] = __ldg(src + e);
+    const float v = __ldg(src + e);
+    atlas[(((size_t)m * ph + (y + 2)) * pw + (x + 2)) * kPad + c] = col ? v * __ldg(col + plane) : v;
   }
   if (kAlpha) {
     const float* asrc = a.templates_alpha + (size_t)m0 * hw;
@@ -197,13 +199,16 @@ __device__ __forceinline__ void build_stage_table(int* tab, int C, int h, int w,
 template <int C>
 __device__ __forceinline__ void stage_templates_tab(float* atlas, const int* tab, const scae_tmpl_args& a, int b, int m0,
                                                     int mc, int tex_stride) {
-  const int chw = C * a.h * a.w;
-  const float inv_chw = 1.0f / (float)chw;
-  const float* src = a.templates + ((size_t)b * a.M + m0) * chw;
+  const int hw = a.h * a.w, chw = C * hw;
+  const float inv_chw = 1.0f / (float)chw, inv_hw = 1.0f / (float)hw;
+  const float* col = a.template_color ? a.template_color + ((size_t)b * a.M + m0) * C : nullptr;   // [mc][C]
+  const float* src = a.templates + ((col ? (size_t)0 : (size_t)b * a.M) + m0) * chw;
   const int n = mc * chw;
   for (int e = threadIdx.x; e < n; e += blockDim.x) {
     const int m = (int)(((float)e + 0.5f) * inv_chw);
-    atlas[m * tex_stride + tab[e - m * chw]] = __ldg(src + e);
+    float v = __ldg(src + e);
+    if (col) v *= __ldg(col + (C == 1 ? m : (int)(((float)e + 0.5f) * inv_hw)));   // (m, c) plane index = e / hw
+    atlas[m * tex_stride + tab[e - m * chw]] = v;
   }
 }
 // the batch-shared alpha logits of templates [m0, m0+mc): channel slot C of every texel

@@ -50,10 +50,19 @@ class GaussianMixture:
 class TemplateMixture:
     """Lazy per-pixel mixture over M warped templates + background (part_decoder.py:233-243's ``rec_pdf``)."""
 
-    def __init__(self, decoder, templates, pose, presence, bg_image):
+    def __init__(self, decoder, templates, pose, presence, bg_image, template_color=None):
+        """``template_color`` (B,M,C): fused colourisation -- ``templates`` are then the batch-shared raw templates
+        (1,M,C,h,w) and the per-image templates ``raw * colour`` are formed inside the kernels only."""
         self._decoder = decoder
         self._inputs = (templates, pose, presence, bg_image)
+        self._color = template_color
         self._materialized = None
+
+    def _full_templates(self):
+        templates = self._inputs[0]
+        if self._color is None:
+            return templates
+        return templates.reshape(1, *templates.shape[-4:]) * self._color[:, :, :, None, None]
 
     # ---- the fused hot path ---------------------------------------------------------------------------------------
     def _fused(self, x):
@@ -65,7 +74,7 @@ class TemplateMixture:
             d.bg_value if d.background_value else None,
             d.bg_mixing_logit if d.use_alpha_channel else None,
             None if d.use_alpha_channel else d.temperature_logit,
-            d.scale if d.learn_output_scale else None, tuple(d.output_size))
+            d.scale if d.learn_output_scale else None, tuple(d.output_size), self._color)
 
     def log_prob(self, x):
         """(B,C,H,W) per-pixel log-likelihood; GaussianMixture.log_prob (distributions.py:41-44)."""
@@ -78,7 +87,7 @@ class TemplateMixture:
     # ---- materialised views (off the hot path) --------------------------------------------------------------------
     @property
     def n_components(self):
-        return self._inputs[0].shape[1] + 1
+        return self._inputs[0].shape[-4] + 1
 
     def _render(self, *want):
         templates, pose, presence, bg_image = self._inputs
@@ -87,7 +96,7 @@ class TemplateMixture:
             templates, pose, presence, bg_image, d.templates_alpha if d.use_alpha_channel else None,
             d.bg_value if d.background_value else None, d.bg_mixing_logit if d.use_alpha_channel else None,
             None if d.use_alpha_channel else d.temperature_logit, d.scale if d.learn_output_scale else None,
-            tuple(d.output_size), want)
+            tuple(d.output_size), want, self._color)
 
     def materialize(self):
         """(transformed_templates, mixing_logits) as the reference's decoder returns them.
@@ -98,9 +107,11 @@ class TemplateMixture:
         """
         if self._materialized is None:
             needs_grad = torch.is_grad_enabled() and any(
-                t is not None and t.requires_grad for t in self._inputs + tuple(self._decoder.parameters()))
+                t is not None and t.requires_grad
+                for t in self._inputs + (self._color,) + tuple(self._decoder.parameters()))
             if needs_grad:
-                self._materialized = self._decoder.differentiable_materialize(*self._inputs)
+                self._materialized = self._decoder.differentiable_materialize(self._full_templates(),
+                                                                              *self._inputs[1:])
             else:
                 r = self._render('transformed_templates', 'mixing_logits')
                 self._materialized = (r['transformed_templates'], r['mixing_logits'])
@@ -127,7 +138,8 @@ class TemplateMixture:
 
     def _fast_point_estimate(self, which):
         needs_grad = torch.is_grad_enabled() and any(
-            t is not None and t.requires_grad for t in self._inputs + tuple(self._decoder.parameters()))
+            t is not None and t.requires_grad
+            for t in self._inputs + (self._color,) + tuple(self._decoder.parameters()))
         if needs_grad or self._materialized is not None:
             return None
         return self._render(which)[which]

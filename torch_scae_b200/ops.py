@@ -217,13 +217,21 @@ def attention_pool(feature_map, n_attention_map):
 # =================================================================================================================
 
 def _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit, temperature_logit,
-               scale, output_size):
-    B, M, C, h, w = templates.shape
+               scale, output_size, color=None):
+    """``color`` (B,M,C): fused colourisation -- ``templates`` are then the batch-shared raw templates (1|-,M,C,h,w)."""
+    M, C, h, w = templates.shape[-4:]
+    B = pose.shape[0]
+    if color is not None:
+        if templates.numel() != M * C * h * w or tuple(color.shape) != (B, M, C):
+            raise ValueError(f'fused colourisation needs raw templates (1,M,C,h,w) and colour (B,M,C); got '
+                             f'{tuple(templates.shape)} and {tuple(color.shape)}')
+    elif templates.dim() != 5 or templates.shape[0] != B:
+        raise ValueError(f'templates have shape {tuple(templates.shape)}, expected ({B}, M, C, h, w)')
     H, W = output_size
     alpha_mode = templates_alpha is not None
     a = TmplArgs(ptr(templates), ptr(templates_alpha), ptr(pose), ptr(presence), ptr(bg_image), ptr(bg_value),
                  ptr(bg_mixing_logit) if alpha_mode else None, None if alpha_mode else ptr(temperature_logit),
-                 ptr(scale), B, M, C, h, w, H, W,
+                 ptr(scale), ptr(color), B, M, C, h, w, H, W,
                  _lib.TMPL_MODE_ALPHA if alpha_mode else _lib.TMPL_MODE_TEMPERATURE)
     return a
 
@@ -236,13 +244,14 @@ class TemplateMixtureLogProb(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, templates, pose, presence, bg_image, x, templates_alpha, bg_value, bg_mixing_logit,
-                temperature_logit, scale, output_size):
+                temperature_logit, scale, output_size, color=None):
         lib = _lib.load()
         tensors = [_f32c(t) for t in (templates, pose, presence, bg_image, x, templates_alpha, bg_value,
-                                      bg_mixing_logit, temperature_logit, scale)]
+                                      bg_mixing_logit, temperature_logit, scale, color)]
         templates, pose, presence, bg_image, x, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, \
-            scale = tensors
-        B, M, C, h, w = templates.shape
+            scale, color = tensors
+        M, C, h, w = templates.shape[-4:]
+        B = pose.shape[0]
         H, W = output_size
         if tuple(x.shape) != (B, C, H, W):
             raise ValueError(f'log_prob target has shape {tuple(x.shape)}, expected {(B, C, H, W)}')
@@ -250,7 +259,7 @@ class TemplateMixtureLogProb(torch.autograd.Function):
             # same failure as the reference (part_decoder.py:192 reads self.bg_value)
             raise AttributeError("'TemplateBasedImageDecoder' object has no attribute 'bg_value'")
         args = _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit,
-                          temperature_logit, scale, (H, W))
+                          temperature_logit, scale, (H, W), color)
         log_prob = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
         ll = torch.empty(B, device=x.device, dtype=torch.float32)
         cache = torch.empty(B, 2, C, H, W, device=x.device, dtype=torch.float32)
@@ -268,12 +277,13 @@ class TemplateMixtureLogProb(torch.autograd.Function):
         saved = list(ctx.saved_tensors)
         cache = saved.pop()
         it = iter(saved)
-        templates, pose, presence, bg_image, x, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale = \
-            [next(it) if p else None for p in ctx.present]
-        B, M, C, h, w = templates.shape
+        templates, pose, presence, bg_image, x, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale, \
+            color = [next(it) if p else None for p in ctx.present]
+        M, C, h, w = templates.shape[-4:]
+        B = pose.shape[0]
         H, W = ctx.output_size
         if g_log_prob is None and g_ll is None:
-            return (None,) * 11
+            return (None,) * 12
         if g_ll is not None:
             g = g_ll.reshape(B, 1, 1, 1).expand(B, C, H, W)
             g = g + g_log_prob if g_log_prob is not None else g
@@ -281,9 +291,10 @@ class TemplateMixtureLogProb(torch.autograd.Function):
             g = g_log_prob
         g = _f32c(g)
         args = _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit,
-                          temperature_logit, scale, (H, W))
+                          temperature_logit, scale, (H, W), color)
         dev = templates.device
-        g_templates = torch.empty_like(templates)
+        g_templates = torch.empty_like(templates)            # raw-template gradient (batch-reduced) with colour
+        g_color = torch.empty_like(color) if color is not None else None
         g_pose = torch.empty_like(pose)
         g_presence = torch.empty_like(presence) if presence is not None else None
         g_bg_image = torch.empty_like(bg_image) if bg_image is not None else None
@@ -293,28 +304,30 @@ class TemplateMixtureLogProb(torch.autograd.Function):
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         # kernel launches: the backward kernel + the partial-sum reductions (alpha gradient, scalar gradients)
         check(_timed('scae_tmpl_ll_bwd', lib.scae_tmpl_ll_bwd, ctypes.byref(args),
-                     ptr(x), ptr(g), ptr(cache), ptr(g_templates), ptr(g_pose), ptr(g_presence), ptr(g_bg_image),
-                     ptr(g_alpha), ptr(g_scalars), ptr(ws), ws_bytes, _stream()), 'scae_tmpl_ll_bwd')
+                     ptr(x), ptr(g), ptr(cache), ptr(g_templates), ptr(g_color), ptr(g_pose), ptr(g_presence),
+                     ptr(g_bg_image), ptr(g_alpha), ptr(g_scalars), ptr(ws), ws_bytes, _stream()), 'scae_tmpl_ll_bwd')
 
         def scalar(i, p):
             return g_scalars[i:i + 1].reshape(p.shape) if p is not None else None
         return (g_templates, g_pose, g_presence, g_bg_image, None, g_alpha, scalar(0, bg_value),
-                scalar(1, bg_mixing_logit), scalar(2, temperature_logit), scalar(3, scale), None)
+                scalar(1, bg_mixing_logit), scalar(2, temperature_logit), scalar(3, scale), None, g_color)
 
 
 def template_render(templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit,
-                    temperature_logit, scale, output_size, want=('transformed_templates', 'mixing_logits')):
+                    temperature_logit, scale, output_size, want=('transformed_templates', 'mixing_logits'), color=None):
     """No-grad materialisation through scae_tmpl_render; returns a dict with the requested tensors."""
     lib = _lib.load()
-    templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale = \
+    templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale, color = \
         [_f32c(t.detach()) if t is not None else None for t in (
-            templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale)]
+            templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale,
+            color)]
     if bg_image is None and bg_value is None:
         raise AttributeError("'TemplateBasedImageDecoder' object has no attribute 'bg_value'")
-    B, M, C, h, w = templates.shape
+    M, C, h, w = templates.shape[-4:]
+    B = pose.shape[0]
     H, W = output_size
     args = _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit,
-                      temperature_logit, scale, (H, W))
+                      temperature_logit, scale, (H, W), color)
     dev = templates.device
     shapes = dict(transformed_templates=(B, M + 1, C, H, W),
                   mixing_logits=(B, M + 1, 1 if templates_alpha is not None else C, H, W),

@@ -40,16 +40,26 @@ class TemplateGenerator(nn.Module):
         if colorize_templates:
             self.templates_color_mlp = MLP(sizes=[dim_feature, 32, n_channels])
 
+    def raw_templates(self):
+        """(1,M,C,h,w): the learnt templates after their non-linearity (part_decoder.py:91)."""
+        return self.template_nonlin(self.template_logits)
+
+    def color(self, feature):
+        """(B,M,C) per-image template colours (part_decoder.py:93-103), or None when templates are not coloured."""
+        if not (self.colorize_templates and feature is not None):
+            return None
+        B, M = feature.shape[:2]
+        color = feature.reshape(B * M, -1)
+        for layer in self.templates_color_mlp:          # Linear/ReLU chain; tall-skinny -> split-K weight grads
+            color = skinny.linear(color, layer) if isinstance(layer, nn.Linear) else layer(color)
+        if self.color_nonlin == relu1:
+            color = color + .99
+        return self.color_nonlin(color).view(B, M, -1)
+
     def forward(self, feature=None, batch_size=None):
-        raw_templates = self.template_nonlin(self.template_logits)
-        if self.colorize_templates and feature is not None:
-            B, M = feature.shape[:2]
-            color = feature.reshape(B * M, -1)
-            for layer in self.templates_color_mlp:      # Linear/ReLU chain; tall-skinny -> split-K weight grads
-                color = skinny.linear(color, layer) if isinstance(layer, nn.Linear) else layer(color)
-            if self.color_nonlin == relu1:
-                color = color + .99
-            color = self.color_nonlin(color).view(B, M, -1)
+        raw_templates = self.raw_templates()
+        color = self.color(feature)
+        if color is not None:
             templates = raw_templates * color[:, :, :, None, None]
         else:
             templates = raw_templates.repeat(batch_size, 1, 1, 1, 1)
@@ -84,13 +94,20 @@ class TemplateBasedImageDecoder(nn.Module):
             return F.softplus(self.scale) + 1e-4
         return torch.ones(1, device=self.bg_mixing_logit.device)
 
-    def forward(self, templates, pose, presence=None, bg_image=None):
+    def forward(self, templates, pose, presence=None, bg_image=None, template_color=None):
         """templates (B,M,C,h,w), pose (B,M,6), presence (B,M)|None, bg_image (B,C,H,W)|None -> AttrDict with the
-        reference's keys ``transformed_templates`` (B,M+1,C,H,W), ``mixing_logits``, ``pdf`` (all lazy)."""
-        B, M = templates.shape[:2]
-        if pose.shape[0] != B or pose.shape[1] != M or pose.shape[-1] != 6:
+        reference's keys ``transformed_templates`` (B,M+1,C,H,W), ``mixing_logits``, ``pdf`` (all lazy).
+
+        Extension: with ``template_color`` (B,M,C), ``templates`` are the batch-shared raw
+        templates (1,M,C,h,w) and the coloured per-image templates ``raw * colour`` (TemplateGenerator.forward,
+        part_decoder.py:90-105) exist only inside the kernels."""
+        M = templates.shape[-4]
+        B = pose.shape[0]
+        if template_color is None and (templates.dim() != 5 or templates.shape[0] != B):
+            raise ValueError(f'templates have shape {tuple(templates.shape)}, expected ({B}, M, C, h, w)')
+        if pose.shape[1] != M or pose.shape[-1] != 6:
             raise ValueError(f'pose has shape {tuple(pose.shape)}, expected {(B, M, 6)}')
-        pdf = TemplateMixture(self, templates, pose.reshape(B, M, 6), presence, bg_image)
+        pdf = TemplateMixture(self, templates, pose.reshape(B, M, 6), presence, bg_image, template_color)
         res = LazyAttrDict(pdf=pdf)
         res.set_lazy('transformed_templates', lambda: pdf.transformed_templates)
         res.set_lazy('mixing_logits', lambda: pdf.mixing_logits)

@@ -67,7 +67,29 @@ class SCAE(nn.Module):
         noise = noise or {}
         B = image.shape[0]
         enc = self.part_encoder(image, presence_noise=noise.get('part_presence'))
-        templates = self.template_generator(feature=enc.feature, batch_size=B).templates
+        # Fused colourisation: when the templates are coloured per image and the object
+        # encoder does not need a gradient through them, the decoder gets (raw templates, colours) and the kernels
+        # colour on the fly -- the differentiable (B,M,C,h,w) product and its backward are never formed.  The object
+        # encoder's detached template features are the only materialised copy.
+        gen = self.template_generator
+        fused = self.stop_grad_caps_input and hasattr(gen, 'color') and hasattr(gen, 'raw_templates')
+        color = gen.color(enc.feature) if fused else None
+        if color is not None:
+            raw = gen.raw_templates()
+            with torch.no_grad():
+                templates = raw * color[:, :, :, None, None]            # values only (features / logging)
+
+            def decode(pose, presence, rep=1, detach=False):
+                r, c = (raw.detach(), color.detach()) if detach else (raw, color)
+                return self.part_decoder(templates=r, pose=pose, presence=presence,
+                                         template_color=c if rep == 1 else c.repeat_interleave(rep, dim=0))
+        else:
+            templates = gen(feature=enc.feature, batch_size=B).templates
+
+            def decode(pose, presence, rep=1, detach=False):
+                t = templates.detach() if detach else templates
+                return self.part_decoder(templates=t if rep == 1 else t.repeat_interleave(rep, dim=0), pose=pose,
+                                         presence=presence)
 
         # object encoder input: [pose, 1 - presence, features, flattened templates] per part
         part_param = torch.cat([enc.pose, 1. - enc.presence.unsqueeze(-1)], -1)
@@ -96,25 +118,22 @@ class SCAE(nn.Module):
         dec_pose = {'enc': enc.pose, 'soft': res.soft_winner, 'hard': res.winner}[self.vote_type]
         dec_presence = {'enc': enc.presence, 'soft': res.soft_winner_presence,
                         'hard': res.winner_presence}[self.presence_type]
-        res.rec = self.part_decoder(templates=templates, pose=dec_pose, presence=dec_presence)
+        res.rec = decode(dec_pose, dec_presence)
 
         if self.reconstruct_alternatives:
             # all lazy: nothing is launched until a validation/logging step reads the pdf or the rendered tensors
             with torch.no_grad():
-                t, pres = templates.detach(), enc.presence.detach()
-                res.bottom_up_rec = self.part_decoder(templates=t, pose=enc.pose.detach(), presence=pres)
-                res.top_down_rec = self.part_decoder(templates=t, pose=res.winner.detach(), presence=pres)
+                pres = enc.presence.detach()
+                res.bottom_up_rec = decode(enc.pose.detach(), pres, detach=True)
+                res.top_down_rec = decode(res.winner.detach(), pres, detach=True)
                 O = res.vote.shape[1]
                 td_presence = pres.repeat_interleave(O, dim=0) * res.vote_presence_binary.view(-1, pres.shape[1])
-                res.top_down_per_caps_rec = self.part_decoder(
-                    templates=t.repeat_interleave(O, dim=0), pose=res.vote.detach().view(-1, *res.vote.shape[2:]),
-                    presence=td_presence)
-
+                res.top_down_per_caps_rec = decode(res.vote.detach().view(-1, *res.vote.shape[2:]), td_presence, O,
+                                                   detach=True)
         res.templates = templates
         res.template_presence = enc.presence
         rec = res.rec
         res.set_lazy('transformed_templates', lambda: rec.transformed_templates)
-
         if self.n_classes is not None:
             assert self.prior_classifier is not None
             assert self.posterior_classifier is not None
@@ -122,7 +141,6 @@ class SCAE(nn.Module):
             # sic: the reference feeds the posterior mass through the *prior* head (:211)
             res.posterior_cls_prob = self.prior_classifier(res.posterior_mixing_prob.sum(-1).detach())
         return res
-
     def loss(self, res, reconstruction_target, label=None):
         log = dict()
         pdf = res.rec.pdf
@@ -133,21 +151,17 @@ class SCAE(nn.Module):
             rec_ll = per_pixel.view(per_pixel.shape[0], -1).sum(-1).mean()
         loss = -rec_ll
         log.update(rec_ll_loss=-rec_ll)
-
         if self.recon_mse_weight > 0:
             mse_per_pixel = (reconstruction_target - pdf.mode()) ** 2
             mse = mse_per_pixel.view(mse_per_pixel.shape[0], -1).sum(-1).mean()
             loss = loss + self.recon_mse_weight * mse
             log.update(mse=mse)
-
         if self.part_caps_sparsity_weight > 0:
             part_caps_l1 = res.part_presence.sum(-1).mean()
             loss = loss + self.part_caps_sparsity_weight * part_caps_l1
             log.update(part_caps_loss=part_caps_l1)
-
         loss = loss - self.caps_ll_weight * res.log_prob
         log.update(log_prob_loss=-res.log_prob)
-
         # both sparsity terms are gated by the *prior* weights in the reference (:243-244, :258-259)
         if self.prior_within_example_sparsity_weight > 0 or self.prior_between_example_sparsity_weight > 0:
             within, between = sparsity_loss(self.prior_sparsity_loss_type, res.caps_presence,
@@ -157,7 +171,6 @@ class SCAE(nn.Module):
             loss = loss + self.prior_within_example_sparsity_weight * within \
                 + self.prior_between_example_sparsity_weight * between
             log.update(prior_within_sparsity_loss=within, prior_between_sparsity_loss=between)
-
             n_points = res.posterior_mixing_prob.shape[-1]
             mass = res.posterior_mixing_prob.sum(-1)
             within, between = sparsity_loss(self.posterior_sparsity_loss_type, mass / n_points,
@@ -165,10 +178,8 @@ class SCAE(nn.Module):
             loss = loss + self.posterior_within_example_sparsity_weight * within \
                 + self.posterior_between_example_sparsity_weight * between
             log.update(posterior_within_sparsity_loss=within, posterior_between_sparsity_loss=between)
-
         loss = loss + self.cpr_dynamic_reg_weight * res.cpr_dynamic_reg_loss
         log.update(cpr_dynamic_reg_loss=res.cpr_dynamic_reg_loss)
-
         if label is not None:
             assert self.n_classes is not None
             prior_cls_xe = F.cross_entropy(res.prior_cls_prob, target=label)          # on softmax outputs (sic)
@@ -176,7 +187,6 @@ class SCAE(nn.Module):
             loss = loss + prior_cls_xe + posterior_cls_xe
             log.update(prior_cls_xe=prior_cls_xe, posterior_cls_xe=posterior_cls_xe)
         return loss, log
-
     def calculate_accuracy(self, res, label: torch.Tensor):
         prior_acc = (res.prior_cls_prob.argmax(-1) == label).float().mean()
         posterior_acc = (res.posterior_cls_prob.argmax(-1) == label).float().mean()
