@@ -233,6 +233,24 @@ int scae_attnpool_fwd(const float* h, float* out, long groups, int D, int S, sca
 /* gh[groups, D + 1, S] from g[groups, D] (recomputes the softmax from h). */
 int scae_attnpool_bwd(const float* h, const float* g, float* gh, long groups, int D, int S, scae_stream_t stream);
 
+/* One set-attention block of the object encoder (reference set_transformer.py:74-153: MAB(x, x) with single-head QKV
+ * attention, residual, presence mask, LayerNorm, feed-forward + residual, LayerNorm) on x[B, N, 16], N <= 64, as one
+ * kernel per direction (csrc/sab.cu).  Weights in nn.Linear layout [out, in] = [16, 16], vectors [16]. */
+typedef struct scae_sab_params {
+  const float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo; /* mqkv.{q,k,v,o}_projector                              */
+  const float *wf, *bf;                               /* fc                                                     */
+  const float *ln0_w, *ln0_b, *ln1_w, *ln1_b;         /* ln0, ln1                                               */
+  float eps0, eps1;
+} scae_sab_params;
+/* y[B, N, 16]; presence[B, N] nullable (no mask, no row scaling). */
+int scae_sab_fwd(const float* x, const float* presence, const scae_sab_params* p, int B, int N, float* y,
+                 scae_stream_t stream);
+size_t scae_sab_bwd_workspace_bytes(int B, int N);
+/* gx[B, N, 16]; g_params[1424] = [g_wq | g_wk | g_wv | g_wo | g_wf (256 each) | g_bq g_bk g_bv g_bo g_bf g_ln0_w
+ * g_ln0_b g_ln1_w g_ln1_b (16 each)], summed over the batch in a fixed order.  presence gets no gradient. */
+int scae_sab_bwd(const float* x, const float* presence, const scae_sab_params* p, const float* gy, int B, int N,
+                 float* gx, float* g_params, void* workspace, size_t workspace_bytes, scae_stream_t stream);
+
 /* torch.optim.RMSprop (centered = False, weight_decay = 0; the reference's optimizer, base_experiment.py:47-53) over
  * FLAT buffers of n floats, one pass: square_avg = alpha square_avg + (1 - alpha) g^2; step = g / (sqrt(square_avg) +
  * eps); with momentum_buf: buf = momentum buf + step, param -= lr buf; without (NULL): param -= lr step. */

@@ -29,6 +29,11 @@ class TmplArgs(Structure):
                [(n, c_int) for n in ('B', 'M', 'C', 'h', 'w', 'H', 'W', 'mode')]
 
 
+class SabParams(Structure):
+    _fields_ = [(n, c_void_p) for n in ('wq', 'bq', 'wk', 'bk', 'wv', 'bv', 'wo', 'bo', 'wf', 'bf', 'ln0_w', 'ln0_b',
+                                        'ln1_w', 'ln1_b')] + [('eps0', c_float), ('eps1', c_float)]
+
+
 class CapsArgs(Structure):
     _fields_ = [(n, c_void_p) for n in ('all_param', 'cpr_static', 'bias_cvr', 'bias_caps', 'bias_vote', 'bias_scale',
                                         'noise_caps', 'noise_vote', 'x', 'presence', 'dummy_vote')] + \
@@ -83,6 +88,10 @@ SYMBOLS = {
     'scae_bias_act_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'scae_bias_act_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                   c_size_t, c_void_p]),
+    'scae_sab_fwd': (c_int, [c_void_p, c_void_p, POINTER(SabParams), c_int, c_int, c_void_p, c_void_p]),
+    'scae_sab_bwd_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'scae_sab_bwd': (c_int, [c_void_p, c_void_p, POINTER(SabParams), c_void_p, c_int, c_int, c_void_p, c_void_p,
+                             c_void_p, c_size_t, c_void_p]),
     'scae_rmsprop_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
                                   c_void_p]),
     'scae_attnpool_fwd': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),

@@ -212,6 +212,59 @@ def attention_pool(feature_map, n_attention_map):
     return _AttentionPool.apply(feature_map, B * n_attention_map, D, S).view(B, C - n_attention_map, 1, 1)
 
 
+class _SetAttentionBlock(torch.autograd.Function):
+    """One SAB of the set transformer as a single kernel per direction (csrc/sab.cu).  ``params`` in the order
+    wq bq wk bk wv bv wo bo wf bf ln0_w ln0_b ln1_w ln1_b."""
+
+    @staticmethod
+    def forward(ctx, x, presence, eps0, eps1, *params):
+        lib = _lib.load()
+        x = x.contiguous()
+        presence = presence.contiguous() if presence is not None else None
+        params = tuple(p.contiguous() for p in params)
+        B, N, _ = x.shape
+        sp = _lib.SabParams(*[ptr(p) for p in params], eps0, eps1)
+        y = torch.empty_like(x)
+        check(_timed('scae_sab_fwd', lib.scae_sab_fwd, ptr(x), ptr(presence), ctypes.byref(sp), B, N, ptr(y),
+                     _stream()), 'scae_sab_fwd')
+        ctx.save_for_backward(x, presence, *params)
+        ctx.eps = (eps0, eps1)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, presence, *params = ctx.saved_tensors
+        B, N, _ = x.shape
+        sp = _lib.SabParams(*[ptr(p) for p in params], *ctx.eps)
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        gp = torch.empty(5 * 256 + 9 * 16, device=x.device, dtype=torch.float32)
+        ws_bytes = lib.scae_sab_bwd_workspace_bytes(B, N)
+        ws = _workspace(ws_bytes, x.device)
+        check(_timed('scae_sab_bwd', lib.scae_sab_bwd, ptr(x), ptr(presence), ctypes.byref(sp), ptr(gy), B, N, ptr(gx),
+                     ptr(gp), ptr(ws), ws_bytes, _stream()), 'scae_sab_bwd')
+        w = [gp[k * 256:(k + 1) * 256].view(16, 16) for k in range(5)]          # wq wk wv wo wf
+        v = [gp[1280 + k * 16:1280 + (k + 1) * 16] for k in range(9)]           # bq bk bv bo bf g0 b0 g1 b1
+        grads = (w[0], v[0], w[1], v[1], w[2], v[2], w[3], v[3], w[4], v[4], v[5], v[6], v[7], v[8])
+        return (gx, None, None, None) + grads
+
+
+def set_attention_block(x, presence, mab):
+    """``MAB(x, x, presence)`` of a set_transformer.MAB (n_heads = 1, d = 16, layer_norm) through the fused kernels, or
+    None when the block / input is not covered (the caller then runs the PyTorch ops)."""
+    att = getattr(mab, 'mqkv', None)
+    ok = (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[-1] == 16 and 0 < x.shape[1] <= 64
+          and att is not None and att.n_heads == 1 and att.d_k == 16 and att.d_v == 16 and mab.layer_norm
+          and (presence is None or (not presence.requires_grad and presence.dtype == torch.float32)))
+    if not ok:
+        return None
+    params = (att.q_projector.weight, att.q_projector.bias, att.k_projector.weight, att.k_projector.bias,
+              att.v_projector.weight, att.v_projector.bias, att.o_projector.weight, att.o_projector.bias,
+              mab.fc.weight, mab.fc.bias, mab.ln0.weight, mab.ln0.bias, mab.ln1.weight, mab.ln1.bias)
+    return _SetAttentionBlock.apply(x, presence, float(mab.ln0.eps), float(mab.ln1.eps), *params)
+
+
 # =================================================================================================================
 # hot path 1
 # =================================================================================================================

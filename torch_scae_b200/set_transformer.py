@@ -104,7 +104,9 @@ class SAB(nn.Module):
         self.mab = MAB(d=d, n_heads=n_heads, layer_norm=layer_norm)
 
     def forward(self, x, presence=None):
-        return self.mab(x, x, presence)
+        from . import ops
+        fused = ops.set_attention_block(x, presence, self.mab)    # one kernel per direction (csrc/sab.cu)
+        return fused if fused is not None else self.mab(x, x, presence)
 
 
 class ISAB(nn.Module):
