@@ -45,6 +45,9 @@ const char* scae_build_arch(void);
 /* Number of CUDA kernels this library has launched from the calling thread so far (monotonic; bench.py's launch
  * accounting reads it before and after each entry point). */
 unsigned long long scae_launch_count(void);
+/* Number of scae_caps_ll_fwd / _bwd calls (process-wide) that the TMA-staged fast path (csrc/caps_ll2.cu) served; the
+ * others ran the general kernels (unsupported shape, misaligned pointers, extra upstream gradients). */
+unsigned long long scae_caps_fast_path_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Hot path 1: template warp + per-pixel template-mixture Gaussian log-likelihood

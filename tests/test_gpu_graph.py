@@ -35,8 +35,9 @@ def test_graph_replay_matches_eager_steps():
         if init is not None:
             model.load_state_dict(init)      # (the template initialiser draws from numpy's RNG)
         bucket = ddp.FlatGradBucket(model)
-        opt = torch.optim.RMSprop(model.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / B ** 2, foreach=True,
-                                  capturable=True)
+        # plain SGD: the update is proportional to the gradient, so last-bit differences between two runs stay
+        # last-bit (RMSprop divides by |g| + eps and turns them into O(lr) differences wherever g is ~0)
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
         return model, bucket, opt
 
     # eager
@@ -63,9 +64,10 @@ def test_graph_replay_matches_eager_steps():
         assert abs(le - lg) <= 1e-5 * abs(le), (losses_e, losses_g)
     moved = 0.0
     for (k, pe), pg in zip(model_e.state_dict().items(), model_g.state_dict().values()):
-        assert torch.allclose(pe, pg, rtol=0, atol=2e-6), k
-        moved = max(moved, float((pe - init[k]).abs().max()))
-    assert moved > 1e-5          # the steps did train
+        step_size = float((pe - init[k]).abs().max())
+        assert float((pe - pg).abs().max()) <= 1e-3 * step_size + 1e-7, k
+        moved = max(moved, step_size)
+    assert moved > 1e-4          # the steps did train
 
 
 def test_graph_step_draws_fresh_noise_on_every_replay():

@@ -122,3 +122,21 @@ def test_mid_size_model_vs_cpu_oracle():
     for k in ('part_encoder.att_conv.weight', 'part_encoder.encoder.network.0.weight'):
         got = dict(model.named_parameters())[k].grad
         assert l2_rel_err(got, sd[k].grad) < 2e-3, k
+
+
+def test_train_step_uses_the_capsule_fast_path_with_flat_parameters():
+    """With parameters re-homed into one flat buffer (ddp.FlatGradBucket(flat_params=True)) every parameter must still be
+    16-byte aligned, otherwise hot path 2 silently falls back from the bulk-copy kernels to the general ones."""
+    from torch_scae_b200 import _lib, ddp, factory
+    model = factory.make_scae(dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=32,
+                                   scae_params=dict(reconstruct_alternatives=False))).to(DEV).train()
+    bucket = ddp.FlatGradBucket(model, assign=True, flat_params=True)
+    assert all(p.data_ptr() % 16 == 0 for p in model.parameters())
+    lib = _lib.load()
+    before = lib.scae_caps_fast_path_count()
+    image = torch.rand(16, 1, 40, 40, device=DEV)
+    label = torch.randint(0, 10, (16,), device=DEV)
+    loss, _ = model.loss(model(image), image, label)
+    loss.backward()
+    bucket.collect()
+    assert lib.scae_caps_fast_path_count() - before == 2      # forward and backward

@@ -70,6 +70,7 @@ SYMBOLS = {
     'scae_last_error': (c_char_p, []),
     'scae_build_arch': (c_char_p, []),
     'scae_launch_count': (c_ulonglong, []),
+    'scae_caps_fast_path_count': (c_ulonglong, []),
     'scae_tmpl_ll_fwd': (c_int, [POINTER(TmplArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'scae_tmpl_ll_bwd_workspace_bytes': (c_size_t, [POINTER(TmplArgs)]),
     'scae_tmpl_ll_bwd': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 11 + [c_size_t, c_void_p]),

@@ -1,5 +1,7 @@
 // libscae_b200: error reporting, device attribute cache and the shared row-reduction kernel.
 #include <stdarg.h>
+
+#include <atomic>
 #include <stdio.h>
 
 #include "common.cuh"
@@ -9,7 +11,10 @@ namespace scae {
 static thread_local char g_error[512] = "";
 static thread_local unsigned long long g_launches = 0;
 
+static std::atomic<unsigned long long> g_fast_path{0};   // process-wide: backward calls come from autograd's thread
+
 void note_launch() { ++g_launches; }
+void note_fast_path() { g_fast_path.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -141,6 +146,8 @@ SCAE_EXPORT const char* scae_last_error(void) { return scae::g_error; }
 SCAE_EXPORT const char* scae_build_arch(void) { return "sm_100a"; }
 
 SCAE_EXPORT unsigned long long scae_launch_count(void) { return scae::g_launches; }
+
+SCAE_EXPORT unsigned long long scae_caps_fast_path_count(void) { return scae::g_fast_path.load(); }
 
 SCAE_EXPORT size_t scae_colsum_workspace_bytes(long rows, int cols) {
   if (!scae::colsum_shape_ok(rows, cols)) return 0;

@@ -678,6 +678,7 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_fwd(const sca
   if (!caps_force_v1()) {   // fast path (caps_ll2.cu) when the image's working set fits in shared memory
     bool handled = false;
     rc = caps2_fwd(a, out, stream, &handled);
+    if (handled) note_fast_path();
     if (rc != SCAE_OK || handled) return rc;
   }
   const int imgs = caps_imgs_per_cta(a->V);
@@ -721,6 +722,7 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_bwd(const sca
     bool handled = false;
     rc = caps2_bwd(a, saved, up, g_all_param, g_shared, g_dummy_vote, g_x, g_presence, workspace, workspace_bytes, stream,
                    &handled);
+    if (handled) note_fast_path();
     if (rc != SCAE_OK || handled) return rc;
   }
   const int B = a->B, O = a->O, V = a->V, A = 8 * V + 7, n = O * A;

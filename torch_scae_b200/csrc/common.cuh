@@ -15,6 +15,7 @@ int cuda_fail(cudaError_t e, const char* what);   // records the message, return
 int sm_count();                                   // SM count of the current device (cached per device)
 int max_smem_optin();                             // max dynamic shared memory per block (opt-in) of the device
 void note_launch();                               // counts one kernel launch of this library (scae_launch_count())
+void note_fast_path();                            // counts one hot-path-2 call served by the bulk-copy fast path
 
 #define SCAE_CUDA_TRY(expr)                                        \
   do {                                                             \

@@ -22,7 +22,7 @@ namespace scae {
 
 constexpr int SD = 16;             // feature width (the reference's dim_hidden)
 constexpr int SP = 20;             // padded row stride in floats: quads of 8 consecutive tokens hit distinct banks
-constexpr int kSabThreads = 256;
+constexpr int kSabThreads = 256;   // maximum; a launch uses max(128, 4 N rounded up to a warp) threads
 constexpr int kSabMaxN = 64;       // tokens per image (4 threads per token)
 constexpr int kSabParamFloats = 5 * SD * SD + 9 * SD;   // wq wk wv wo wf | bq bk bv bo bf g0 b0 g1 b1
 
@@ -248,7 +248,7 @@ static inline size_t sab_bwd_smem(int N) {
 }
 
 template <bool kMask>
-__global__ void __launch_bounds__(kSabThreads) sab_fwd_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kSabThreads, 2) sab_fwd_kernel(const float* __restrict__ x,
                                                               const float* __restrict__ presence,
                                                               const scae_sab_params p, int B, int N,
                                                               float* __restrict__ y) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kSabThreads) sab_fwd_kernel(const float* __res
 }
 
 template <bool kMask>
-__global__ void __launch_bounds__(kSabThreads) sab_bwd_kernel(const float* __restrict__ x,
+__global__ void __launch_bounds__(kSabThreads, 2) sab_bwd_kernel(const float* __restrict__ x,
                                                               const float* __restrict__ presence,
                                                               const scae_sab_params p, const float* __restrict__ gy,
                                                               int B, int N, float* __restrict__ gx,
@@ -297,9 +297,9 @@ __global__ void __launch_bounds__(kSabThreads) sab_bwd_kernel(const float* __res
   sab_load_params(W, p);
   const int tid = threadIdx.x, i = min(tid >> 2, N - 1), q = tid & 3;
   const bool tok = tid < 4 * N;
-  // parameter-gradient accumulators: weight entry (o, c) = (tid >> 4, tid & 15) of each of the 5 matrices, and one entry
-  // of the 9 x 16 vector block for the first 144 threads
-  float acc_w[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, acc_v = 0.0f;
+  // parameter-gradient accumulators: entries e = tid, tid + blockDim of the 256-entry weight matrices (e = 16 o + c)
+  // and of the 144-entry vector block; blockDim >= 128, so two slots per thread are enough
+  float acc_w[5][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, acc_v[2] = {0.f, 0.f};
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
@@ -425,33 +425,52 @@ __global__ void __launch_bounds__(kSabThreads) sab_bwd_kernel(const float* __res
     __syncthreads();    // every gradient matrix of the image is complete
     // ---- parameter gradients: d W[o][c] += sum_i G[i][o] IN[i][c] ; vectors: column sums --------------------------------
     {
-      const int o = tid >> 4, c = tid & 15;
       const float* G[5] = {GQ, GK, GV, G0, GF};
       const float* IN[5] = {s.X, s.X, s.X, s.O, s.H2};
+      const float* V9[9] = {GQ, GK, GV, G0, GF, P0, G2, P1, GY};   // bq bk bv bo bf | ln0 gamma, beta | ln1 gamma, beta
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        float a = acc_w[k];
-        for (int t = 0; t < N; ++t) a = fmaf(G[k][t * SP + o], IN[k][t * SP + c], a);
-        acc_w[k] = a;
-      }
-      if (tid < 9 * SD) {
-        const float* V9[9] = {GQ, GK, GV, G0, GF, P0, G2, P1, GY};   // bq bk bv bo bf | ln0 gamma, beta | ln1 gamma, beta
-        const float* src = V9[tid >> 4];
-        float a = acc_v;
-        for (int t = 0; t < N; ++t) a += src[t * SP + c];
-        acc_v = a;
+      for (int u = 0; u < 2; ++u) {
+        const int e = tid + u * (int)blockDim.x;
+        if (e < SD * SD) {
+          const int o = e >> 4, c = e & 15;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            float a = acc_w[k][u];
+            for (int t = 0; t < N; ++t) a = fmaf(G[k][t * SP + o], IN[k][t * SP + c], a);
+            acc_w[k][u] = a;
+          }
+        }
+        if (e < 9 * SD) {
+          const float* src = V9[e >> 4] + (e & 15);
+          float a = acc_v[u];
+          for (int t = 0; t < N; ++t) a += src[t * SP];
+          acc_v[u] = a;
+        }
       }
     }
   }
   float* row = partials + (size_t)blockIdx.x * kSabParamFloats;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) row[k * SD * SD + tid] = acc_w[k];
-  if (tid < 9 * SD) row[5 * SD * SD + tid] = acc_v;
+  for (int u = 0; u < 2; ++u) {
+    const int e = tid + u * (int)blockDim.x;
+    if (e < SD * SD) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) row[k * SD * SD + e] = acc_w[k][u];
+    }
+    if (e < 9 * SD) row[5 * SD * SD + e] = acc_v[u];
+  }
 }
 
-static int sab_grid(int B, size_t smem) {
+static int sab_threads(int N) {
+  const int t = (4 * N + 31) / 32 * 32;
+  return t < 128 ? 128 : t;
+}
+
+static int sab_grid(int B, int N, size_t smem, int regs_per_thread) {
+  const int threads = sab_threads(N);
   int per_sm = (int)(((size_t)max_smem_optin() + 1024) / (smem + 1024));
-  if (per_sm > 2048 / kSabThreads) per_sm = 2048 / kSabThreads;
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  if (per_sm > 65536 / (threads * regs_per_thread)) per_sm = 65536 / (threads * regs_per_thread);
   if (per_sm < 1) per_sm = 1;
   const long slots = (long)sm_count() * per_sm;
   return (int)(B < slots ? B : slots);
@@ -484,7 +503,7 @@ SCAE_EXPORT int scae_sab_fwd(const float* x, const float* presence, const scae_s
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   auto kern = presence ? sab_fwd_kernel<true> : sab_fwd_kernel<false>;
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<sab_grid(B, smem), kSabThreads, smem, stream>>>(x, presence, *p, B, N, y);
+  kern<<<sab_grid(B, N, smem, 104), sab_threads(N), smem, stream>>>(x, presence, *p, B, N, y);
   note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   return SCAE_OK;
@@ -492,7 +511,7 @@ SCAE_EXPORT int scae_sab_fwd(const float* x, const float* presence, const scae_s
 
 SCAE_EXPORT size_t scae_sab_bwd_workspace_bytes(int B, int N) {
   if (B <= 0 || N <= 0 || N > kSabMaxN) return 0;
-  return (size_t)sab_grid(B, sab_bwd_smem(N)) * kSabParamFloats * sizeof(float);
+  return (size_t)sab_grid(B, N, sab_bwd_smem(N), 128) * kSabParamFloats * sizeof(float);
 }
 
 SCAE_EXPORT int scae_sab_bwd(const float* x, const float* presence, const scae_sab_params* p, const float* gy, int B,
@@ -504,14 +523,14 @@ SCAE_EXPORT int scae_sab_bwd(const float* x, const float* presence, const scae_s
                "sab bwd: gy, gx (16-byte aligned) and g_params are required");
   const size_t smem = sab_bwd_smem(N);
   SCAE_REQUIRE(smem <= (size_t)max_smem_optin(), SCAE_ELIMIT, "sab bwd: %zu bytes of shared memory needed", smem);
-  const int grid = sab_grid(B, smem);
+  const int grid = sab_grid(B, N, smem, 128);
   SCAE_REQUIRE(workspace && workspace_bytes >= (size_t)grid * kSabParamFloats * sizeof(float), SCAE_EINVAL,
                "sab bwd: workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   auto kern = presence ? sab_bwd_kernel<true> : sab_bwd_kernel<false>;
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* partials = static_cast<float*>(workspace);
-  kern<<<grid, kSabThreads, smem, stream>>>(x, presence, *p, gy, B, N, gx, partials);
+  kern<<<grid, sab_threads(N), smem, stream>>>(x, presence, *p, gy, B, N, gx, partials);
   note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   return launch_reduce_rows(partials, g_params, grid, kSabParamFloats, stream);

@@ -27,17 +27,17 @@ class FlatGradBucket:
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = process_group
         self.assign = assign
-        n = sum(p.numel() for p in self.params)
+        # every parameter starts on a 16-byte boundary of the flat buffers (sizes rounded up to 4 floats): kernels that
+        # take parameters as raw pointers (bulk copies, float4 loads) rely on that alignment
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, device=ref.device, dtype=ref.dtype)
         self.flat_param = None
         if flat_params:
-            self.flat_param = torch.empty(n, device=ref.device, dtype=ref.dtype)
+            self.flat_param = torch.zeros(n, device=ref.device, dtype=ref.dtype)
         self.views = []
         off = 0
         for p in self.params:
-            # every segment starts on a 16-byte boundary relative to the buffer only if all sizes are multiples of 4;
-            # the flat kernels work on the whole buffer, so per-parameter alignment does not matter
             view = self.flat[off:off + p.numel()].view_as(p)
             self.views.append(view)
             if flat_params:
@@ -46,7 +46,7 @@ class FlatGradBucket:
                     home.copy_(p)
                     p.data = home
             p.grad = None if assign else view      # autograd accumulates into the views in place
-            off += p.numel()
+            off += (p.numel() + 3) // 4 * 4
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
 
     def zero(self):
