@@ -329,6 +329,10 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
         sgyY = fmaf(gty, Y, sgyY);
         spres += glp;
 
+        // Cells that touch no interior texel land in the zero border, whose gradient is discarded.  Parts cover a
+        // fraction of the image, so whole passes miss the template: they keep their logit / presence gradient (above) and
+        // skip the scatter.
+        if (!__any_sync(0xffffffffu, valid && t.interior)) continue;
         // ---- segmented scan over lanes that share (row, cell) -------------------------------------------------------
         // the base-grid Y is strictly increasing with the row, so "same row" is "same Y"
         float v[4][NCH];

@@ -126,6 +126,7 @@ struct PixLse {
 // Bilinear footprint of one (pixel, template): element offset of the north-west tap inside the atlas and the weights.
 struct Tap {
   unsigned off;               // in floats, relative to the atlas base (template offset included)
+  bool interior;              // the cell touches at least one interior (non-border) texel
   float fx, fy;
   float w00, w10, w01, w11;   // nw, ne, sw, se  (ATen grid_sampler_2d naming)
 };
@@ -138,6 +139,8 @@ __device__ __forceinline__ void tap_setup(float tx, float ty, float lim_x, float
   tx = fminf(fmaxf(tx, 0.5f), lim_x);
   ty = fminf(fmaxf(ty, 0.5f), lim_y);
   const float ux = __fadd_rd(tx, kMagic), uy = __fadd_rd(ty, kMagic);   // 2^23 + floor(t): exact floor, no F2I
+  // interior texels sit at 2 .. w + 1, a cell (cx, cy) touches texels cx, cx + 1: interior iff 1 <= cx <= w + 1
+  t.interior = tx >= 1.0f && tx < lim_x - 0.5f && ty >= 1.0f && ty < lim_y - 0.5f;
   t.fx = tx - (ux - kMagic);
   t.fy = ty - (uy - kMagic);
   t.off = __float_as_uint(uy) * row + __float_as_uint(ux) * (unsigned)kPad + base;
