@@ -254,6 +254,11 @@ size_t scae_sab_bwd_workspace_bytes(int B, int N);
 int scae_sab_bwd(const float* x, const float* presence, const scae_sab_params* p, const float* gy, int B, int N,
                  float* gx, float* g_params, void* workspace, size_t workspace_bytes, scae_stream_t stream);
 
+/* cv_ops.geometric_transform(pose, similarity, nonlinear=True, as_matrix=False) (reference cv_ops.py:20-76, as called by
+ * the part encoder, part_encoder.py:110) on rows of 6 raw pose parameters.  g == NULL: out[rows, 6] = the affine
+ * parameters; g != NULL (the gradient w.r.t. them): out[rows, 6] = the gradient w.r.t. t. */
+int scae_pose_transform(const float* t, const float* g, float* out, long rows, int similarity, scae_stream_t stream);
+
 /* torch.optim.RMSprop (centered = False, weight_decay = 0; the reference's optimizer, base_experiment.py:47-53) over
  * FLAT buffers of n floats, one pass: square_avg = alpha square_avg + (1 - alpha) g^2; step = g / (sqrt(square_avg) +
  * eps); with momentum_buf: buf = momentum buf + step, param -= lr buf; without (NULL): param -= lr step. */

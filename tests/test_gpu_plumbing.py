@@ -214,3 +214,19 @@ def test_fused_set_attention_block_matches_pytorch_ops(B, N, pres):
         assert err < 1e-4, (name, err)
     y2 = gpu(x, pr)                                     # the module routes through the fused path, bit-reproducibly
     assert torch.equal(y, y2)
+
+
+@pytest.mark.parametrize('similarity', [False, True])
+def test_pose_transform_matches_reference_formula(similarity):
+    """scae_pose_transform vs cv_ops.geometric_transform's PyTorch formula (cv_ops.py:20-76) in fp64."""
+    from torch_scae_b200 import cv_ops
+    g = torch.Generator().manual_seed(9)
+    t0 = torch.randn(37, 40, 6, generator=g) * 0.7
+    up = torch.randn(37, 40, 6, generator=g)
+    t = t0.cuda().requires_grad_(True)
+    out = cv_ops.geometric_transform(t, similarity)
+    (gt,) = torch.autograd.grad((out * up.cuda()).sum(), [t])
+    t64 = t0.double().requires_grad_(True)
+    ref = cv_ops.geometric_transform(t64, similarity)              # CPU tensor: the PyTorch formula
+    (rt,) = torch.autograd.grad((ref * up.double()).sum(), [t64])
+    assert rel_err(out, ref) < 1e-5 and rel_err(gt, rt) < 1e-5

@@ -93,6 +93,7 @@ SYMBOLS = {
     'scae_sab_bwd_workspace_bytes': (c_size_t, [c_int, c_int]),
     'scae_sab_bwd': (c_int, [c_void_p, c_void_p, POINTER(SabParams), c_void_p, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
+    'scae_pose_transform': (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p]),
     'scae_rmsprop_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
                                   c_void_p]),
     'scae_attnpool_fwd': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),

@@ -302,6 +302,40 @@ __global__ void __launch_bounds__(256) attnpool_bwd_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// cv_ops.geometric_transform (nonlinear=True, as_matrix=False) on rows of 6 pose parameters: thread per row
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool kSim>
+__global__ void __launch_bounds__(256) pose_transform_fwd_kernel(const float* __restrict__ t, float* __restrict__ out,
+                                                                 long rows) {
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long)gridDim.x * blockDim.x) {
+    float v[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = __ldg(t + r * 6 + k);
+    PoseAffine o;
+    pose_affine_fwd<kSim>(v, o);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) out[r * 6 + k] = o.a[k];
+  }
+}
+template <bool kSim>
+__global__ void __launch_bounds__(256) pose_transform_bwd_kernel(const float* __restrict__ t, const float* __restrict__ g,
+                                                                 float* __restrict__ gt, long rows) {
+  for (long r = (long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long)gridDim.x * blockDim.x) {
+    float v[6], ga[6], gv[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      v[k] = __ldg(t + r * 6 + k);
+      ga[k] = __ldg(g + r * 6 + k);
+    }
+    PoseAffine o;
+    pose_affine_fwd<kSim>(v, o);
+    pose_affine_bwd<kSim>(ga, o, gv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) gt[r * 6 + k] = gv[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // RMSprop with momentum over flat parameter / gradient / state buffers: one pass instead of seven foreach launches
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -427,6 +461,25 @@ SCAE_EXPORT int scae_bias_act_bwd(const float* g, const float* y, float* gx, flo
   note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   return launch_reduce_rows(partial, g_bias, slabs, C, stream);
+}
+
+SCAE_EXPORT int scae_pose_transform(const float* t, const float* g, float* out, long rows, int similarity,
+                                    scae_stream_t stream_) {
+  SCAE_REQUIRE(t && out && rows > 0, SCAE_EINVAL, "pose_transform: t, out and rows > 0 are required");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  long grid = (rows + 255) / 256;
+  const long cap = 8L * sm_count();
+  if (grid > cap) grid = cap;
+  if (g == nullptr) {
+    if (similarity) pose_transform_fwd_kernel<true><<<(int)grid, 256, 0, stream>>>(t, out, rows);
+    else pose_transform_fwd_kernel<false><<<(int)grid, 256, 0, stream>>>(t, out, rows);
+  } else {
+    if (similarity) pose_transform_bwd_kernel<true><<<(int)grid, 256, 0, stream>>>(t, g, out, rows);
+    else pose_transform_bwd_kernel<false><<<(int)grid, 256, 0, stream>>>(t, g, out, rows);
+  }
+  note_launch();
+  SCAE_CUDA_TRY(cudaGetLastError());
+  return SCAE_OK;
 }
 
 SCAE_EXPORT int scae_rmsprop_step(float* param, const float* grad, float* square_avg, float* momentum_buf, long n,

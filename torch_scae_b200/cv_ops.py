@@ -10,6 +10,11 @@ import torch
 
 
 def geometric_transform(pose_tensor, similarity=False, nonlinear=True, as_matrix=False):
+    if nonlinear and not as_matrix and pose_tensor.is_cuda:
+        from . import ops
+        fused = ops.pose_transform(pose_tensor, similarity)      # ~60 tiny launches fwd + bwd -> one kernel each
+        if fused is not None:
+            return fused
     sx, sy, theta, shear, tx, ty = pose_tensor.unbind(-1)
     if nonlinear:
         sx, sy = torch.sigmoid(sx) + 1e-2, torch.sigmoid(sy) + 1e-2

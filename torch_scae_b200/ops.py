@@ -212,6 +212,37 @@ def attention_pool(feature_map, n_attention_map):
     return _AttentionPool.apply(feature_map, B * n_attention_map, D, S).view(B, C - n_attention_map, 1, 1)
 
 
+class _PoseTransform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, similarity):
+        lib = _lib.load()
+        t = t.contiguous()
+        out = torch.empty_like(t)
+        rows = t.numel() // 6
+        check(_timed('scae_pose_transform', lib.scae_pose_transform, ptr(t), None, ptr(out), rows, int(similarity),
+                     _stream()), 'scae_pose_transform')
+        ctx.save_for_backward(t)
+        ctx.similarity = similarity
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (t,) = ctx.saved_tensors
+        gt = torch.empty_like(t)
+        check(_timed('scae_pose_transform', lib.scae_pose_transform, ptr(t), ptr(g.contiguous()), ptr(gt),
+                     t.numel() // 6, int(ctx.similarity), _stream()), 'scae_pose_transform')
+        return gt, None
+
+
+def pose_transform(pose_tensor, similarity):
+    """cv_ops.geometric_transform(nonlinear=True, as_matrix=False) as one kernel per direction; None when not covered."""
+    if not (pose_tensor.is_cuda and pose_tensor.dtype == torch.float32 and pose_tensor.shape[-1] == 6
+            and pose_tensor.numel() > 0):
+        return None
+    return _PoseTransform.apply(pose_tensor, bool(similarity))
+
+
 class _SetAttentionBlock(torch.autograd.Function):
     """One SAB of the set transformer as a single kernel per direction (csrc/sab.cu).  ``params`` in the order
     wq bq wk bk wv bv wo bo wf bf ln0_w ln0_b ln1_w ln1_b."""
