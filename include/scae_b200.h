@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SCAE_B200_ABI_VERSION 2
+#define SCAE_B200_ABI_VERSION 3
 
 #define SCAE_OK 0
 #define SCAE_EINVAL (-1)   /* bad shape / flag / NULL where a pointer is required / misaligned pointer */
@@ -258,6 +258,46 @@ int scae_sab_bwd(const float* x, const float* presence, const scae_sab_params* p
  * the part encoder, part_encoder.py:110) on rows of 6 raw pose parameters.  g == NULL: out[rows, 6] = the affine
  * parameters; g != NULL (the gradient w.r.t. them): out[rows, 6] = the gradient w.r.t. t. */
 int scae_pose_transform(const float* t, const float* g, float* out, long rows, int similarity, scae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Loss head (csrc/loss_head.cu): the (B,O)-sized tail of SCAE.loss on the outputs of hot
+ * path 2, one forward and one backward call instead of ~130 stock launches.  Replaces, with identical results,
+ *   - capsule_l2_loss / capsule_entropy_loss / neg_capsule_kl (reference object_decoder.py:431-493) as called by
+ *     SCAE.loss (stacked_capsule_auto_encoder.py:243-271): the prior term on caps_presence[B,O] and the posterior term on
+ *     posterior_mixing_prob[B,O,V].sum(-1) / V;
+ *   - the classifier heads softmax(linear(x)) on the DETACHED caps_presence and posterior mass, both through
+ *     prior_classifier (sic, :203-213), and F.cross_entropy applied to their softmax OUTPUTS (sic, :279-285).
+ * O <= 64, K <= 16.  Deterministic (fixed-order batch sums).  Batch statistics are those of the B rows passed in (the
+ * reference's semantics under Lightning DDP; the sync_batch_stats extension stays in PyTorch).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define SCAE_LOSS_L2 0      /* capsule_l2_loss                                   */
+#define SCAE_LOSS_ENTROPY 1 /* capsule_entropy_loss, k = 1                       */
+#define SCAE_LOSS_KL 2      /* neg_capsule_kl = capsule_entropy_loss with k = O  */
+
+typedef struct scae_loss_head_args {
+  const float* caps_presence; /* [B,O]                                                                          */
+  const float* posterior;     /* [B,O,V] posterior_mixing_prob                                                  */
+  const long long* label;     /* [B] int64 class labels; NULL: no classifier terms                              */
+  const float* cls_weight;    /* [K,O] prior_classifier[0].weight (required with label)                         */
+  const float* cls_bias;      /* [K]   prior_classifier[0].bias                                                 */
+  int B, O, V, K;
+  int sparsity;               /* 0: no sparsity terms (both prior weights are 0, stacked_capsule_auto_encoder.py:243) */
+  int prior_type, posterior_type; /* SCAE_LOSS_*                                                                */
+  float prior_within_weight, prior_between_weight, posterior_within_weight, posterior_between_weight;
+  float prior_within_constant, posterior_within_constant; /* l2 only: O / n_classes unless overridden           */
+  float between_constant;     /* l2 only: B / n_classes                                                         */
+} scae_loss_head_args;
+
+size_t scae_loss_head_workspace_bytes(const scae_loss_head_args* a); /* 0 when the shape is not supported */
+/* terms[8] = {prior within, prior between, posterior within, posterior between, prior xe, posterior xe, TOTAL, 0}
+ * with TOTAL = sum of weight * sparsity term + both cross-entropies (what SCAE.loss adds to its loss);
+ * cls_prob[2,B,K] nullable = prior_cls_prob | posterior_cls_prob; stats[128] is what the backward needs. */
+int scae_loss_head_fwd(const scae_loss_head_args* a, float* terms, float* cls_prob, float* stats, void* workspace,
+                       size_t workspace_bytes, scae_stream_t stream);
+/* g_total: DEVICE scalar, the gradient w.r.t. TOTAL.  g_caps_presence[B,O] and g_posterior[B,O,V] (nullable; written
+ * only when sparsity != 0); g_cls[K*O + K] = gradient of cls_weight | cls_bias (required with label). */
+int scae_loss_head_bwd(const scae_loss_head_args* a, const float* stats, const float* g_total, float* g_caps_presence,
+                       float* g_posterior, float* g_cls, void* workspace, size_t workspace_bytes, scae_stream_t stream);
 
 /* torch.optim.RMSprop (centered = False, weight_decay = 0; the reference's optimizer, base_experiment.py:47-53) over
  * FLAT buffers of n floats, one pass: square_avg = alpha square_avg + (1 - alpha) g^2; step = g / (sqrt(square_avg) +

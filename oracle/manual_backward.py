@@ -284,3 +284,93 @@ def template_forward_backward(templates, pose, x, grad_out, presence=None, bg_im
                           (g_gy * Xs).sum((2, 3)), (g_gy * Ys).sum((2, 3)), g_gy.sum((2, 3))], -1)
     return dict(log_prob=log_prob, g_templates=g_templates.view(B, M, C, h, w), g_pose=g_pose, g_presence=g_presence,
                 g_bg_image=g_bg_image, g_alpha=g_alpha.view(M, h, w) if alpha_mode else None, g_scalars=g_scalars)
+
+
+# =============================================================================================================
+# loss head: capsule sparsity losses + classifier cross-entropies
+# =============================================================================================================
+
+LOG_SAFE_EPS, LOG_SAFE_FLOOR = 1e-16, -1e8
+
+
+def _head_within(kind, x, within_constant):
+    """Per-row within-example term t[B] and d t / d x [B,O] (object_decoder.py:431-470).  ``kind``: 'l2' |
+    'entropy' | 'kl'."""
+    rs = x.sum(1, keepdim=True)
+    if kind == 'l2':
+        d = rs - within_constant
+        return (d * d).squeeze(1), (2.0 * d).expand_as(x)
+    k = 1.0 if kind == 'entropy' else float(x.shape[1])
+    den = rs + 1e-8
+    p = x / den
+    tiny = p * k < LOG_SAFE_EPS
+    L = torch.where(tiny, torch.full_like(p, LOG_SAFE_FLOOR), torch.log(torch.where(tiny, torch.ones_like(p), p * k)))
+    t = -(p * L).sum(1)
+    gp = -(L + (~tiny).to(x.dtype))            # d/dp of -sum p log_safe(k p): log_safe passes no gradient when tiny
+    dot = (gp * p).sum(1, keepdim=True)
+    return t, (gp - dot) / den
+
+
+def _head_between(kind, col, batch_size, n_classes):
+    """Between-example term (scalar) and its gradient w.r.t. the column sums col[O]."""
+    O = col.shape[0]
+    if kind == 'l2':
+        d = col - float(batch_size) / n_classes
+        return (d * d).mean(), 2.0 * d / O
+    t, g = _head_within(kind, col.unsqueeze(0), None)
+    return -t[0], -g[0]                        # negated: this entropy is to be increased (object_decoder.py:469)
+
+
+def _head_classifier(x, weight, bias, label):
+    """mean cross_entropy(softmax(linear(x)), label) -- on softmax OUTPUTS, sic (stacked_capsule_auto_encoder.py:
+    67-74, :281-282) -- with the gradients of the head's weight / bias; x is detached in the reference (:209-211)."""
+    B = x.shape[0]
+    p = torch.softmax(x @ weight.t() + bias, -1)
+    u = torch.log_softmax(p, -1)
+    onehot = F.one_hot(label, p.shape[1]).to(x.dtype)
+    xe = -(u * onehot).sum(1).mean()
+    r = torch.softmax(p, -1) - onehot
+    dz = p * (r - (p * r).sum(1, keepdim=True)) / B
+    return xe, p, dz.t() @ x, dz.sum(0)
+
+
+def loss_head_forward_backward(caps_presence, posterior, label, weight, bias, n_classes, prior_type, posterior_type,
+                               weights, within_constant=None, sparsity=True):
+    """What csrc/loss_head.cu computes.  caps_presence [B,O], posterior [B,O,V] (posterior_mixing_prob), label [B]
+    int64 | None, weight [K,O] / bias [K] of prior_classifier[0] (used for BOTH heads, sic :211), ``weights`` =
+    (prior within, prior between, posterior within, posterior between).  Returns terms (6 scalars, 0 where off), the
+    weighted total, the two class-probability matrices and the gradients of the total."""
+    B, O, V = posterior.shape
+    dt = posterior.dtype
+    zero = torch.zeros((), dtype=dt)
+    terms = [zero] * 6
+    g_cp = torch.zeros_like(caps_presence)
+    g_post = torch.zeros_like(posterior)
+    g_w = torch.zeros_like(weight) if weight is not None else None
+    g_b = torch.zeros_like(bias) if bias is not None else None
+    mass = posterior.sum(-1)
+    total = zero
+    if sparsity:
+        wc = float(O) / n_classes if (within_constant is None and n_classes) else within_constant
+        for slot, (kind, x, c, scale) in enumerate(((prior_type, caps_presence, wc, 1.0),
+                                                    (posterior_type, mass / V,
+                                                     float(O) / n_classes if n_classes else None, 1.0 / V))):
+            ww, wb = weights[2 * slot], weights[2 * slot + 1]
+            t, gx = _head_within(kind, x, c)
+            tb, gcol = _head_between(kind, x.sum(0), B, n_classes)
+            terms[2 * slot], terms[2 * slot + 1] = t.mean(), tb
+            total = total + ww * t.mean() + wb * tb
+            g = (ww * gx / B + wb * gcol.unsqueeze(0)) * scale
+            if slot == 0:
+                g_cp = g
+            else:
+                g_post = g.unsqueeze(-1).expand(B, O, V).clone()
+    probs = [None, None]
+    if label is not None:
+        for slot, x in enumerate((caps_presence, mass)):
+            xe, p, gw, gb = _head_classifier(x, weight, bias, label)
+            terms[4 + slot], probs[slot] = xe, p
+            total = total + xe
+            g_w, g_b = g_w + gw, g_b + gb
+    return dict(terms=torch.stack(terms), total=total, prior_cls_prob=probs[0], posterior_cls_prob=probs[1],
+                g_caps_presence=g_cp, g_posterior=g_post, g_weight=g_w, g_bias=g_b)

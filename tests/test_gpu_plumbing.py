@@ -230,3 +230,148 @@ def test_pose_transform_matches_reference_formula(similarity):
     ref = cv_ops.geometric_transform(t64, similarity)              # CPU tensor: the PyTorch formula
     (rt,) = torch.autograd.grad((ref * up.double()).sum(), [t64])
     assert rel_err(out, ref) < 1e-5 and rel_err(gt, rt) < 1e-5
+
+
+def _loss_head_reference(cp, post, label, weight, bias, K, prior_type, posterior_type, ws, sparsity):
+    """The PyTorch ops of SCAE.loss (stacked_capsule_auto_encoder.py:243-285) in fp64 on the CPU, with autograd."""
+    import torch.nn.functional as F
+    from torch_scae_b200.object_decoder import sparsity_loss
+    leaves = [t.double().clone().requires_grad_(True) for t in (cp, post, weight, bias)]
+    a, b, w_, b_ = leaves
+    V = post.shape[-1]
+    total, terms = 0.0, [torch.zeros((), dtype=torch.float64)] * 6
+    if sparsity:
+        pw, pb = sparsity_loss(prior_type, a, n_classes=K, within_example_constant=None)
+        qw, qb = sparsity_loss(posterior_type, b.sum(-1) / V, n_classes=K)
+        total = ws[0] * pw + ws[1] * pb + ws[2] * qw + ws[3] * qb
+        terms[:4] = [pw, pb, qw, qb]
+    probs = None
+    if label is not None:
+        p1 = torch.softmax(F.linear(a.detach(), w_, b_), -1)
+        p2 = torch.softmax(F.linear(b.sum(-1).detach(), w_, b_), -1)
+        terms[4:] = [F.cross_entropy(p1, label), F.cross_entropy(p2, label)]
+        total = total + terms[4] + terms[5]
+        probs = torch.stack([p1, p2])
+    grads = torch.autograd.grad(total * 1.7, leaves, allow_unused=True)
+    return total, torch.stack([t.detach() for t in terms]), probs, grads
+
+
+@pytest.mark.parametrize('B,O,V,K', [(37, 10, 40, 10), (1024, 32, 40, 10), (64, 40, 24, 16), (5, 64, 7, 3),
+                                      (300, 33, 6, 2)])
+@pytest.mark.parametrize('prior_type,posterior_type', [('l2', 'entropy'), ('entropy', 'kl'), ('kl', 'l2')])
+@pytest.mark.parametrize('with_label', [True, False])
+def test_loss_head_matches_pytorch_ops(B, O, V, K, prior_type, posterior_type, with_label):
+    """scae_loss_head_fwd/bwd vs the stock ops they replace (object_decoder.py:431-493 sparsity losses, classifier heads
+    and cross-entropies on softmax outputs, stacked_capsule_auto_encoder.py:203-213,:279-285), values and gradients."""
+    from torch_scae_b200 import ops
+    g = torch.Generator().manual_seed(B + O + V)
+    cp = torch.rand(B, O, generator=g)
+    post = torch.rand(B, O, V, generator=g) / O
+    label = torch.randint(0, K, (B,), generator=g) if with_label else None
+    lin = torch.nn.Linear(O, K)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(K, O, generator=g) * 0.3)
+        lin.bias.copy_(torch.randn(K, generator=g) * 0.3)
+    ws = (2.0, 0.35, 0.7, 0.2)
+    ref_total, ref_terms, ref_probs, ref_grads = _loss_head_reference(
+        cp, post, label, lin.weight.detach(), lin.bias.detach(), K, prior_type, posterior_type, ws, True)
+
+    lin = lin.cuda()
+    cpd, postd = cp.cuda().requires_grad_(True), post.cuda().requires_grad_(True)
+    out = ops.loss_head(cpd, postd, label.cuda() if with_label else None, lin if with_label else None, K, prior_type,
+                        posterior_type, ws)
+    assert out is not None
+    total, terms, probs = out
+    assert rel_err(total, ref_total) < 1e-5
+    for i in range(6 if with_label else 4):
+        assert abs(float(terms[i]) - float(ref_terms[i])) <= 1e-5 * abs(float(ref_terms[i])) + 1e-7, i
+    assert rel_err(terms[6], ref_total) < 1e-5
+    wanted = [cpd, postd] + ([lin.weight, lin.bias] if with_label else [])
+    grads = torch.autograd.grad(total * 1.7, wanted)
+    for name, got, ref in zip(('caps_presence', 'posterior', 'weight', 'bias'), grads, ref_grads):
+        assert rel_err(got, ref) < 1e-4, name
+    if with_label:
+        assert rel_err(probs, ref_probs) < 1e-5
+    # bit-reproducible (fixed summation orders)
+    total2, terms2, _ = ops.loss_head(cpd, postd, label.cuda() if with_label else None, lin if with_label else None, K,
+                                      prior_type, posterior_type, ws)
+    assert torch.equal(terms, terms2) and torch.equal(total, total2)
+
+
+def test_loss_head_log_safe_floor_and_classifier_only():
+    """Zero capsule presences hit log_safe's -1e8 floor in the entropy losses (math_ops.py:18-22); and with both prior
+    weights 0 the reference skips the sparsity terms (stacked_capsule_auto_encoder.py:243) but keeps the classifiers."""
+    from torch_scae_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    B, O, V, K = 19, 12, 8, 10
+    cp = torch.rand(B, O, generator=g)
+    cp[3, 5] = 0.0
+    post = torch.rand(B, O, V, generator=g) / O
+    post[7, 2] = 0.0
+    label = torch.randint(0, K, (B,), generator=g)
+    lin = torch.nn.Linear(O, K)
+    ws = (1.0, 1.0, 1.0, 1.0)
+    for sparsity in (True, False):
+        ref_total, ref_terms, _, ref_grads = _loss_head_reference(cp, post, label, lin.weight.detach(),
+                                                                  lin.bias.detach(), K, 'entropy', 'entropy', ws, sparsity)
+        lin_d = torch.nn.Linear(O, K).cuda()
+        lin_d.load_state_dict(lin.state_dict())
+        cpd, postd = cp.cuda().requires_grad_(True), post.cuda().requires_grad_(True)
+        total, terms, _ = ops.loss_head(cpd, postd, label.cuda(), lin_d, K, 'entropy', 'entropy', ws, sparsity=sparsity)
+        assert rel_err(total, ref_total) < 1e-5
+        for i in range(6):
+            assert abs(float(terms[i]) - float(ref_terms[i])) <= 1e-5 * abs(float(ref_terms[i])) + 1e-7, i
+        grads = torch.autograd.grad(total * 1.7, [cpd, postd, lin_d.weight, lin_d.bias], allow_unused=True)
+        for name, got, ref in zip(('caps_presence', 'posterior', 'weight', 'bias'), grads, ref_grads):
+            if ref is None:
+                assert got is None or float(got.abs().max()) == 0.0, name
+            else:
+                assert rel_err(got, ref) < 1e-4, name
+
+
+def test_scae_loss_uses_the_loss_head_and_matches_the_pytorch_tail():
+    """SCAE.loss through the fused loss head vs the same model with the head disabled (stock PyTorch ops): loss, log
+    entries, class probabilities and every parameter gradient."""
+    from golden.cases import tiny_model_params
+    from torch_scae_b200 import factory
+    from torch_scae_b200.stacked_capsule_auto_encoder import SCAE
+    torch.manual_seed(5)
+    model = factory.make_scae(tiny_model_params()).cuda().train()
+    image = torch.rand(6, 1, 20, 20, device='cuda')
+    label = torch.randint(0, 10, (6,), device='cuda')
+    M, O = model.part_encoder.n_caps, model.obj_decoder.n_obj_capsules
+    noise = dict(part_presence=(torch.rand(6, M, device='cuda') - .5) * 4,
+                 caps=(torch.rand(6, O, 1, device='cuda') - .5) * 4, vote=(torch.rand(6, O, M, device='cuda') - .5) * 4)
+
+    def run(fused):
+        model.zero_grad(set_to_none=True)
+        res = model(image, noise=noise)
+        if fused:
+            loss, log = model.loss(res, image, label)
+        else:
+            orig = SCAE._fused_loss_head
+            SCAE._fused_loss_head = lambda self, res, label: None
+            try:
+                loss, log = model.loss(res, image, label)
+            finally:
+                SCAE._fused_loss_head = orig
+        loss.backward()
+        acc = model.calculate_accuracy(res, label)
+        return loss, log, res, acc, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    from torch_scae_b200 import ops
+    with ops.KernelTimer() as timer:
+        loss_f, log_f, res_f, acc_f, grads_f = run(True)
+    torch.cuda.synchronize()
+    assert 'scae_loss_head_fwd' in timer.summary() and 'scae_loss_head_bwd' in timer.summary()
+    loss_e, log_e, res_e, acc_e, grads_e = run(False)
+    assert rel_err(loss_f, loss_e) < 1e-6
+    assert set(log_f) == set(log_e)
+    for k in log_e:
+        assert rel_err(log_f[k], log_e[k]) < 1e-5, k
+    assert rel_err(res_f.prior_cls_prob, res_e.prior_cls_prob) < 1e-5
+    assert rel_err(res_f.posterior_cls_prob, res_e.posterior_cls_prob) < 1e-5
+    assert float(acc_f) == float(acc_e)
+    assert set(grads_f) == set(grads_e)
+    for k in grads_e:
+        assert rel_err(grads_f[k], grads_e[k]) < 1e-4, k

@@ -39,7 +39,7 @@ def test_ctypes_structs_match_header_field_order():
         return names
     for struct, cls in (('scae_tmpl_args', _lib.TmplArgs), ('scae_caps_args', _lib.CapsArgs),
                         ('scae_caps_outputs', _lib.CapsOutputs), ('scae_caps_upstream', _lib.CapsUpstream),
-                        ('scae_caps_saved', _lib.CapsSaved)):
+                        ('scae_caps_saved', _lib.CapsSaved), ('scae_loss_head_args', _lib.LossHeadArgs)):
         assert fields(struct) == [f[0] for f in cls._fields_], struct
 
 

@@ -104,3 +104,43 @@ def test_template_manual_backward(case):
     for i, name in enumerate(('bg_value', 'bg_mixing_logit', 'temperature_logit', 'scale')):
         if name in params and params[name].grad is not None:
             assert rel_err(got['g_scalars'][i], params[name].grad.reshape(())) < 1e-9, name
+
+
+@pytest.mark.parametrize('prior_type,posterior_type', [('l2', 'entropy'), ('entropy', 'kl'), ('kl', 'l2')])
+@pytest.mark.parametrize('with_label', [True, False])
+def test_loss_head_manual_backward(prior_type, posterior_type, with_label):
+    """The loss-head formulas (sparsity losses + classifier cross-entropies on softmax outputs) vs autograd through the
+    product's PyTorch restatement of object_decoder.py:431-493 / stacked_capsule_auto_encoder.py:243-285."""
+    import torch.nn.functional as F
+    from torch_scae_b200.object_decoder import sparsity_loss
+    torch.manual_seed(3)
+    B, O, V, K = 7, 5, 4, 3
+    cp = torch.rand(B, O, dtype=F64)
+    cp[2, 1] = 0.0                                      # log_safe's floor branch (k p < 1e-16)
+    post = torch.rand(B, O, V, dtype=F64)
+    post[4, 3] = 0.0
+    label = torch.randint(0, K, (B,)) if with_label else None
+    weight, bias = torch.randn(K, O, dtype=F64), torch.randn(K, dtype=F64)
+    ws = (2.0, 0.35, 0.7, 0.2)
+    leaves = [t.clone().requires_grad_(True) for t in (cp, post, weight, bias)]
+    a, b, w_, b_ = leaves
+    pw, pb = sparsity_loss(prior_type, a, n_classes=K, within_example_constant=None)
+    qw, qb = sparsity_loss(posterior_type, b.sum(-1) / V, n_classes=K)
+    total = ws[0] * pw + ws[1] * pb + ws[2] * qw + ws[3] * qb
+    terms = [pw, pb, qw, qb]
+    if with_label:
+        p1 = torch.softmax(F.linear(a.detach(), w_, b_), -1)
+        p2 = torch.softmax(F.linear(b.sum(-1).detach(), w_, b_), -1)
+        x1, x2 = F.cross_entropy(p1, label), F.cross_entropy(p2, label)
+        total = total + x1 + x2
+        terms += [x1, x2]
+    grads = torch.autograd.grad(total, leaves, allow_unused=True)
+    got = mb.loss_head_forward_backward(cp, post, label, weight, bias, K, prior_type, posterior_type, ws)
+    assert rel_err(got['total'], total) < 1e-12
+    for i, t in enumerate(terms):
+        assert rel_err(got['terms'][i], t) < 1e-12, i
+    assert rel_err(got['g_caps_presence'], grads[0]) < 1e-10
+    assert rel_err(got['g_posterior'], grads[1]) < 1e-10
+    if with_label:
+        assert rel_err(got['prior_cls_prob'], p1) < 1e-12 and rel_err(got['posterior_cls_prob'], p2) < 1e-12
+        assert rel_err(got['g_weight'], grads[2]) < 1e-10 and rel_err(got['g_bias'], grads[3]) < 1e-10

@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_size_
 
 from .build import LIB_PATH
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 TMPL_MODE_ALPHA = 0
 TMPL_MODE_TEMPERATURE = 1
@@ -17,6 +17,7 @@ CAPS_SIMILARITY = 1
 CAPS_LEARN_VOTE_SCALE = 2
 CAPS_ALLOW_DEFORM = 4
 CAPS_RELU_GRAD = 8
+LOSS_TYPES = {'l2': 0, 'entropy': 1, 'kl': 2}
 
 
 class ScaeError(RuntimeError):
@@ -32,6 +33,14 @@ class TmplArgs(Structure):
 class SabParams(Structure):
     _fields_ = [(n, c_void_p) for n in ('wq', 'bq', 'wk', 'bk', 'wv', 'bv', 'wo', 'bo', 'wf', 'bf', 'ln0_w', 'ln0_b',
                                         'ln1_w', 'ln1_b')] + [('eps0', c_float), ('eps1', c_float)]
+
+
+class LossHeadArgs(Structure):
+    _fields_ = [(n, c_void_p) for n in ('caps_presence', 'posterior', 'label', 'cls_weight', 'cls_bias')] + \
+               [(n, c_int) for n in ('B', 'O', 'V', 'K', 'sparsity', 'prior_type', 'posterior_type')] + \
+               [(n, c_float) for n in ('prior_within_weight', 'prior_between_weight', 'posterior_within_weight',
+                                       'posterior_between_weight', 'prior_within_constant',
+                                       'posterior_within_constant', 'between_constant')]
 
 
 class CapsArgs(Structure):
@@ -94,6 +103,9 @@ SYMBOLS = {
     'scae_sab_bwd': (c_int, [c_void_p, c_void_p, POINTER(SabParams), c_void_p, c_int, c_int, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
     'scae_pose_transform': (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p]),
+    'scae_loss_head_workspace_bytes': (c_size_t, [POINTER(LossHeadArgs)]),
+    'scae_loss_head_fwd': (c_int, [POINTER(LossHeadArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'scae_loss_head_bwd': (c_int, [POINTER(LossHeadArgs)] + [c_void_p] * 6 + [c_size_t, c_void_p]),
     'scae_rmsprop_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
                                   c_void_p]),
     'scae_attnpool_fwd': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),

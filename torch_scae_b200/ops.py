@@ -243,6 +243,101 @@ def pose_transform(pose_tensor, similarity):
     return _PoseTransform.apply(pose_tensor, bool(similarity))
 
 
+class _LossHead(torch.autograd.Function):
+    """Sparsity losses + classifier cross-entropies of SCAE.loss on the outputs of hot path 2 (csrc/loss_head.cu)."""
+
+    @staticmethod
+    def forward(ctx, caps_presence, posterior, label, weight, bias, cfg):
+        lib = _lib.load()
+        caps_presence, posterior = caps_presence.contiguous(), posterior.contiguous()
+        label = label.contiguous() if label is not None else None
+        weight = weight.contiguous() if label is not None else None
+        bias = bias.contiguous() if label is not None else None
+        B, O, V = posterior.shape
+        K = weight.shape[0] if weight is not None else 0
+        dev = posterior.device
+        args = _lib.LossHeadArgs(ptr(caps_presence), ptr(posterior), ptr(label), ptr(weight), ptr(bias), B, O, V, K,
+                                 *cfg)
+        terms = torch.empty(8, device=dev, dtype=torch.float32)
+        stats = torch.empty(128, device=dev, dtype=torch.float32)
+        probs = torch.empty(2, B, K, device=dev, dtype=torch.float32) if label is not None else None
+        ws_bytes = lib.scae_loss_head_workspace_bytes(ctypes.byref(args))
+        ws = _workspace(ws_bytes, dev)
+        check(_timed('scae_loss_head_fwd', lib.scae_loss_head_fwd, ctypes.byref(args), ptr(terms), ptr(probs),
+                     ptr(stats), ptr(ws), ws_bytes, _stream()), 'scae_loss_head_fwd')
+        saved = [caps_presence, posterior, stats] + ([label, weight, bias] if label is not None else [])
+        ctx.save_for_backward(*saved)
+        ctx.cfg = cfg
+        total = terms[6].clone()
+        if probs is None:
+            probs = terms.new_empty(0)
+        ctx.mark_non_differentiable(terms, probs)
+        return total, terms, probs
+
+    @staticmethod
+    def backward(ctx, g_total, _g_terms, _g_probs):
+        lib = _lib.load()
+        caps_presence, posterior, stats, *cls = ctx.saved_tensors
+        label, weight, bias = cls if cls else (None, None, None)
+        B, O, V = posterior.shape
+        K = weight.shape[0] if weight is not None else 0
+        dev = posterior.device
+        cfg = ctx.cfg
+        args = _lib.LossHeadArgs(ptr(caps_presence), ptr(posterior), ptr(label), ptr(weight), ptr(bias), B, O, V, K,
+                                 *cfg)
+        sparsity = bool(cfg[0])
+        g_cp = torch.empty_like(caps_presence) if sparsity and ctx.needs_input_grad[0] else None
+        g_post = torch.empty_like(posterior) if sparsity and ctx.needs_input_grad[1] else None
+        g_cls = torch.empty(K * O + K, device=dev, dtype=torch.float32) if label is not None else None
+        ws_bytes = lib.scae_loss_head_workspace_bytes(ctypes.byref(args))
+        ws = _workspace(ws_bytes, dev)
+        g_total = _f32c(g_total).reshape(1)
+        check(_timed('scae_loss_head_bwd', lib.scae_loss_head_bwd, ctypes.byref(args), ptr(stats), ptr(g_total),
+                     ptr(g_cp), ptr(g_post), ptr(g_cls), ptr(ws), ws_bytes, _stream()), 'scae_loss_head_bwd')
+        g_w = g_cls[:K * O].view(K, O) if g_cls is not None else None
+        g_b = g_cls[K * O:] if g_cls is not None else None
+        return g_cp, g_post, None, g_w, g_b, None
+
+
+LOSS_HEAD_TERMS = ('prior_within_sparsity_loss', 'prior_between_sparsity_loss', 'posterior_within_sparsity_loss',
+                   'posterior_between_sparsity_loss', 'prior_cls_xe', 'posterior_cls_xe')
+
+
+def loss_head(caps_presence, posterior, label, classifier, n_classes, prior_type, posterior_type, weights,
+              prior_within_constant=None, sparsity=True):
+    """The (B,O)-sized tail of SCAE.loss (stacked_capsule_auto_encoder.py:243-285) in one kernel pair per direction:
+    the prior sparsity loss on ``caps_presence`` (B,O), the posterior one on ``posterior.sum(-1) / V`` and, with
+    ``label``, the cross-entropies of both classifier heads (``classifier`` = nn.Linear shared by both, sic :211; its
+    inputs are detached as in the reference).  ``weights`` = (prior within, prior between, posterior within,
+    posterior between).  Returns (total, terms (8,), class probabilities (2,B,K) | None) with total = the weighted sum
+    SCAE.loss adds, or None when the kernels do not cover the request (the caller then runs the PyTorch ops)."""
+    if not (caps_presence.is_cuda and caps_presence.dtype == torch.float32 and posterior.dtype == torch.float32
+            and posterior.dim() == 3 and tuple(caps_presence.shape) == tuple(posterior.shape[:2])
+            and 0 < posterior.shape[1] <= 64 and posterior.shape[0] > 0 and posterior.shape[2] > 0):
+        return None
+    if not (sparsity or label is not None):
+        return None
+    B, O, V = posterior.shape
+    if sparsity:
+        if prior_type not in _lib.LOSS_TYPES or posterior_type not in _lib.LOSS_TYPES:
+            return None
+        if 'l2' in (prior_type, posterior_type) and not n_classes:
+            return None                       # the reference fails on the division; let the PyTorch path do that
+    weight = bias = None
+    if label is not None:
+        weight, bias = classifier.weight, classifier.bias
+        if not (bias is not None and weight.dtype == torch.float32 and 0 < weight.shape[0] <= 16
+                and weight.shape[1] == O and label.dtype == torch.int64 and tuple(label.shape) == (B,)):
+            return None
+    default_c = float(O) / n_classes if n_classes else 0.0
+    cfg = (int(bool(sparsity)), _lib.LOSS_TYPES.get(prior_type, 0), _lib.LOSS_TYPES.get(posterior_type, 0),
+           float(weights[0]), float(weights[1]), float(weights[2]), float(weights[3]),
+           float(default_c if prior_within_constant is None else prior_within_constant), float(default_c),
+           float(B) / n_classes if n_classes else 0.0)
+    total, terms, probs = _LossHead.apply(caps_presence, posterior, label, weight, bias, cfg)
+    return total, terms, probs if label is not None else None
+
+
 class _SetAttentionBlock(torch.autograd.Function):
     """One SAB of the set transformer as a single kernel per direction (csrc/sab.cu).  ``params`` in the order
     wq bq wk bk wv bv wo bo wf bf ln0_w ln0_b ln1_w ln1_b."""

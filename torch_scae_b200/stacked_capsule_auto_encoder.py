@@ -137,10 +137,35 @@ class SCAE(nn.Module):
         if self.n_classes is not None:
             assert self.prior_classifier is not None
             assert self.posterior_classifier is not None
-            res.prior_cls_prob = self.prior_classifier(res.caps_presence.detach())
+            # lazy: on CUDA the loss head (csrc/loss_head.cu) evaluates both heads inside SCAE.loss and stores its
+            # probabilities here; read before that (or on the PyTorch path) they are computed by the modules
+            caps_presence, posterior = res.caps_presence, res.posterior_mixing_prob
+            res.set_lazy('prior_cls_prob', lambda: self.prior_classifier(caps_presence.detach()))
             # sic: the reference feeds the posterior mass through the *prior* head (:211)
-            res.posterior_cls_prob = self.prior_classifier(res.posterior_mixing_prob.sum(-1).detach())
+            res.set_lazy('posterior_cls_prob', lambda: self.prior_classifier(posterior.sum(-1).detach()))
         return res
+
+    def _fused_loss_head(self, res, label):
+        """Sparsity losses + classifier cross-entropies through ops.loss_head, or None (-> the PyTorch ops below)."""
+        sparsity = self.prior_within_example_sparsity_weight > 0 or self.prior_between_example_sparsity_weight > 0
+        cp, post = res.get('caps_presence'), res.get('posterior_mixing_prob')
+        if not (torch.is_tensor(cp) and cp.is_cuda and torch.is_tensor(post)) or self.sync_batch_stats:
+            return None
+        if label is not None:
+            head = self.prior_classifier
+            if not (self.n_classes is not None and isinstance(head, nn.Sequential) and len(head) == 2
+                    and isinstance(head[0], nn.Linear) and isinstance(head[1], nn.Softmax)
+                    and isinstance(res, LazyAttrDict) and 'prior_cls_prob' in res
+                    and not res.is_materialized('prior_cls_prob') and not res.is_materialized('posterior_cls_prob')):
+                return None
+        from . import ops
+        return ops.loss_head(cp, post, label, self.prior_classifier[0] if label is not None else None, self.n_classes,
+                             self.prior_sparsity_loss_type, self.posterior_sparsity_loss_type,
+                             (self.prior_within_example_sparsity_weight, self.prior_between_example_sparsity_weight,
+                              self.posterior_within_example_sparsity_weight,
+                              self.posterior_between_example_sparsity_weight),
+                             self.prior_within_example_constant, sparsity)
+
     def loss(self, res, reconstruction_target, label=None):
         log = dict()
         pdf = res.rec.pdf
@@ -162,6 +187,21 @@ class SCAE(nn.Module):
             log.update(part_caps_loss=part_caps_l1)
         loss = loss - self.caps_ll_weight * res.log_prob
         log.update(log_prob_loss=-res.log_prob)
+        head = self._fused_loss_head(res, label)
+        if head is not None:
+            # the (B,O)-sized tail -- sparsity terms (:243-271) and classifier cross-entropies (:279-285) -- as one
+            # kernel pair per direction; `total` is their weighted sum, `terms` the individual values for the log
+            from .ops import LOSS_HEAD_TERMS
+            total, terms, probs = head
+            loss = loss + total + self.cpr_dynamic_reg_weight * res.cpr_dynamic_reg_loss
+            if self.prior_within_example_sparsity_weight > 0 or self.prior_between_example_sparsity_weight > 0:
+                log.update({k: terms[i] for i, k in enumerate(LOSS_HEAD_TERMS[:4])})
+            log.update(cpr_dynamic_reg_loss=res.cpr_dynamic_reg_loss)
+            if label is not None:
+                assert self.n_classes is not None
+                log.update({k: terms[4 + i] for i, k in enumerate(LOSS_HEAD_TERMS[4:])})
+                res.prior_cls_prob, res.posterior_cls_prob = probs[0], probs[1]
+            return loss, log
         # both sparsity terms are gated by the *prior* weights in the reference (:243-244, :258-259)
         if self.prior_within_example_sparsity_weight > 0 or self.prior_between_example_sparsity_weight > 0:
             within, between = sparsity_loss(self.prior_sparsity_loss_type, res.caps_presence,
