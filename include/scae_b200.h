@@ -236,6 +236,16 @@ int scae_attnpool_fwd(const float* h, float* out, long groups, int D, int S, sca
 /* gh[groups, D + 1, S] from g[groups, D] (recomputes the softmax from h). */
 int scae_attnpool_bwd(const float* h, const float* g, float* gh, long groups, int D, int S, scae_stream_t stream);
 
+/* The same pooling on a CHANNELS-LAST map y[B, S, n * (D + 1)] (csrc/attnpool_cl.cu): what the part encoder's 1x1
+ * attention convolution (reference part_encoder.py:95) leaves when it runs as one GEMM over the B*S positions instead of
+ * B per-image products.  groups = B * n; out[groups, D].  scae_attnpool_cl_supported: 1 when the shape fits the
+ * kernels' per-warp shared-memory tile (S <= 64 and S * ((D+1)|1) + 2 S + D <= 1408 floats). */
+int scae_attnpool_cl_supported(long groups, int n, int D, int S);
+int scae_attnpool_cl_fwd(const float* y, float* out, long groups, int n, int D, int S, scae_stream_t stream);
+/* gy[B, S, n * (D + 1)] from g[groups, D] (recomputes the softmax from y). */
+int scae_attnpool_cl_bwd(const float* y, const float* g, float* gy, long groups, int n, int D, int S,
+                         scae_stream_t stream);
+
 /* One set-attention block of the object encoder (reference set_transformer.py:74-153: MAB(x, x) with single-head QKV
  * attention, residual, presence mask, LayerNorm, feed-forward + residual, LayerNorm) on x[B, N, 16], N <= 64, as one
  * kernel per direction (csrc/sab.cu).  Weights in nn.Linear layout [out, in] = [16, 16], vectors [16]. */

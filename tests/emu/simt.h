@@ -3,8 +3,8 @@
 // One std::thread per CUDA thread, one CTA at a time; __syncthreads() is a CTA-wide barrier and the *_sync warp
 // shuffles exchange values through a per-warp buffer between two warp-wide barriers, so divergence bugs (a shuffle or
 // barrier not reached by every thread) dead-lock here just as they would hang the GPU.  __shared__ variables become
-// function-local statics (shared by all threads; CTAs run one after another).  Only what csrc/loss_head.cu uses is
-// provided: no textures, atomics, TMA or asynchronous copies.
+// function-local statics (shared by all threads; CTAs run one after another).  Only what the tested kernels use is
+// provided (csrc/loss_head.cu, csrc/attnpool_cl.cu): no textures, atomics, TMA or asynchronous copies.
 #pragma once
 #include <math.h>
 #include <stddef.h>
@@ -47,6 +47,7 @@ inline T __ldg(const T* p) {
   return *p;
 }
 inline void __syncthreads() { emu_cta_barrier->arrive_and_wait(); }
+inline void __syncwarp() { emu_my_warp->bar.arrive_and_wait(); }
 inline float __shfl_xor_sync(unsigned, float v, int d) {
   emu_my_warp->slot[emu_lane] = v;
   emu_my_warp->bar.arrive_and_wait();

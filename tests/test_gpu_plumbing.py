@@ -375,3 +375,61 @@ def test_scae_loss_uses_the_loss_head_and_matches_the_pytorch_tail():
     assert set(grads_f) == set(grads_e)
     for k in grads_e:
         assert rel_err(grads_f[k], grads_e[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize('B,Cin,G_,n,D', [(37, 128, 5, 40, 23), (8, 16, 3, 24, 23), (5, 8, 7, 3, 8), (1024, 128, 5, 40, 23)])
+def test_attention_conv_pool_matches_conv_then_pooling(B, Cin, G_, n, D):
+    """ops.attention_conv_pool (GEMM over positions + csrc/attnpool_cl.cu + bias after pooling) vs the reference
+    formulation conv2d -> multiple_attention_pooling_2d (part_encoder.py:95-101, nn_ext.py:76-101) in fp64."""
+    import torch.nn.functional as F
+    from torch_scae_b200 import nn_ext, ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(B + n)
+    conv = torch.nn.Conv2d(Cin, n * (D + 1), 1)
+    x = torch.randn(B, Cin, G_, G_, generator=g)
+    up = torch.randn(B, n * D, 1, 1, generator=g)
+    x64 = x.double().requires_grad_(True)
+    w64, b64 = conv.weight.detach().double().requires_grad_(True), conv.bias.detach().double().requires_grad_(True)
+    ref = nn_ext.multiple_attention_pooling_2d(F.conv2d(x64, w64, b64), n)
+    g_ref = torch.autograd.grad((ref * up.double()).sum(), [x64, w64, b64])
+    conv = conv.cuda()
+    xd = x.cuda().requires_grad_(True)
+    got = ops.attention_conv_pool(xd, conv, n)
+    assert got is not None and got.shape == ref.shape
+    assert rel_err(got, ref) < 1e-5
+    g_got = torch.autograd.grad((got * up.cuda()).sum(), [xd, conv.weight, conv.bias])
+    for name, a, r in zip(('x', 'weight', 'bias'), g_got, g_ref):
+        assert rel_err(a, r) < 1e-4, name
+
+
+def test_part_encoder_head_paths_agree():
+    """CapsuleImageEncoder with the GEMM head (default) vs the cuDNN convolution + NCHW pooling (SCAE_B200_ATT_GEMM=0)."""
+    import os
+    from torch_scae_b200.part_encoder import CapsuleImageEncoder, CNNEncoder
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(2)
+    enc = CapsuleImageEncoder((1, 40, 40), CNNEncoder((1, 40, 40), [32] * 4, [3] * 4, [2, 2, 1, 1]), n_caps=40,
+                              n_poses=6, n_special_features=16).cuda().train()
+    image = torch.rand(9, 1, 40, 40, device='cuda')
+    noise = (torch.rand(9, 40, device='cuda') - .5) * 4
+
+    def run():
+        enc.zero_grad(set_to_none=True)
+        r = enc(image, presence_noise=noise)
+        (r.pose.sum() * 0.3 + (r.presence * r.presence).sum() + (r.feature ** 2).sum()).backward()
+        return r, {k: p.grad.clone() for k, p in enc.named_parameters()}
+    from torch_scae_b200 import ops
+    with ops.KernelTimer() as timer:
+        r1, g1 = run()
+    torch.cuda.synchronize()
+    assert 'scae_attnpool_cl_fwd' in timer.summary() and 'scae_attnpool_cl_bwd' in timer.summary()
+    os.environ['SCAE_B200_ATT_GEMM'] = '0'
+    try:
+        r0, g0 = run()
+    finally:
+        del os.environ['SCAE_B200_ATT_GEMM']
+    for k in ('pose', 'presence', 'feature'):
+        assert rel_err(r1[k], r0[k]) < 1e-5, k
+    for k in g0:
+        assert rel_err(g1[k], g0[k]) < 1e-4, k

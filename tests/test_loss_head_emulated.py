@@ -4,7 +4,6 @@ CUDA thread, real barriers behind __syncthreads and the warp shuffles), against 
 -- indexing, lane masks, the partial-sum layout, the launch sequence -- is verified where no GPU is present; the GPU
 parity tests (tests/test_gpu_plumbing.py) then only have to confirm it."""
 import os
-import re
 import struct
 import subprocess
 
@@ -22,20 +21,9 @@ TYPES = {'l2': 0, 'entropy': 1, 'kl': 2}
 
 @pytest.fixture(scope='module')
 def emu_binary(tmp_path_factory):
-    build = tmp_path_factory.mktemp('loss_head_emu')
-    src = open(os.path.join(CSRC, 'loss_head.cu')).read()
-    body = src.split('namespace scae {', 1)[1].split('// ---- host side', 1)[0]
-    open(build / 'loss_head_device.inc', 'w').write(body)
-    common = open(os.path.join(CSRC, 'common.cuh')).read()
-    consts = re.findall(r'^constexpr float kLogSafe\w+ = [^;]+;', common, re.M)
-    warp_sum = re.search(r'__device__ __forceinline__ float warp_sum\(float v\) \{.*?\n\}', common, re.S).group(0)
-    assert len(consts) == 2
-    open(build / 'common_device.inc', 'w').write('\n'.join(consts) + '\n' + warp_sum + '\n')
-    exe = build / 'loss_head_emu'
-    subprocess.run(['g++', '-std=c++20', '-O1', '-pthread', '-I', str(build), '-I', EMU,
-                    '-I', os.path.join(ROOT, 'include'), os.path.join(EMU, 'loss_head_harness.cpp'), '-o', str(exe)],
-                   check=True)
-    return str(exe)
+    from test_attnpool_cl_emulated import build_emulated
+    return build_emulated(tmp_path_factory.mktemp('loss_head_emu'), 'loss_head.cu', 'loss_head_harness.cpp',
+                          'loss_head_emu')
 
 
 def run_emulated(exe, tmp_path, cp, post, label, weight, bias, cfg, grid, g_total):

@@ -144,3 +144,27 @@ def test_loss_head_manual_backward(prior_type, posterior_type, with_label):
     if with_label:
         assert rel_err(got['prior_cls_prob'], p1) < 1e-12 and rel_err(got['posterior_cls_prob'], p2) < 1e-12
         assert rel_err(got['g_weight'], grads[2]) < 1e-10 and rel_err(got['g_bias'], grads[3]) < 1e-10
+
+
+def test_attention_head_as_gemm_is_the_same_function():
+    """The restructured capsule head of the part encoder (1x1 convolution as a GEMM over positions, pooling on the
+    channels-last result, bias after the pooling: ops.attention_conv_pool_reference) equals the reference formulation
+    conv2d -> multiple_attention_pooling_2d (part_encoder.py:95-101, nn_ext.py:76-101), values and gradients, in fp64.
+    The bias gradient of the groups' logit channels is analytically zero (softmax is shift invariant); autograd through
+    the reference formulation leaves rounding noise there."""
+    import torch.nn.functional as F
+    from torch_scae_b200 import nn_ext, ops
+    torch.manual_seed(1)
+    B, Cin, H, W, n, G = 3, 6, 4, 5, 7, 5
+    x = torch.randn(B, Cin, H, W, dtype=F64, requires_grad=True)
+    w = torch.randn(n * G, Cin, 1, 1, dtype=F64, requires_grad=True)
+    b = torch.randn(n * G, dtype=F64, requires_grad=True)
+    up = torch.randn(B, n * (G - 1), 1, 1, dtype=F64)
+    ref = nn_ext.multiple_attention_pooling_2d(F.conv2d(x, w, b), n)
+    got = ops.attention_conv_pool_reference(x, w, b, n)
+    assert rel_err(got, ref) < 1e-12
+    g_ref = torch.autograd.grad((ref * up).sum(), [x, w, b])
+    g_got = torch.autograd.grad((got * up).sum(), [x, w, b])
+    for a, r in zip(g_got, g_ref):
+        assert rel_err(a, r) < 1e-12
+    assert float(g_got[2].view(n, G)[:, -1].abs().max()) == 0.0

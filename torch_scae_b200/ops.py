@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns device memory and the stream; the arithmetic o
 csrc/tmpl_ll.cu and csrc/caps_ll.cu.  All tensors crossing the boundary are made contiguous fp32 first.
 """
 import ctypes
+import os
 
 import torch
 
@@ -142,10 +143,14 @@ class _ConvBiasAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, relu):
         lib = _lib.load()
-        y = torch.nn.functional.conv2d(x, weight, None, stride).contiguous()
-        N, C, H, W = y.shape
-        check(_timed('scae_bias_act_fwd', lib.scae_bias_act_fwd, ptr(y), ptr(bias), N, C, H * W, int(relu), _stream()),
-              'scae_bias_act_fwd')
+        if relu and os.environ.get('SCAE_B200_CUDNN_FUSED_RELU', '0') == '1':
+            # experiment (off by default): cuDNN's own fused convolution + bias + ReLU forward, no separate pass
+            y = torch.cudnn_convolution_relu(x, weight, bias, stride, (0, 0), (1, 1), 1).contiguous()
+        else:
+            y = torch.nn.functional.conv2d(x, weight, None, stride).contiguous()
+            N, C, H, W = y.shape
+            check(_timed('scae_bias_act_fwd', lib.scae_bias_act_fwd, ptr(y), ptr(bias), N, C, H * W, int(relu),
+                         _stream()), 'scae_bias_act_fwd')
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.stride, ctx.relu = stride, relu
         return y
@@ -210,6 +215,94 @@ def attention_pool(feature_map, n_attention_map):
     if not (feature_map.is_cuda and feature_map.dtype == torch.float32 and S <= 64 and 0 < D <= 1024):
         return None
     return _AttentionPool.apply(feature_map, B * n_attention_map, D, S).view(B, C - n_attention_map, 1, 1)
+
+
+class _AttentionPoolCL(torch.autograd.Function):
+    """Attention pooling of a channels-last map y (B, S, n*(D+1)) -> (B*n, D) (csrc/attnpool_cl.cu)."""
+
+    @staticmethod
+    def forward(ctx, y, n, D):
+        lib = _lib.load()
+        y = y.contiguous()
+        B, S, _ = y.shape
+        out = torch.empty(B * n, D, device=y.device, dtype=torch.float32)
+        check(_timed('scae_attnpool_cl_fwd', lib.scae_attnpool_cl_fwd, ptr(y), ptr(out), B * n, n, D, S, _stream()),
+              'scae_attnpool_cl_fwd')
+        ctx.save_for_backward(y)
+        ctx.dims = (n, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (y,) = ctx.saved_tensors
+        n, D = ctx.dims
+        B, S, _ = y.shape
+        gy = torch.empty_like(y)
+        check(_timed('scae_attnpool_cl_bwd', lib.scae_attnpool_cl_bwd, ptr(y), ptr(g.contiguous()), ptr(gy), B * n, n,
+                     D, S, _stream()), 'scae_attnpool_cl_bwd')
+        return gy, None, None
+
+
+class _PositionsGemm(torch.autograd.Function):
+    """y = x @ w^T for x (rows, in) tall and w (out, in): plain cuBLAS SGEMMs, the weight gradient split over row chunks
+    (its (out x rows) @ (rows x in) product has few output tiles and a very long reduction)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return x @ w.t()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = g @ w
+        if ctx.needs_input_grad[1]:
+            rows = x.shape[0]
+            s = max((d for d in range(1, 33) if rows % d == 0 and rows // d >= 256), default=1)
+            if s > 1:
+                gw = torch.bmm(g.view(s, rows // s, -1).transpose(1, 2), x.view(s, rows // s, -1)).sum(0)
+            else:
+                gw = g.t() @ x
+        return gx, gw
+
+
+def attention_conv_pool_reference(feature_map, weight, bias, n_caps):
+    """The algebra of ``attention_conv_pool`` in stock PyTorch ops (any device / dtype): 1x1 convolution as a GEMM over
+    the positions, attention pooling on the channels-last result, bias added AFTER the pooling -- exact, because the
+    softmax weights of a group sum to one (pooled channels) and a constant added to every position's logit does not
+    change the softmax (the group's logit channel).  Used by the tests to pin the restructuring against the reference
+    formulation conv -> multiple_attention_pooling_2d (part_encoder.py:95-101, nn_ext.py:76-101)."""
+    B, Cin, H, W = feature_map.shape
+    Ctot = weight.shape[0]
+    G = Ctot // n_caps
+    y = feature_map.permute(0, 2, 3, 1).reshape(B * H * W, Cin) @ weight.reshape(Ctot, Cin).t()
+    grouped = y.view(B, H * W, n_caps, G)
+    pooled = (grouped[..., :-1] * torch.softmax(grouped[..., -1:], 1)).sum(1)            # (B, n, D)
+    return (pooled + bias.view(n_caps, G)[:, :-1]).reshape(B, n_caps * (G - 1), 1, 1)
+
+
+def attention_conv_pool(feature_map, conv, n_caps):
+    """``multiple_attention_pooling_2d(conv(feature_map), n_caps)`` for the part encoder's 1x1 attention convolution
+    (part_encoder.py:95-101) as GEMM + channels-last pooling kernel + bias on the pooled result; (B, n*D, 1, 1), or None
+    when the layer / shape is not covered (the caller then runs convolution and pooling separately)."""
+    if not (feature_map.is_cuda and feature_map.dtype == torch.float32 and feature_map.dim() == 4
+            and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is not None
+            and conv.weight.dtype == torch.float32 and conv.out_channels % n_caps == 0
+            and conv.out_channels // n_caps >= 2):
+        return None
+    B, Cin, H, W = feature_map.shape
+    S, Ctot = H * W, conv.out_channels
+    G = Ctot // n_caps
+    if B == 0 or not _lib.load().scae_attnpool_cl_supported(B * n_caps, n_caps, G - 1, S):
+        return None
+    x2d = feature_map.permute(0, 2, 3, 1).reshape(B * S, Cin)
+    y = _PositionsGemm.apply(x2d, conv.weight.view(Ctot, Cin))
+    pooled = _AttentionPoolCL.apply(y.view(B, S, Ctot), n_caps, G - 1).view(B, n_caps, G - 1)
+    return (pooled + conv.bias.view(n_caps, G)[:, :-1]).reshape(B, n_caps * (G - 1), 1, 1)
 
 
 class _PoseTransform(torch.autograd.Function):

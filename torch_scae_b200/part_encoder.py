@@ -2,6 +2,7 @@
 
 API and state-dict layout of the reference's part_encoder.py:26-113.
 """
+import os
 from typing import Tuple
 
 import torch
@@ -48,8 +49,14 @@ class CapsuleImageEncoder(nn.Module):
         (part_encoder.py:105-107); used by parity tests to inject the reference's noise."""
         B = image.shape[0]
         from . import ops
-        h = ops.conv_bias_act(self.encoder(image) + self.img_embedding_bias.unsqueeze(0), self.att_conv, relu=False)
-        h = multiple_attention_pooling_2d(h, self.n_caps).view(B, self.n_caps, self.n_total_caps_dims)
+        feature_map = self.encoder(image) + self.img_embedding_bias.unsqueeze(0)
+        # 1x1 attention convolution + attention pooling: on CUDA one GEMM over the B*S positions and a channels-last
+        # pooling kernel (ops.attention_conv_pool); SCAE_B200_ATT_GEMM=0 keeps the cuDNN convolution (A/B timing)
+        h = ops.attention_conv_pool(feature_map, self.att_conv, self.n_caps) \
+            if os.environ.get('SCAE_B200_ATT_GEMM', '1') != '0' else None
+        if h is None:
+            h = multiple_attention_pooling_2d(ops.conv_bias_act(feature_map, self.att_conv, relu=False), self.n_caps)
+        h = h.view(B, self.n_caps, self.n_total_caps_dims)
         pose, presence_logit, feature = torch.split(h, self.caps_dim_splits, -1)
         presence_logit = presence_logit.squeeze(-1)
         if presence_noise is not None:

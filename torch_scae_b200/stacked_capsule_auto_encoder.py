@@ -6,6 +6,8 @@ section 9).  Differences are only in *when* things are computed: the reconstruct
 fused kernel launched from ``loss``), ``res.transformed_templates`` is rendered on first read, and the alternative
 reconstructions cost nothing unless somebody looks at them.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -146,7 +148,10 @@ class SCAE(nn.Module):
         return res
 
     def _fused_loss_head(self, res, label):
-        """Sparsity losses + classifier cross-entropies through ops.loss_head, or None (-> the PyTorch ops below)."""
+        """Sparsity losses + classifier cross-entropies through ops.loss_head, or None (-> the PyTorch ops below).
+        SCAE_B200_LOSS_HEAD=0 in the environment forces the PyTorch ops (A/B timing, bisecting)."""
+        if os.environ.get('SCAE_B200_LOSS_HEAD', '1') == '0':
+            return None
         sparsity = self.prior_within_example_sparsity_weight > 0 or self.prior_between_example_sparsity_weight > 0
         cp, post = res.get('caps_presence'), res.get('posterior_mixing_prob')
         if not (torch.is_tensor(cp) and cp.is_cuda and torch.is_tensor(post)) or self.sync_batch_stats:
