@@ -84,3 +84,39 @@ def test_graph_step_draws_fresh_noise_on_every_replay():
     b = float(step(image, label))
     assert a == a and b == b
     assert a != b                # lr = 0: only the presence noises differ between the two replays
+
+
+def test_staged_host_batches_give_the_same_steps_as_direct_copies():
+    """GraphedTrainStep.stage(): pinned host batches copied to device staging buffers on a side stream (the next batch's
+    transfer overlapping the current step) must feed the replays the same data, in order, as passing the batches
+    directly."""
+    from torch_scae_b200 import ddp, graph
+    strict_fp32()
+    B, n_steps = 32, 5
+    g = torch.Generator().manual_seed(4)
+    images = [torch.rand(B, 1, 40, 40, generator=g).pin_memory() for _ in range(n_steps)]
+    labels = [torch.randint(0, 10, (B,), generator=g).pin_memory() for _ in range(n_steps)]
+
+    def run(staged):
+        model = _model()
+        model.load_state_dict(init)
+        bucket = ddp.FlatGradBucket(model)
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, foreach=True)
+        step = graph.GraphedTrainStep(model, opt, bucket, images[0].to(DEV), labels[0].to(DEV))
+        losses = []
+        if staged:
+            step.stage(images[0], labels[0])
+            for i in range(n_steps):
+                loss = step()
+                if i + 1 < n_steps:
+                    step.stage(images[i + 1], labels[i + 1])
+                losses.append(float(loss))
+        else:
+            for img, lab in zip(images, labels):
+                losses.append(float(step(img, lab, non_blocking=False)))
+        return losses
+
+    init = copy.deepcopy(_model().state_dict())
+    direct, staged = run(False), run(True)
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(direct, staged)), (direct, staged)
+    assert len(set(direct)) == n_steps          # different batches give different losses: the order matters

@@ -98,8 +98,44 @@ class GraphedTrainStep:
                 self.optimizer.step()
             self.graphs.append(g_b)
 
+    # ---- input prefetch: the host->device copy of the NEXT batch overlaps the current step -----------------------------
+    def stage(self, image, label=None):
+        """Starts copying a (pinned host) batch into one of two device staging buffers on a side stream and returns at
+        once; the next ``__call__()`` without arguments consumes it (a 6 MB device-to-device copy in front of the graph).
+        Staging batch i+1 right after launching step i hides the PCIe transfer behind the step."""
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_img = [torch.empty_like(self.static_image) for _ in range(2)]
+            self._stage_lab = [torch.empty_like(self.static_label) if self.static_label is not None else None
+                               for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._consumed = [torch.cuda.Event() for _ in range(2)]
+            self._staged, self._stage_idx = [], 0
+        if len(self._staged) == 2:
+            raise RuntimeError('both staging buffers hold batches that no step has consumed yet')
+        k = self._stage_idx
+        self._copy_stream.wait_event(self._consumed[k])     # no-op until a step has read this buffer
+        with torch.cuda.stream(self._copy_stream):
+            self._stage_img[k].copy_(image, non_blocking=True)
+            if label is not None and self._stage_lab[k] is not None:
+                self._stage_lab[k].copy_(label, non_blocking=True)
+            self._ready[k].record(self._copy_stream)
+        self._staged.append(k)
+        self._stage_idx = k ^ 1
+
+    def _consume_staged(self):
+        k = self._staged.pop(0)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[k])
+        self.static_image.copy_(self._stage_img[k], non_blocking=True)
+        if self._stage_lab[k] is not None:
+            self.static_label.copy_(self._stage_lab[k], non_blocking=True)
+        self._consumed[k].record(cur)
+
     def __call__(self, image=None, label=None, non_blocking=True):
         """Copies the batch into the static buffers (host or device source) and replays the step."""
+        if image is None and getattr(self, '_staged', None):
+            self._consume_staged()
         if image is not None and image is not self.static_image:
             self.static_image.copy_(image, non_blocking=non_blocking)
         if label is not None and label is not self.static_label:
