@@ -92,35 +92,65 @@ def ncu_traffic():
 # clocks sampling
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled while the timed regions run: through NVML in-process (a few
+    samples per 100 ms) when pynvml can find the device, else through `nvidia-smi` (about one sample per second)."""
     FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
               'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag = index, [], False      # samples: (sm_mhz, max_mhz, [reason flags])
+        self.source, self.nvml, self.handle = 'nvidia-smi', None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = 'GPU-' + str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.source = pynvml, 'nvml'
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        masks = (n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                 n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap)
+        return int(sm), int(mx), [bool(r & m) for m in masks]
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.FIELDS}',
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(',')]
+        if len(parts) < 6 or not parts[0].isdigit():
+            return None
+        return int(parts[0]), int(parts[1]) if parts[1].isdigit() else None, \
+            [p.lower().startswith('active') for p in parts[2:6]]
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.FIELDS}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(',')]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                s = self._sample_nvml() if self.nvml is not None else self._sample_smi()
+                if s is not None:
+                    self.samples.append(s)
             except Exception:
-                pass
-            time.sleep(0.2)
+                if self.nvml is not None:                  # NVML query failed: fall back to nvidia-smi
+                    self.nvml, self.source = None, 'nvidia-smi'
+            time.sleep(0.05 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag = True
         if not self.samples:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None,
-                    sm_max_mhz=int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                    reasons=reasons, samples=len(self.samples))
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, source=self.source)
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2][i] for s in self.samples)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.samples[0][1], reasons=reasons, samples=len(self.samples),
+                    source=self.source)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -261,7 +261,8 @@ class _PositionsGemm(torch.autograd.Function):
             gx = g @ w
         if ctx.needs_input_grad[1]:
             rows = x.shape[0]
-            s = max((d for d in range(1, 33) if rows % d == 0 and rows // d >= 256), default=1)
+            cap = int(os.environ.get('SCAE_B200_ATT_SPLITK', '32'))          # 1: leave the split to cuBLAS
+            s = max((d for d in range(1, cap + 1) if rows % d == 0 and rows // d >= 256), default=1)
             if s > 1:
                 gw = torch.bmm(g.view(s, rows // s, -1).transpose(1, 2), x.view(s, rows // s, -1)).sum(0)
             else:
