@@ -246,6 +246,16 @@ int scae_attnpool_cl_fwd(const float* y, float* out, long groups, int n, int D, 
 int scae_attnpool_cl_bwd(const float* y, const float* g, float* gy, long groups, int n, int D, int S,
                          scae_stream_t stream);
 
+/* im2col / col2im for the part encoder's unpadded 3x3 convolutions (reference nn_ext.py:34-59; csrc/conv_cols.cu), so
+ * that their passes run as cuBLAS SGEMMs on rows = (image, output position), columns = (channel, ky, kx) -- the order
+ * of weight.view(C_out, C_in * 9).  stride 1 or 2; L = Ho * Wo, Ho = (H - 3) / stride + 1.  Deterministic.
+ * scae_conv_cols_supported: 1 when a channel group's tile fits shared memory (e.g. 19x19 / 9x9 / 7x7 maps; not 31x31). */
+int scae_conv_cols_supported(int B, int C, int H, int W, int stride);
+/* x[B, C, H, W] -> cols[B * L, C * 9] */
+int scae_im2col3x3(const float* x, float* cols, int B, int C, int H, int W, int stride, scae_stream_t stream);
+/* dcols[B * L, C * 9] -> dx[B, C, H, W]: the adjoint of im2col (the data gradient's scatter, written as a gather) */
+int scae_col2im3x3(const float* dcols, float* dx, int B, int C, int H, int W, int stride, scae_stream_t stream);
+
 /* One set-attention block of the object encoder (reference set_transformer.py:74-153: MAB(x, x) with single-head QKV
  * attention, residual, presence mask, LayerNorm, feed-forward + residual, LayerNorm) on x[B, N, 16], N <= 64, as one
  * kernel per direction (csrc/sab.cu).  Weights in nn.Linear layout [out, in] = [16, 16], vectors [16]. */

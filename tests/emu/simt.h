@@ -4,7 +4,7 @@
 // shuffles exchange values through a per-warp buffer between two warp-wide barriers, so divergence bugs (a shuffle or
 // barrier not reached by every thread) dead-lock here just as they would hang the GPU.  __shared__ variables become
 // function-local statics (shared by all threads; CTAs run one after another).  Only what the tested kernels use is
-// provided (csrc/loss_head.cu, csrc/attnpool_cl.cu): no textures, atomics, TMA or asynchronous copies.
+// provided (csrc/loss_head.cu, csrc/attnpool_cl.cu, csrc/conv_cols.cu): no textures, atomics, TMA or asynchronous copies.
 #pragma once
 #include <math.h>
 #include <stddef.h>
@@ -41,6 +41,13 @@ static std::barrier<>* emu_cta_barrier = nullptr;
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+// dynamic shared memory (common.cuh's SCAE_DYNAMIC_SMEM): one host buffer, CTAs run one after another
+static float emu_dynamic_smem[64 * 1024];
+#define SCAE_DYNAMIC_SMEM(name) float* name = emu_dynamic_smem
+template <class T>
+inline T min(T a, T b) {
+  return b < a ? b : a;
+}
 
 template <class T>
 inline T __ldg(const T* p) {

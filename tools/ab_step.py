@@ -6,7 +6,8 @@ autotune): for every variant the step is re-captured as a CUDA graph and replaye
 Switches (read at call time by the modules): SCAE_B200_LOSS_HEAD (csrc/loss_head.cu vs the PyTorch loss tail),
 SCAE_B200_ATT_GEMM (1x1 attention convolution as a GEMM + channels-last pooling vs cuDNN + NCHW pooling),
 SCAE_B200_CUDNN_FUSED_RELU (cuDNN's fused conv+bias+ReLU forward vs conv + scae_bias_act_fwd), SCAE_B200_ATT_SPLITK
-(row chunks of the attention GEMM's weight gradient).
+(row chunks of the attention GEMM's weight gradient), SCAE_B200_CONV_GEMM (0 | dgrad | full | auto: GEMM-form passes of
+the 3x3 convolutions, csrc/conv_cols.cu).
 """
 import argparse
 import json
@@ -25,8 +26,10 @@ VARIANTS = [
     ('att_gemm_off', {'SCAE_B200_ATT_GEMM': '0'}),
     ('both_off', {'SCAE_B200_LOSS_HEAD': '0', 'SCAE_B200_ATT_GEMM': '0'}),
     ('cudnn_fused_relu', {'SCAE_B200_CUDNN_FUSED_RELU': '1'}),
-    ('att_splitk_1', {'SCAE_B200_ATT_SPLITK': '1'}),
-    ('att_splitk_8', {'SCAE_B200_ATT_SPLITK': '8'}),
+    ('conv_gemm_off', {'SCAE_B200_CONV_GEMM': '0'}),
+    ('conv_gemm_dgrad_only', {'SCAE_B200_CONV_GEMM': 'dgrad'}),
+    ('conv_gemm_full_everywhere', {'SCAE_B200_CONV_GEMM': 'full'}),
+    ('conv_gemm_off_fused_relu', {'SCAE_B200_CONV_GEMM': '0', 'SCAE_B200_CUDNN_FUSED_RELU': '1'}),
     ('default_again', {}),
 ]
 
@@ -50,7 +53,8 @@ def main():
     label = torch.randint(0, 10, (B,), device=dev)
     lib = _lib.load()
     for name, env in VARIANTS:
-        for k in ('SCAE_B200_LOSS_HEAD', 'SCAE_B200_ATT_GEMM', 'SCAE_B200_CUDNN_FUSED_RELU', 'SCAE_B200_ATT_SPLITK'):
+        for k in ('SCAE_B200_LOSS_HEAD', 'SCAE_B200_ATT_GEMM', 'SCAE_B200_CUDNN_FUSED_RELU', 'SCAE_B200_ATT_SPLITK',
+                  'SCAE_B200_CONV_GEMM'):
             os.environ.pop(k, None)
         os.environ.update(env)
         out = dict(variant=name, env=env, batch=B)

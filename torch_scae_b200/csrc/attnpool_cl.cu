@@ -23,13 +23,26 @@ __host__ __device__ inline int pool_row_stride(int G) { return G | 1; }
 // floats a warp needs: tile [S][stride] | softmax weights [S] | logit gradients [S] | upstream gradient [D]
 __host__ __device__ inline int pool_floats(int D, int S) { return S * pool_row_stride(D + 1) + 2 * S + D; }
 
-// stage the group's tile: tile[s * stride + d] = y[(b * S + s) * Ctot + cap * G + d]
+// stage the group's tile: tile[s * stride + d] = y[(b * S + s) * Ctot + cap * G + d]; eight loads in flight per lane
 __device__ __forceinline__ void pool_stage(const float* __restrict__ base, float* tile, int S, int G, int Ctot,
                                            int stride, int lane) {
+  constexpr int kBatch = 8;
   const float inv_G = 1.0f / (float)G;
-  for (int e = lane; e < S * G; e += 32) {
-    const int s = (int)(((float)e + 0.5f) * inv_G), d = e - s * G;
-    tile[s * stride + d] = __ldg(base + (long)s * Ctot + d);
+  const int n = S * G;
+  for (int e0 = lane; e0 < n; e0 += 32 * kBatch) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int e = e0 + 32 * u;
+      const int s = (int)(((float)e + 0.5f) * inv_G), d = e - s * G;
+      v[u] = e < n ? __ldg(base + (long)s * Ctot + d) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int e = e0 + 32 * u;
+      const int s = (int)(((float)e + 0.5f) * inv_G), d = e - s * G;
+      if (e < n) tile[s * stride + d] = v[u];
+    }
   }
 }
 

@@ -37,6 +37,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int launch_reduce_rows(const float* partials, float* out, int n_parts, int n, cudaStream_t stream);
 
 // ---- device side -----------------------------------------------------------------------------------------------
+// dynamic shared memory of a kernel as a float array (a macro so that tests/emu/simt.h can substitute a host buffer)
+#define SCAE_DYNAMIC_SMEM(name) extern __shared__ __align__(16) float name[]
+
 constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))  (torch/distributions/normal.py log_prob)
 constexpr float kTwoPi = 6.283185307179586f;             // 2. * math.pi rounded to fp32 (cv_ops.py:45)
 constexpr float kLogSafeEps = 1e-16f;                    // math_ops.py:18

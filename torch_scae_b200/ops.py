@@ -173,6 +173,114 @@ class _ConvBiasAct(torch.autograd.Function):
         return gx, gw, g_bias if ctx.needs_input_grad[2] else None, None, None
 
 
+def _split_k_wgrad(g2d, cols, cap=32, min_rows=256):
+    """g2d^T @ cols for tall operands (rows, C_out) / (rows, K): few output tiles and a very long reduction, so the
+    rows are cut into up to ``cap`` chunks reduced by one batched GEMM and summed (60 vs 44 TFLOP/s on B200 for the
+    stride-2 layer, tools/conv_gemm_probe.py)."""
+    rows = g2d.shape[0]
+    s = max((d for d in range(1, cap + 1) if rows % d == 0 and rows // d >= min_rows), default=1)
+    if s > 1:
+        return torch.bmm(g2d.view(s, rows // s, -1).transpose(1, 2), cols.view(s, rows // s, -1)).sum(0)
+    return g2d.t() @ cols
+
+
+def conv3x3_gemm_reference(x, weight, bias, stride, relu, g):
+    """The GEMM formulation of ``relu?(conv2d(x, weight, bias, stride))`` and of its three gradients for an upstream
+    gradient ``g``, in stock PyTorch ops (any device / dtype; F.unfold / F.fold stand in for the im2col / col2im
+    kernels).  Returns (y, (gx, gw, gb)).  Pins ``_Conv3x3Gemm`` against F.conv2d in the CPU tests."""
+    B, C, H, W = x.shape
+    Co = weight.shape[0]
+    Ho, Wo = (H - 3) // stride + 1, (W - 3) // stride + 1
+    cols = torch.nn.functional.unfold(x, 3, stride=stride).transpose(1, 2).reshape(B * Ho * Wo, C * 9)
+    w2d = weight.reshape(Co, C * 9)
+    y2d = cols @ w2d.t() + bias
+    if relu:
+        y2d = torch.relu(y2d)
+    y = y2d.view(B, Ho, Wo, Co).permute(0, 3, 1, 2)
+    g2d = (g * (y > 0) if relu else g).permute(0, 2, 3, 1).reshape(B * Ho * Wo, Co)
+    dcols = g2d @ w2d
+    gx = torch.nn.functional.fold(dcols.view(B, Ho * Wo, C * 9).transpose(1, 2), (H, W), 3, stride=stride)
+    return y, (gx, (g2d.t() @ cols).view_as(weight), g2d.sum(0))
+
+
+class _Conv3x3Gemm(torch.autograd.Function):
+    """``relu?(conv2d(x, weight, bias, stride))`` for an unpadded 3x3 convolution with GEMM-form passes (csrc/conv_cols.cu).
+
+    ``full``: im2col + one cuBLAS SGEMM forward (bias and ReLU in its epilogue), weight gradient as a split-K GEMM on the
+    saved columns.  Otherwise forward and weight gradient stay with cuDNN.  The data gradient is a GEMM + col2im either
+    way -- cuDNN's fp32 data-gradient engine runs these layers at 24-25 TFLOP/s, the GEMM at 43-49."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, relu, full):
+        lib = _lib.load()
+        B, C, H, W = x.shape
+        Co = weight.shape[0]
+        Ho, Wo = (H - 3) // stride + 1, (W - 3) // stride + 1
+        cols = None
+        if full:
+            cols = torch.empty(B * Ho * Wo, C * 9, device=x.device, dtype=torch.float32)
+            check(_timed('scae_im2col3x3', lib.scae_im2col3x3, ptr(x), ptr(cols), B, C, H, W, stride, _stream()),
+                  'scae_im2col3x3')
+            w2d_t = weight.view(Co, C * 9).t()
+            y2d = torch._addmm_activation(bias, cols, w2d_t) if relu else torch.addmm(bias, cols, w2d_t)
+            y = y2d.view(B, Ho, Wo, Co).permute(0, 3, 1, 2).contiguous()
+        elif relu and os.environ.get('SCAE_B200_CUDNN_FUSED_RELU', '0') == '1':
+            y = torch.cudnn_convolution_relu(x, weight, bias, (stride, stride), (0, 0), (1, 1), 1).contiguous()
+        else:
+            y = torch.nn.functional.conv2d(x, weight, None, stride).contiguous()
+            check(_timed('scae_bias_act_fwd', lib.scae_bias_act_fwd, ptr(y), ptr(bias), B, Co, Ho * Wo, int(relu),
+                         _stream()), 'scae_bias_act_fwd')
+        ctx.save_for_backward(cols if full else x, weight, y if relu else None)
+        ctx.cfg = (stride, relu, full, (B, C, H, W))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        saved, weight, y = ctx.saved_tensors
+        stride, relu, full, (B, C, H, W) = ctx.cfg
+        Co = weight.shape[0]
+        g = g.contiguous()
+        _, _, Ho, Wo = g.shape
+        g_bias = torch.empty(Co, device=g.device, dtype=torch.float32)
+        gx_pre = torch.empty_like(g) if relu else g
+        ws_bytes = lib.scae_bias_act_bwd_workspace_bytes(B, Co, Ho * Wo)
+        ws = _workspace(ws_bytes, g.device)
+        check(_timed('scae_bias_act_bwd', lib.scae_bias_act_bwd, ptr(g), ptr(y), ptr(gx_pre) if relu else None,
+                     ptr(g_bias), B, Co, Ho * Wo, int(relu), ptr(ws), ws_bytes, _stream()), 'scae_bias_act_bwd')
+        g2d = gx_pre.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Co)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            dcols = g2d @ weight.view(Co, C * 9)
+            gx = torch.empty(B, C, H, W, device=g.device, dtype=torch.float32)
+            check(_timed('scae_col2im3x3', lib.scae_col2im3x3, ptr(dcols), ptr(gx), B, C, H, W, stride, _stream()),
+                  'scae_col2im3x3')
+        if ctx.needs_input_grad[1]:
+            if full:
+                gw = _split_k_wgrad(g2d, saved).view_as(weight)
+            else:
+                gw = torch.ops.aten.convolution_backward(gx_pre, saved, weight, None, (stride, stride), (0, 0), (1, 1),
+                                                         False, (0, 0), 1, [False, True, False])[1]
+        return gx, gw, g_bias if ctx.needs_input_grad[2] else None, None, None, None
+
+
+def _conv_gemm_mode(x, conv):
+    """None (cuDNN for everything), 'dgrad' or 'full' for an nn.Conv2d applied to x; SCAE_B200_CONV_GEMM=0|dgrad|full
+    overrides the rule (A/B timing).  Rule from tools/conv_gemm_probe.py on B200: the data gradient as GEMM + col2im
+    whenever the layer is wide enough for the GEMM to pay (C_in >= 32); forward and weight gradient too for strided
+    layers, where cuDNN's fp32 kernels are ~30 TFLOP/s (its stride-1 Winograd forward / weight gradient are faster
+    than any SIMT GEMM and stay)."""
+    want = os.environ.get('SCAE_B200_CONV_GEMM', 'auto')
+    if want == '0' or conv.kernel_size != (3, 3) or conv.stride[0] != conv.stride[1] or conv.stride[0] not in (1, 2):
+        return None
+    B, C, H, W = x.shape
+    if C < 32 or conv.out_channels < 32 or not _lib.load().scae_conv_cols_supported(B, C, H, W, conv.stride[0]):
+        return None
+    if want in ('dgrad', 'full'):
+        return want
+    return 'full' if conv.stride[0] == 2 else 'dgrad'
+
+
 def conv_bias_act(x, conv, relu):
     """``relu(conv(x))`` / ``conv(x)`` for an nn.Conv2d; the bias add, the ReLU and (backward) the ReLU mask + bias
     gradient run as one pass each instead of four."""
@@ -182,6 +290,9 @@ def conv_bias_act(x, conv, relu):
     if not ok:
         y = conv(x)
         return torch.relu(y) if relu else y
+    mode = _conv_gemm_mode(x, conv)
+    if mode is not None:
+        return _Conv3x3Gemm.apply(x.contiguous(), conv.weight, conv.bias, conv.stride[0], bool(relu), mode == 'full')
     return _ConvBiasAct.apply(x.contiguous(), conv.weight, conv.bias, tuple(conv.stride), bool(relu))
 
 
