@@ -19,16 +19,17 @@ def emu_binary(tmp_path_factory):
                           'conv_cols_emu')
 
 
+@pytest.mark.parametrize('group', [16, 32])
 @pytest.mark.parametrize('B,C,H,W,stride', [(2, 40, 19, 19, 2), (1, 32, 9, 9, 1), (2, 5, 7, 6, 1), (1, 33, 8, 11, 2),
                                             (1, 64, 3, 3, 1)])
-def test_emulated_im2col_col2im(emu_binary, tmp_path, B, C, H, W, stride):
+def test_emulated_im2col_col2im(emu_binary, tmp_path, B, C, H, W, stride, group):
     g = torch.Generator().manual_seed(C + H + stride)
     Ho, Wo = (H - 3) // stride + 1, (W - 3) // stride + 1
     L = Ho * Wo
     x = torch.randn(B, C, H, W, generator=g)
     dcols = torch.randn(B * L, C * 9, generator=g)
     with open(tmp_path / 'in.bin', 'wb') as f:
-        f.write(struct.pack('5i', B, C, H, W, stride))
+        f.write(struct.pack('6i', B, C, H, W, stride, group))
         f.write(x.numpy().tobytes())
         f.write(dcols.numpy().tobytes())
     subprocess.run([emu_binary, str(tmp_path / 'in.bin'), str(tmp_path / 'out.bin')], check=True, timeout=600)

@@ -147,6 +147,9 @@ static int ln_grid(long rows) {
 // ---------------------------------------------------------------------------------------------------------------------
 // per-channel bias (+ ReLU) on an NCHW tensor.  CTA (c, slab): the planes (n, c) of a slab of images
 // ---------------------------------------------------------------------------------------------------------------------
+// Loads in flight: 8 CTAs per SM x 256 threads x kBiasUnroll x (1 or 2 streams) x 4 B ~ 64-128 KB per SM; with 4 CTAs
+// and 4 elements the kernels ran at half of the HBM rate (profiles/r01m).
+constexpr int kBiasUnroll = 8;
 __global__ void __launch_bounds__(256) bias_act_fwd_kernel(float* __restrict__ y, const float* __restrict__ bias, int N,
                                                            int C, int HW, int relu, int n_per_slab) {
   const int c = blockIdx.x;
@@ -155,19 +158,20 @@ __global__ void __launch_bounds__(256) bias_act_fwd_kernel(float* __restrict__ y
   const long plane = (long)C * HW;
   const int total = (n1 - n0) * HW;
   const float inv_hw = 1.0f / (float)HW;
-  // four independent elements per thread and iteration: enough loads in flight to cover the HBM latency
-  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
-    float* p[4];
-    float v[4];
+  // kBiasUnroll independent elements per thread and iteration: enough loads in flight to cover the HBM latency
+  for (int e0 = threadIdx.x; e0 < total; e0 += kBiasUnroll * blockDim.x) {
+    float* p[kBiasUnroll];
+    float v[kBiasUnroll];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBiasUnroll; ++u) {
       const int e = e0 + u * blockDim.x;
       const int dn = (int)(((float)e + 0.5f) * inv_hw), s = e - dn * HW;
       p[u] = y + (long)(n0 + dn) * plane + (long)c * HW + s;
       v[u] = e < total ? *p[u] : 0.0f;
     }
+    asm volatile("" ::: "memory");   // all loads of the batch are issued before the first store (keeps them in flight)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBiasUnroll; ++u) {
       const float t = v[u] + b;
       if (e0 + u * (int)blockDim.x < total) *p[u] = relu ? fmaxf(t, 0.0f) : t;
     }
@@ -185,11 +189,11 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* __restri
   const int total = (n1 - n0) * HW;
   const float inv_hw = 1.0f / (float)HW;
   float acc = 0.0f;
-  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * blockDim.x) {
-    long off[4];
-    float v[4], yv[4];
+  for (int e0 = threadIdx.x; e0 < total; e0 += kBiasUnroll * blockDim.x) {
+    long off[kBiasUnroll];
+    float v[kBiasUnroll], yv[kBiasUnroll];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBiasUnroll; ++u) {
       const int e = e0 + u * blockDim.x;
       const int dn = (int)(((float)e + 0.5f) * inv_hw), s = e - dn * HW;
       off[u] = (long)(n0 + dn) * plane + (long)c * HW + s;
@@ -198,7 +202,7 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* __restri
       yv[u] = (ok && relu) ? y[off[u]] : 1.0f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kBiasUnroll; ++u) {
       const float t = yv[u] > 0.0f ? v[u] : 0.0f;
       if (relu && e0 + u * (int)blockDim.x < total) gx[off[u]] = t;
       acc += t;
@@ -215,8 +219,8 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* __restri
 }
 
 static int bias_slabs(int N, int C, int HW) {
-  // about 4 CTAs per SM over (C x slabs), at least ~2048 elements per CTA, HW * n_per_slab < 2^22 (fast division)
-  long slabs = (4L * sm_count() + C - 1) / C;
+  // about 8 CTAs per SM over (C x slabs), at least ~2048 elements per CTA, HW * n_per_slab < 2^22 (fast division)
+  long slabs = (8L * sm_count() + C - 1) / C;
   const long max_by_work = ((long)N * HW + 2047) / 2048;
   if (slabs > max_by_work) slabs = max_by_work;
   if (slabs > N) slabs = N;
