@@ -31,7 +31,15 @@ __global__ void __launch_bounds__(kColsThreads) im2col3x3_kernel(const float* __
   const int cg = min(kColsGroup, C - c0);
   const int HW = H * W, L = Ho * Wo, rowlen = cg * 9;
   const float* src = x + ((long)b * C + c0) * HW;
-  for (int i = tid; i < cg * HW; i += T) sm[i] = __ldg(src + i);
+  constexpr int kBatch = 8;
+  for (int i0 = tid; i0 < cg * HW; i0 += T * kBatch) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) v[u] = i0 + u * T < cg * HW ? __ldg(src + i0 + u * T) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      if (i0 + u * T < cg * HW) sm[i0 + u * T] = v[u];
+  }
   __syncthreads();
   float* dst = cols + (long)b * L * ((long)C * 9) + (long)c0 * 9;
   const float inv_row = 1.0f / (float)rowlen, inv_wo = 1.0f / (float)Wo;
@@ -58,9 +66,24 @@ __global__ void __launch_bounds__(kColsThreads) col2im3x3_kernel(const float* __
   const int HW = H * W, L = Ho * Wo, rowlen = cg * 9, rowpad = rowlen | 1;
   const float* src = dcols + (long)b * L * ((long)C * 9) + (long)c0 * 9;
   const float inv_row = 1.0f / (float)rowlen;
-  for (int e = tid; e < L * rowlen; e += T) {
-    const int l = cols_div(e, inv_row), j = e - l * rowlen;
-    sm[l * rowpad + j] = __ldg(src + (long)l * ((long)C * 9) + j);
+  // eight loads in flight per thread: with one, the staging loop is a chain of ~45 dependent HBM round trips per CTA
+  // (0.5 ms for the 19x19 layer at B = 1024, profiles/r01n)
+  constexpr int kBatch = 8;
+  const int n = L * rowlen;
+  for (int e0 = tid; e0 < n; e0 += T * kBatch) {
+    float v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int e = e0 + u * T;
+      const int l = cols_div(e, inv_row), j = e - l * rowlen;
+      v[u] = e < n ? __ldg(src + (long)l * ((long)C * 9) + j) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int e = e0 + u * T;
+      const int l = cols_div(e, inv_row), j = e - l * rowlen;
+      if (e < n) sm[l * rowpad + j] = v[u];
+    }
   }
   __syncthreads();
   float* dst = dx + ((long)b * C + c0) * HW;
