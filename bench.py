@@ -375,6 +375,8 @@ def run_gpu(args):
     traffic = ncu_traffic().get(dominant)
     roofline = dict(kernel=dominant, bound='hbm', achieved=kernels[dominant]['achieved_gbs'], peak=peak, unit='GB/s',
                     frac=kernels[dominant]['frac_of_hbm_peak'], traffic=traffic, peak_source=peak_src,
+                    binding_roof=kernels[dominant]['binding_roof'],
+                    frac_of_binding_roof=kernels[dominant].get('frac_of_issue_roof', kernels[dominant]['frac_of_hbm_peak']),
                     note='path-1 kernels are fp32-issue / shared-memory bound by construction (the B x K x H x W tensor '
                          'is never written); see DESIGN.md section 5 and the `kernels` object for all four entry points')
 
