@@ -44,9 +44,9 @@ def test_emulated_im2col_col2im(emu_binary, tmp_path, B, C, H, W, stride, group)
 
 @pytest.mark.parametrize('stride', [1, 2])
 def test_gemm_form_convolution_is_conv2d(stride):
-    """ops.conv3x3_gemm_reference: y = cols @ W2d^T + b, dx = col2im(g2d @ W2d), dW = g2d^T @ cols -- the formulation the
+    """formulations.conv3x3_gemm_reference -- y = cols @ W2d^T + b, dx = col2im(g2d @ W2d), dW = g2d^T @ cols, what the
     CUDA path uses -- equals F.conv2d and its autograd gradients (nn_ext.py:34-59 Conv2dStack layers)."""
-    from torch_scae_b200 import ops
+    import formulations
     torch.manual_seed(stride)
     x = torch.randn(3, 6, 9, 8, dtype=torch.float64, requires_grad=True)
     w = torch.randn(5, 6, 3, 3, dtype=torch.float64, requires_grad=True)
@@ -54,7 +54,7 @@ def test_gemm_form_convolution_is_conv2d(stride):
     ref = torch.relu(F.conv2d(x, w, b, stride))
     up = torch.randn_like(ref)
     g_ref = torch.autograd.grad((ref * up).sum(), [x, w, b])
-    y, (gx, gw, gb) = ops.conv3x3_gemm_reference(x.detach(), w.detach(), b.detach(), stride, True, up)
+    y, (gx, gw, gb) = formulations.conv3x3_gemm_reference(x.detach(), w.detach(), b.detach(), stride, True, up)
     assert rel_err(y, ref) < 1e-12
     for a, r in zip((gx, gw, gb), g_ref):
         assert rel_err(a, r) < 1e-12

@@ -148,12 +148,13 @@ def test_loss_head_manual_backward(prior_type, posterior_type, with_label):
 
 def test_attention_head_as_gemm_is_the_same_function():
     """The restructured capsule head of the part encoder (1x1 convolution as a GEMM over positions, pooling on the
-    channels-last result, bias after the pooling: ops.attention_conv_pool_reference) equals the reference formulation
+    channels-last result, bias after the pooling: tests/formulations.py) equals the reference formulation
     conv2d -> multiple_attention_pooling_2d (part_encoder.py:95-101, nn_ext.py:76-101), values and gradients, in fp64.
     The bias gradient of the groups' logit channels is analytically zero (softmax is shift invariant); autograd through
     the reference formulation leaves rounding noise there."""
     import torch.nn.functional as F
-    from torch_scae_b200 import nn_ext, ops
+    import formulations
+    from torch_scae_b200 import nn_ext
     torch.manual_seed(1)
     B, Cin, H, W, n, G = 3, 6, 4, 5, 7, 5
     x = torch.randn(B, Cin, H, W, dtype=F64, requires_grad=True)
@@ -161,7 +162,7 @@ def test_attention_head_as_gemm_is_the_same_function():
     b = torch.randn(n * G, dtype=F64, requires_grad=True)
     up = torch.randn(B, n * (G - 1), 1, 1, dtype=F64)
     ref = nn_ext.multiple_attention_pooling_2d(F.conv2d(x, w, b), n)
-    got = ops.attention_conv_pool_reference(x, w, b, n)
+    got = formulations.attention_conv_pool_reference(x, w, b, n)
     assert rel_err(got, ref) < 1e-12
     g_ref = torch.autograd.grad((ref * up).sum(), [x, w, b])
     g_got = torch.autograd.grad((got * up).sum(), [x, w, b])
