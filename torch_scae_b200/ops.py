@@ -202,7 +202,7 @@ class _Conv3x3Gemm(torch.autograd.Function):
             cols = torch.empty(B * Ho * Wo, C * 9, device=x.device, dtype=torch.float32)
             check(_timed('scae_im2col3x3', lib.scae_im2col3x3, ptr(x), ptr(cols), B, C, H, W, stride, _stream()),
                   'scae_im2col3x3')
-            w2d_t = weight.view(Co, C * 9).t()
+            w2d_t = weight.reshape(Co, C * 9).t()
             y2d = torch._addmm_activation(bias, cols, w2d_t) if relu else torch.addmm(bias, cols, w2d_t)
             y = y2d.view(B, Ho, Wo, Co).permute(0, 3, 1, 2).contiguous()
         elif relu and os.environ.get('SCAE_B200_CUDNN_FUSED_RELU', '0') == '1':
@@ -232,7 +232,7 @@ class _Conv3x3Gemm(torch.autograd.Function):
         g2d = gx_pre.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Co)
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            dcols = g2d @ weight.view(Co, C * 9)
+            dcols = g2d @ weight.reshape(Co, C * 9)
             gx = torch.empty(B, C, H, W, device=g.device, dtype=torch.float32)
             check(_timed('scae_col2im3x3', lib.scae_col2im3x3, ptr(dcols), ptr(gx), B, C, H, W, stride, _stream()),
                   'scae_col2im3x3')
@@ -378,7 +378,7 @@ def attention_conv_pool(feature_map, conv, n_caps):
     if B == 0 or not _lib.load().scae_attnpool_cl_supported(B * n_caps, n_caps, G - 1, S):
         return None
     x2d = feature_map.permute(0, 2, 3, 1).reshape(B * S, Cin)
-    y = _PositionsGemm.apply(x2d, conv.weight.view(Ctot, Cin))
+    y = _PositionsGemm.apply(x2d, conv.weight.reshape(Ctot, Cin))
     pooled = _AttentionPoolCL.apply(y.view(B, S, Ctot), n_caps, G - 1).view(B, n_caps, G - 1)
     return (pooled + conv.bias.view(n_caps, G)[:, :-1]).reshape(B, n_caps * (G - 1), 1, 1)
 
