@@ -6,6 +6,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace scae {
 
@@ -23,22 +24,6 @@ struct CapsPair {
 // the ranges that occur here, against the 1e-5 / 1e-4 parity tolerances (tests/test_gpu_capsule.py).
 constexpr float kLog2eF = 1.4426950408889634f;
 constexpr float kLn2F = 0.6931471805599453f;
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // 1 / (1 + e^-x); saturates cleanly: e^-x = inf -> 0, e^-x = 0 -> 1
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-x * kLog2eF)); }
@@ -98,45 +83,7 @@ __device__ __forceinline__ void compose_vote(const float* r, const float* A_, fl
   vt[5] = r[3] * A_[2] + r[4] * A_[5] + r[5];
 }
 
-// ---- mbarrier + bulk (TMA) copies, 1-D --------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// generic-proxy writes to shared memory -> visible to the async proxy (bulk copies reading or overwriting them)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  unsigned done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-// global -> shared, completion counted in bytes on `bar`; dst, src and bytes multiples of 16
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(bar)
-               : "memory");
-}
-// shared -> global; src, dst and bytes multiples of 16
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// all bulk stores of this thread have finished READING their shared-memory source
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
+// ---- 1-D bulk (TMA) copy runs ---------------------------------------------------------------------------------
 // A run of n floats at a 4-byte-aligned global address, staged so that float i lands at base[off + i] with
 // off = (address / 4) mod 4: shared and global addresses are then congruent modulo 16 bytes, the 16-byte-aligned
 // interior [head, head + body) moves as one bulk copy and at most 3 + 3 edge floats move through registers.
