@@ -1,0 +1,98 @@
+// Host stand-ins for the inline-PTX primitives of torch_scae_b200/csrc/ptx_sm100.cuh (TEST INFRASTRUCTURE): same names,
+// same arguments, so that the capsule kernels' device code runs unmodified on the CPU under tests/emu/simt.h.
+//
+// The asynchronous copies are emulated as DEFERRED work, which is what makes ordering bugs visible:
+//   * a bulk global->shared copy is only queued when issued; the bytes land when some thread WAITS on the mbarrier
+//     (and the phase flips once the expected byte count has landed and the arrival count is met) -- code that reads the
+//     destination before waiting sees stale shared memory;
+//   * a bulk shared->global store is only queued when issued; its source is read when the issuing thread executes
+//     cp.async.bulk.wait_group.read (or exits) -- code that overwrites the source before that stores the wrong data.
+#pragma once
+#define SCAE_PTX_SM100_CUH_   // keeps the real header out
+
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "simt.h"
+
+namespace scae {
+
+inline float ex2_approx(float x) { return exp2f(x); }
+inline float lg2_approx(float x) { return log2f(x); }
+inline float rcp_approx(float x) { return 1.0f / x; }
+
+struct emu_copy {
+  void* dst;
+  const void* src;
+  unsigned bytes;
+};
+struct emu_mbarrier {
+  int count = 0, pending = 0, phase = 0;
+  long tx = 0;
+  std::vector<emu_copy> queued;
+};
+static std::mutex emu_async_mutex;
+static std::map<unsigned, emu_mbarrier> emu_mbarriers;            // keyed by shared-memory byte offset
+static thread_local std::vector<emu_copy> emu_pending_stores;     // bulk groups are per thread
+
+inline unsigned smem_u32(const void* p) {
+  return (unsigned)((const char*)p - (const char*)emu_dynamic_smem);
+}
+inline void mbar_init(unsigned bar, unsigned count) {
+  std::lock_guard<std::mutex> lock(emu_async_mutex);
+  emu_mbarrier& b = emu_mbarriers[bar];
+  b = emu_mbarrier();
+  b.count = b.pending = (int)count;
+}
+inline void fence_mbar_init() {}
+inline void fence_proxy_async() {}
+inline void mbar_expect_tx(unsigned bar, unsigned bytes) {      // arrive + expect_tx
+  std::lock_guard<std::mutex> lock(emu_async_mutex);
+  emu_mbarrier& b = emu_mbarriers.at(bar);
+  b.tx += bytes;
+  b.pending -= 1;
+}
+inline void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
+  if ((reinterpret_cast<uintptr_t>(smem_dst) | reinterpret_cast<uintptr_t>(gsrc) | bytes) & 15u) {
+    fprintf(stderr, "emu: bulk_g2s operands must be 16-byte aligned / sized\n");
+    abort();
+  }
+  std::lock_guard<std::mutex> lock(emu_async_mutex);
+  emu_mbarriers.at(bar).queued.push_back({smem_dst, gsrc, bytes});
+}
+inline void mbar_wait(unsigned bar, unsigned parity) {
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> lock(emu_async_mutex);
+      emu_mbarrier& b = emu_mbarriers.at(bar);
+      if ((unsigned)b.phase != parity) return;                  // the phase with this parity has completed
+      for (const emu_copy& c : b.queued) {                      // the queued copies land now
+        memcpy(c.dst, c.src, c.bytes);
+        b.tx -= c.bytes;
+      }
+      b.queued.clear();
+      if (b.pending == 0 && b.tx == 0) {
+        b.phase ^= 1;
+        b.pending = b.count;
+      }
+    }
+    std::this_thread::yield();
+  }
+}
+inline void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+  if ((reinterpret_cast<uintptr_t>(gdst) | reinterpret_cast<uintptr_t>(smem_src) | bytes) & 15u) {
+    fprintf(stderr, "emu: bulk_s2g operands must be 16-byte aligned / sized\n");
+    abort();
+  }
+  emu_pending_stores.push_back({gdst, smem_src, bytes});
+}
+inline void bulk_commit() {}
+inline void bulk_wait_read_all() {
+  for (const emu_copy& c : emu_pending_stores) memcpy(c.dst, c.src, c.bytes);
+  emu_pending_stores.clear();
+}
+inline void emu_flush_bulk_stores_at_exit() { bulk_wait_read_all(); }
+
+}  // namespace scae

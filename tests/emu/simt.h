@@ -4,11 +4,12 @@
 // shuffles exchange values through a per-warp buffer between two warp-wide barriers, so divergence bugs (a shuffle or
 // barrier not reached by every thread) dead-lock here just as they would hang the GPU.  __shared__ variables become
 // function-local statics (shared by all threads; CTAs run one after another).  Only what the tested kernels use is
-// provided (csrc/loss_head.cu, csrc/attnpool_cl.cu, csrc/conv_cols.cu): no textures, atomics, TMA or asynchronous copies.
+// provided (csrc/loss_head.cu, csrc/attnpool_cl.cu, csrc/conv_cols.cu, csrc/caps_ll2.cu with tests/emu/ptx_emu.h): no textures, atomics, TMA or asynchronous copies.
 #pragma once
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <barrier>
 #include <memory>
@@ -22,9 +23,13 @@ struct float4 {
   float x, y, z, w;
 };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct float2 {
+  float x, y;
+};
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 struct emu_warp {
-  float slot[32];
+  uint32_t slot[32];
   std::barrier<> bar{32};
 };
 
@@ -42,7 +47,7 @@ static std::barrier<>* emu_cta_barrier = nullptr;
 #define __launch_bounds__(...)
 #define __shared__ static
 // dynamic shared memory (common.cuh's SCAE_DYNAMIC_SMEM): one host buffer, CTAs run one after another
-static float emu_dynamic_smem[64 * 1024];
+alignas(16) static float emu_dynamic_smem[64 * 1024];
 #define SCAE_DYNAMIC_SMEM(name) float* name = emu_dynamic_smem
 template <class T>
 inline T min(T a, T b) {
@@ -55,13 +60,51 @@ inline T __ldg(const T* p) {
 }
 inline void __syncthreads() { emu_cta_barrier->arrive_and_wait(); }
 inline void __syncwarp() { emu_my_warp->bar.arrive_and_wait(); }
-inline float __shfl_xor_sync(unsigned, float v, int d) {
-  emu_my_warp->slot[emu_lane] = v;
+// warp shuffles for 4-byte types: every lane publishes its value between two warp-wide barriers
+template <class T>
+inline T emu_shfl(T v, int src_lane) {
+  static_assert(sizeof(T) == 4, "4-byte shuffles only");
+  uint32_t bits;
+  memcpy(&bits, &v, 4);
+  emu_my_warp->slot[emu_lane] = bits;
   emu_my_warp->bar.arrive_and_wait();
-  const float r = emu_my_warp->slot[emu_lane ^ d];
+  bits = emu_my_warp->slot[src_lane & 31];
   emu_my_warp->bar.arrive_and_wait();
+  T r;
+  memcpy(&r, &bits, 4);
   return r;
 }
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int d) {
+  return emu_shfl(v, emu_lane ^ d);
+}
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src) {
+  return emu_shfl(v, src);
+}
+
+// device math intrinsics used by the csrc headers
+#define __align__(n) alignas(n)
+inline float __frcp_rn(float x) { return 1.0f / x; }
+inline float __expf(float x) { return expf(x); }
+inline float __logf(float x) { return logf(x); }
+inline void sincospif(float x, float* s, float* c) {
+  *s = (float)sin(M_PI * (double)x);
+  *c = (float)cos(M_PI * (double)x);
+}
+inline int __float_as_int(float f) {
+  int i;
+  memcpy(&i, &f, 4);
+  return i;
+}
+inline float __int_as_float(int i) {
+  float f;
+  memcpy(&f, &i, 4);
+  return f;
+}
+
+// called by every emulated thread when its kernel body returns (ptx_emu.h flushes pending bulk stores there)
+static void (*emu_thread_exit_hook)() = nullptr;
 
 // kernel<<<grid, block>>>(args...) -> emu_launch(grid, block, [&] { kernel(args...); })
 template <class F>
@@ -81,6 +124,7 @@ void emu_launch(int grid, int block, F body) {
         emu_my_warp = warps[t / 32].get();
         emu_lane = t % 32;
         body();
+        if (emu_thread_exit_hook) emu_thread_exit_hook();
       });
     }
     for (auto& th : threads) th.join();

@@ -106,7 +106,7 @@ __device__ __forceinline__ PairConst load_pair_const(const scae_caps_args& a, in
 template <bool kSim>
 __global__ void __launch_bounds__(kF2MaxThreads, 2) caps2_fwd_kernel(const scae_caps_args a, const scae_caps_outputs o,
                                                                      const Caps2FwdLayout L) {
-  extern __shared__ __align__(16) float smem[];
+  SCAE_DYNAMIC_SMEM(smem);
   const int tid = threadIdx.x, T = blockDim.x, b = blockIdx.x;
   const int O = a.O, V = a.V, A = 8 * V + 7, P = O * V, Vp = V | 1;
   const float inv_V = 1.0f / (float)V;
@@ -513,7 +513,7 @@ template <bool kSim>
 __global__ void __launch_bounds__(kB2MaxThreads, 1) caps2_bwd_kernel(const scae_caps_args a, const scae_caps_saved sv,
                                                                      const scae_caps_upstream up, const Caps2BwdOut out,
                                                                      const Caps2BwdLayout L) {
-  extern __shared__ __align__(16) float smem[];
+  SCAE_DYNAMIC_SMEM(smem);
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int O = a.O, V = a.V, A = 8 * V + 7, P = O * V, P1 = P + 1;
   const float inv_V = 1.0f / (float)V;
@@ -818,9 +818,8 @@ __global__ void __launch_bounds__(kB2MaxThreads, 1) caps2_bwd_kernel(const scae_
   if (tid == 0) bulk_wait_read_all();
 }
 
-// ================================================================================================================
-// host
-// ================================================================================================================
+// ---- host side ----------------------------------------------------------------------------------------------------
+// (tests/emu runs everything ABOVE this line on the CPU under a SIMT emulation: keep device code above, launches below)
 bool caps_force_v1() {
   const char* e = getenv("SCAE_CAPS_IMPL");
   return e != nullptr && strcmp(e, "v1") == 0;

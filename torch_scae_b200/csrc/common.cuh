@@ -38,7 +38,9 @@ int launch_reduce_rows(const float* partials, float* out, int n_parts, int n, cu
 
 // ---- device side -----------------------------------------------------------------------------------------------
 // dynamic shared memory of a kernel as a float array (a macro so that tests/emu/simt.h can substitute a host buffer)
+#ifndef SCAE_DYNAMIC_SMEM
 #define SCAE_DYNAMIC_SMEM(name) extern __shared__ __align__(16) float name[]
+#endif
 
 constexpr float kHalfLog2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))  (torch/distributions/normal.py log_prob)
 constexpr float kTwoPi = 6.283185307179586f;             // 2. * math.pi rounded to fp32 (cv_ops.py:45)

@@ -1,7 +1,8 @@
 // Every inline-PTX primitive of the capsule-likelihood kernels in one place (sm_100a): MUFU approximations, mbarrier
 // and 1-D bulk (TMA) copies.  Kept apart from the arithmetic that uses them so that tests/emu can execute the kernels'
 // device code on the CPU with host stand-ins for exactly these functions (tests/emu/ptx_emu.h) and nothing else.
-#pragma once
+#ifndef SCAE_PTX_SM100_CUH_   // (a classic guard: the emulation pre-defines it to substitute its stand-ins)
+#define SCAE_PTX_SM100_CUH_
 
 #include <stdint.h>
 
@@ -64,3 +65,4 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 }  // namespace scae
+#endif  // SCAE_PTX_SM100_CUH_
