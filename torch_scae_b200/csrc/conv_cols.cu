@@ -96,18 +96,33 @@ __global__ void __launch_bounds__(kColsThreads) col2im3x3_kernel(const float* __
     // branches -- the lanes of a warp differ in parity and border position -- each re-deriving the shared-memory window
     // address: 0.45 ms for the 19x19 layer at B = 1024, profiles/r01o.)
     float acc = 0.0f;
+    if (kStride == 2) {
+      // only taps of the pixel's own parity can hit: ky = (iy & 1) + 2 jy, oy = (iy >> 1) - jy -- four candidates, not nine
+      const int py = iy & 1, px = ix & 1, ay = iy >> 1, ax = ix >> 1;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int ty = iy - ky;
-      const int oy = kStride == 2 ? ty >> 1 : ty;
-      const bool vy = ty >= 0 && oy < Ho && (kStride == 1 || !(ty & 1));
+      for (int jy = 0; jy < 2; ++jy) {
+        const int ky = py + 2 * jy, oy = ay - jy;
+        const bool vy = ky < 3 && oy >= 0 && oy < Ho;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int tx = ix - kx;
-        const int ox = kStride == 2 ? tx >> 1 : tx;
-        const bool ok = vy && tx >= 0 && ox < Wo && (kStride == 1 || !(tx & 1));
-        const float t = tap[ok ? (oy * Wo + ox) * rowpad + ky * 3 + kx : 0];
-        acc += ok ? t : 0.0f;
+        for (int jx = 0; jx < 2; ++jx) {
+          const int kx = px + 2 * jx, ox = ax - jx;
+          const bool ok = vy && kx < 3 && ox >= 0 && ox < Wo;
+          const float t = tap[ok ? (oy * Wo + ox) * rowpad + ky * 3 + kx : 0];
+          acc += ok ? t : 0.0f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int oy = iy - ky;
+        const bool vy = oy >= 0 && oy < Ho;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ox = ix - kx;
+          const bool ok = vy && ox >= 0 && ox < Wo;
+          const float t = tap[ok ? (oy * Wo + ox) * rowpad + ky * 3 + kx : 0];
+          acc += ok ? t : 0.0f;
+        }
       }
     }
     dst[i] = acc;
