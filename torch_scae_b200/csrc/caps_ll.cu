@@ -59,16 +59,6 @@ __host__ __device__ inline size_t caps_bwd_smem_floats(int imgs, int O, int V) {
   return (size_t)imgs * O * 8 * 2 + (size_t)kCapsIlp * 7 * (kCapsThreads + 1) + 2 * caps_stage_floats(imgs, V, true);
 }
 
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 // Issues the asynchronous, fully coalesced copy of one object group into a staging buffer.  The rows of objects
 // o0 .. o0+nobj-1 of one image are contiguous in every source tensor, so each (tensor, image) is one run (4-byte
 // cp.async: all_param rows are only 4-byte aligned because A = 8V+7 is odd).  Replaces per-thread global loads whose

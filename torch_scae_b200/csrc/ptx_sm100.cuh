@@ -1,5 +1,5 @@
-// Every inline-PTX primitive of the capsule-likelihood kernels in one place (sm_100a): MUFU approximations, mbarrier
-// and 1-D bulk (TMA) copies.  Kept apart from the arithmetic that uses them so that tests/emu can execute the kernels'
+// Every inline-PTX primitive of the likelihood kernels in one place (sm_100a): MUFU approximations, mbarrier and 1-D
+// bulk (TMA) copies, cp.async, the optimisation barrier.  Kept apart from the arithmetic that uses them so that tests/emu can execute the kernels'
 // device code on the CPU with host stand-ins for exactly these functions (tests/emu/ptx_emu.h) and nothing else.
 #ifndef SCAE_PTX_SM100_CUH_   // (a classic guard: the emulation pre-defines it to substitute its stand-ins)
 #define SCAE_PTX_SM100_CUH_
@@ -63,6 +63,29 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsig
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- cp.async (Ampere-style 4-byte asynchronous copies; the general capsule path stages ragged rows with them) -------
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- optimisation barrier --------------------------------------------------------------------------------------------
+// Hides a loop-invariant value from the optimiser: ptxas otherwise re-derives it from the kernel parameters in every
+// pass of the hot loop (rematerialisation) instead of keeping it in a register.
+__device__ __forceinline__ unsigned keep(unsigned v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ float keep(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
+}
 
 }  // namespace scae
 #endif  // SCAE_PTX_SM100_CUH_

@@ -144,17 +144,6 @@ __device__ __forceinline__ void write_scalar_partials(const scae_tmpl_args& a, c
 // ================================================================================================================
 constexpr int kScanThreads = 256;
 
-// Hides a loop-invariant value from the optimiser: ptxas otherwise re-derives it from the kernel parameters in every
-// pass of the hot loop (rematerialisation) instead of keeping it in a register.
-__device__ __forceinline__ unsigned keep(unsigned v) {
-  asm volatile("" : "+r"(v));
-  return v;
-}
-__device__ __forceinline__ float keep(float v) {
-  asm volatile("" : "+f"(v));
-  return v;
-}
-
 // texel += v over the NCH live channels, as one vector read-modify-write of the padded texel
 template <int kPad, int NCH>
 __device__ __forceinline__ void texel_add(float* dst, const float* v) {

@@ -13,6 +13,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace scae {
 
@@ -100,11 +101,7 @@ constexpr unsigned kMagicBits = 0x4B000000u;
 
 // exp2 on the MUFU pipe without the denormal-range fix-up __expf/exp2f emit (results below 2^-126 flush to zero,
 // which is what a mixture weight that small should do anyway)
-__device__ __forceinline__ float ex2_ftz(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+__device__ __forceinline__ float ex2_ftz(float x) { return ex2_approx(x); }
 constexpr float kLog2e = 1.4426950408889634f;
 
 // Streaming-logsumexp state for the per-pixel mixtures: value = m + log(s), one MUFU per update.
