@@ -25,7 +25,6 @@ int main(int argc, char** argv) {
   const int B = cfg[0], O = cfg[1], V = cfg[2], A = 8 * V + 7, P = O * V;
   const unsigned flags = (unsigned)cfg[3];
   const int threads_fwd = cfg[4], threads_bwd = cfg[5], grid_bwd = cfg[6];
-  emu_thread_exit_hook = emu_flush_bulk_stores_at_exit;
 
   scae_caps_args a;
   a.all_param = in["all_param"].as<float>();

@@ -29,19 +29,13 @@ int main(int argc, char** argv) {
   const int groups = (C + kColsGroup - 1) / kColsGroup;
   const int group2 = h[5];               // channel group of the col2im instantiation under test: 16 or 32
   const int groups2 = (C + group2 - 1) / group2;
-  for (int b = 0; b < B; ++b) {          // grid (groups, B): the emulator launches 1-D grids, so one image at a time
-    emu_launch(groups, kColsThreads, [&, b] {
-      blockIdx.y = (unsigned)b;
-      im2col3x3_kernel(x.data(), cols.data(), C, H, W, Ho, Wo, stride);
-    });
-    emu_launch(groups2, kColsThreads, [&, b] {
-      blockIdx.y = (unsigned)b;
-      if (stride == 2 && group2 == 16) col2im3x3_kernel<2, 16>(dcols.data(), dx.data(), C, H, W, Ho, Wo);
-      else if (stride == 2) col2im3x3_kernel<2, kColsGroup>(dcols.data(), dx.data(), C, H, W, Ho, Wo);
-      else if (group2 == 16) col2im3x3_kernel<1, 16>(dcols.data(), dx.data(), C, H, W, Ho, Wo);
-      else col2im3x3_kernel<1, kColsGroup>(dcols.data(), dx.data(), C, H, W, Ho, Wo);
-    });
-  }
+  emu_launch(dim3(groups, B), dim3(kColsThreads), [&] { im2col3x3_kernel(x.data(), cols.data(), C, H, W, Ho, Wo, stride); });
+  emu_launch(dim3(groups2, B), dim3(kColsThreads), [&] {
+    if (stride == 2 && group2 == 16) col2im3x3_kernel<2, 16>(dcols.data(), dx.data(), C, H, W, Ho, Wo);
+    else if (stride == 2) col2im3x3_kernel<2, kColsGroup>(dcols.data(), dx.data(), C, H, W, Ho, Wo);
+    else if (group2 == 16) col2im3x3_kernel<1, 16>(dcols.data(), dx.data(), C, H, W, Ho, Wo);
+    else col2im3x3_kernel<1, kColsGroup>(dcols.data(), dx.data(), C, H, W, Ho, Wo);
+  });
   FILE* o = fopen(argv[2], "wb");
   if (!o) return 1;
   fwrite(cols.data(), 4, cols.size(), o);

@@ -33,9 +33,9 @@ struct emu_mbarrier {
   long tx = 0;
   std::vector<emu_copy> queued;
 };
-static std::mutex emu_async_mutex;
-static std::map<unsigned, emu_mbarrier> emu_mbarriers;            // keyed by shared-memory byte offset
-static thread_local std::vector<emu_copy> emu_pending_stores;     // bulk groups are per thread
+inline std::mutex emu_async_mutex;
+inline std::map<unsigned, emu_mbarrier> emu_mbarriers;            // keyed by shared-memory byte offset
+inline thread_local std::vector<emu_copy> emu_pending_stores;     // bulk groups are per thread
 
 inline unsigned smem_u32(const void* p) {
   return (unsigned)((const char*)p - (const char*)emu_dynamic_smem);
@@ -94,5 +94,37 @@ inline void bulk_wait_read_all() {
   emu_pending_stores.clear();
 }
 inline void emu_flush_bulk_stores_at_exit() { bulk_wait_read_all(); }
+
+// cp.async: 4-byte copies queued per thread in groups; a group lands when cp_async_wait<N> leaves at most N younger
+// groups pending (or when the thread exits)
+inline thread_local std::vector<std::vector<emu_copy>> emu_cp_groups;
+inline thread_local std::vector<emu_copy> emu_cp_open;
+inline void cp_async4(float* smem_dst, const float* gsrc) { emu_cp_open.push_back({smem_dst, gsrc, 4u}); }
+inline void cp_async_commit() {
+  emu_cp_groups.push_back(emu_cp_open);
+  emu_cp_open.clear();
+}
+inline void emu_cp_land(size_t keep_groups) {
+  while (emu_cp_groups.size() > keep_groups) {
+    for (const emu_copy& c : emu_cp_groups.front()) memcpy(c.dst, c.src, c.bytes);
+    emu_cp_groups.erase(emu_cp_groups.begin());
+  }
+}
+template <int N>
+inline void cp_async_wait() {
+  emu_cp_land((size_t)N);
+}
+inline void emu_async_thread_exit() {
+  bulk_wait_read_all();
+  cp_async_commit();
+  emu_cp_land(0);
+}
+
+// every emulated thread completes its outstanding asynchronous copies when its kernel body returns
+inline const bool emu_async_hook_installed = (emu_thread_exit_hook = emu_async_thread_exit, true);
+
+// optimisation barrier: nothing to hide from on the host
+inline unsigned keep(unsigned v) { return v; }
+inline float keep(float v) { return v; }
 
 }  // namespace scae

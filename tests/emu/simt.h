@@ -11,13 +11,15 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <barrier>
 #include <memory>
 #include <thread>
 #include <vector>
 
-struct emu_dim3 {
-  unsigned x = 1, y = 1, z = 1;
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct float4 {
   float x, y, z, w;
@@ -30,14 +32,17 @@ inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 struct emu_warp {
   uint32_t slot[32];
-  std::barrier<> bar{32};
+  std::barrier<> bar;
+  explicit emu_warp(int lanes) : bar(lanes) {}
 };
 
-static thread_local emu_dim3 threadIdx, blockIdx;
-static emu_dim3 blockDim, gridDim;
-static thread_local emu_warp* emu_my_warp = nullptr;
-static thread_local int emu_lane = 0;
-static std::barrier<>* emu_cta_barrier = nullptr;
+// (inline variables: ONE instance per program / shared library -- the csrc headers define inline device functions such as
+// warp_sum that several translation units share, so per-file statics would split the state)
+inline thread_local dim3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+inline thread_local emu_warp* emu_my_warp = nullptr;
+inline thread_local int emu_lane = 0;
+inline std::barrier<>* emu_cta_barrier = nullptr;
 
 #define __global__
 #define __device__
@@ -47,12 +52,20 @@ static std::barrier<>* emu_cta_barrier = nullptr;
 #define __launch_bounds__(...)
 #define __shared__ static
 // dynamic shared memory (common.cuh's SCAE_DYNAMIC_SMEM): one host buffer, CTAs run one after another
-alignas(16) static float emu_dynamic_smem[64 * 1024];
+alignas(16) inline float emu_dynamic_smem[64 * 1024];
 #define SCAE_DYNAMIC_SMEM(name) float* name = emu_dynamic_smem
 template <class T>
 inline T min(T a, T b) {
   return b < a ? b : a;
 }
+template <class T>
+inline T max(T a, T b) {
+  return a < b ? b : a;
+}
+inline long min(long a, int b) { return b < a ? (long)b : a; }
+inline long min(int a, long b) { return b < a ? b : (long)a; }
+inline long max(long a, int b) { return a < b ? (long)b : a; }
+inline long max(int a, long b) { return a < b ? b : (long)a; }
 
 template <class T>
 inline T __ldg(const T* p) {
@@ -84,8 +97,11 @@ inline T __shfl_sync(unsigned, T v, int src) {
 }
 
 // device math intrinsics used by the csrc headers
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 inline float __frcp_rn(float x) { return 1.0f / x; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fsqrt_rn(float x) { return sqrtf(x); }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline float __expf(float x) { return expf(x); }
 inline float __logf(float x) { return logf(x); }
 inline void sincospif(float x, float* s, float* c) {
@@ -103,30 +119,89 @@ inline float __int_as_float(int i) {
   return f;
 }
 
-// called by every emulated thread when its kernel body returns (ptx_emu.h flushes pending bulk stores there)
-static void (*emu_thread_exit_hook)() = nullptr;
+inline unsigned __float_as_uint(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+inline float __uint_as_float(unsigned u) {
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline float __fadd_rn(float a, float b) { return a + b; }      // (compiled with -ffp-contract=off: never fused)
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fadd_rd(float a, float b) {                       // round toward -infinity
+  const double exact = (double)a + (double)b;                    // exact: both addends are floats
+  float r = (float)exact;
+  if ((double)r > exact) r = nextafterf(r, -INFINITY);
+  return r;
+}
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+  return emu_shfl(v, emu_lane >= (int)delta ? emu_lane - (int)delta : emu_lane);
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  emu_my_warp->slot[emu_lane] = pred ? 1u : 0u;
+  emu_my_warp->bar.arrive_and_wait();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m |= (emu_my_warp->slot[l] & 1u) << l;
+  emu_my_warp->bar.arrive_and_wait();
+  return m;
+}
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+inline unsigned __match_any_sync(unsigned, unsigned value) {
+  emu_my_warp->slot[emu_lane] = value;
+  emu_my_warp->bar.arrive_and_wait();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m |= (emu_my_warp->slot[l] == value ? 1u : 0u) << l;
+  emu_my_warp->bar.arrive_and_wait();
+  return m;
+}
 
-// kernel<<<grid, block>>>(args...) -> emu_launch(grid, block, [&] { kernel(args...); })
+// called by every emulated thread when its kernel body returns (ptx_emu.h flushes pending bulk stores there)
+inline void (*emu_thread_exit_hook)() = nullptr;
+
+// kernel<<<grid, block, smem, stream>>>(args...) -> emu_launch(grid, block, [&] { kernel(args...); })
+// (tests/emu/build_lib.py rewrites the launches of whole .cu files this way).  A thread whose body returns leaves the
+// CTA and warp barriers, so kernels with early exits do not dead-lock the threads that go on.
+template <class F>
+void emu_launch(dim3 grid, dim3 block, F body) {
+  gridDim = grid;
+  blockDim = block;
+  const int n_threads = (int)block.x;
+  for (unsigned by = 0; by < grid.y; ++by) {
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+      std::barrier<> cta_bar(n_threads);
+      emu_cta_barrier = &cta_bar;
+      std::vector<std::unique_ptr<emu_warp>> warps;
+      for (int w = 0; w * 32 < n_threads; ++w) warps.emplace_back(new emu_warp(std::min(32, n_threads - w * 32)));
+      for (auto& w : warps)
+        for (int l = 0; l < 32; ++l) w->slot[l] = 0;
+      std::vector<std::thread> threads;
+      for (int t = 0; t < n_threads; ++t) {
+        threads.emplace_back([&, t] {
+          threadIdx = dim3((unsigned)t);
+          blockIdx = dim3(bx, by);
+          emu_my_warp = warps[t / 32].get();
+          emu_lane = t % 32;
+          body();
+          if (emu_thread_exit_hook) emu_thread_exit_hook();
+          emu_my_warp->bar.arrive_and_drop();
+          cta_bar.arrive_and_drop();
+        });
+      }
+      for (auto& th : threads) th.join();
+    }
+  }
+}
 template <class F>
 void emu_launch(int grid, int block, F body) {
-  gridDim.x = (unsigned)grid;
-  blockDim.x = (unsigned)block;
-  for (int cta = 0; cta < grid; ++cta) {
-    std::barrier<> cta_bar(block);
-    emu_cta_barrier = &cta_bar;
-    std::vector<std::unique_ptr<emu_warp>> warps;
-    for (int w = 0; w < (block + 31) / 32; ++w) warps.emplace_back(new emu_warp);
-    std::vector<std::thread> threads;
-    for (int t = 0; t < block; ++t) {
-      threads.emplace_back([&, t] {
-        threadIdx.x = (unsigned)t;
-        blockIdx.x = (unsigned)cta;
-        emu_my_warp = warps[t / 32].get();
-        emu_lane = t % 32;
-        body();
-        if (emu_thread_exit_hook) emu_thread_exit_hook();
-      });
-    }
-    for (auto& th : threads) th.join();
-  }
+  emu_launch(dim3((unsigned)grid), dim3((unsigned)block), body);
 }

@@ -1,5 +1,37 @@
-// Stand-in for <cuda_runtime.h> when the csrc headers are compiled for the host by tests/emu (TEST INFRASTRUCTURE).
+// Stand-in for <cuda_runtime.h> when the csrc sources are compiled for the host by tests/emu (TEST INFRASTRUCTURE):
+// the handful of runtime calls libscae_b200 makes, answered for an imaginary device with EMU_SM_COUNT SMs.
 #pragma once
+#include <stddef.h>
+#include <string.h>
+
+#include "simt.h"   // dim3, threadIdx, ...
+
+#ifndef EMU_SM_COUNT
+#define EMU_SM_COUNT 2
+#endif
+
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount, cudaDevAttrMaxSharedMemoryPerBlockOptin };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize, cudaFuncAttributePreferredSharedMemoryCarveout };
+enum { cudaSharedmemCarveoutMaxShared = 100 };
+
+inline cudaError_t cudaGetDevice(int* dev) {
+  *dev = 0;
+  return cudaSuccess;
+}
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
+  *v = attr == cudaDevAttrMultiProcessorCount ? EMU_SM_COUNT : 227 * 1024;
+  return cudaSuccess;
+}
+template <class F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) {
+  return cudaSuccess;
+}
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated device"; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+  memset(p, v, n);
+  return cudaSuccess;
+}
