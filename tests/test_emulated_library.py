@@ -194,3 +194,102 @@ def test_emulated_whole_model_vs_reference_golden(emu, case):
             continue
         e = l2_rel_err(got, ref) if k.startswith('part_encoder.') else rel_err(got, ref)
         assert e < (2e-3 if k.startswith('part_encoder.') else 1e-4), (k, e)
+
+
+def test_emulated_loss_head_attention_head_and_gemm_convolutions(emu):
+    """The round's newer kernels through their C entry points (host-side grid / workspace logic included): loss head vs
+    the analytic oracle, channels-last attention pooling vs nn_ext's formula, GEMM-form convolution vs F.conv2d."""
+    import torch.nn.functional as F
+    from oracle import manual_backward as mb
+    from torch_scae_b200 import nn_ext, ops
+    g = torch.Generator().manual_seed(5)
+    # ---- loss head (csrc/loss_head.cu): 70 rows -> several rows per warp on the 2-SM emulated device
+    B, O, V, K = 70, 10, 8, 10
+    cp = torch.rand(B, O, generator=g).requires_grad_(True)
+    post = (torch.rand(B, O, V, generator=g) / O).requires_grad_(True)
+    label = torch.randint(0, K, (B,), generator=g)
+    lin = torch.nn.Linear(O, K)
+    ws = (2.0, 0.35, 0.7, 0.2)
+    cfg = (1, 0, 1, *ws, float(O) / K, float(O) / K, float(B) / K)          # l2 prior, entropy posterior
+    total, terms, probs = ops._LossHead.apply(cp, post, label, lin.weight, lin.bias, cfg)
+    got = torch.autograd.grad(total * 1.3, [cp, post, lin.weight, lin.bias])
+    ref = mb.loss_head_forward_backward(cp.detach().double(), post.detach().double(), label, lin.weight.detach().double(),
+                                        lin.bias.detach().double(), K, 'l2', 'entropy', ws)
+    assert rel_err(total, ref['total']) < 1e-5 and rel_err(probs[0], ref['prior_cls_prob']) < 1e-5
+    for a, k in zip(got, ('g_caps_presence', 'g_posterior', 'g_weight', 'g_bias')):
+        assert rel_err(a, 1.3 * ref[k]) < 1e-4, k
+    # ---- channels-last attention pooling (csrc/attnpool_cl.cu)
+    Bq, n, D, S = 5, 6, 7, 9
+    y = torch.randn(Bq, S, n * (D + 1), generator=g, requires_grad=True)
+    up = torch.randn(Bq * n, D, generator=g)
+    out = ops._AttentionPoolCL.apply(y, n, D)
+    (gy,) = torch.autograd.grad((out * up).sum(), [y])
+    y64 = y.detach().double().requires_grad_(True)
+    nchw = y64.view(Bq, 3, 3, n * (D + 1)).permute(0, 3, 1, 2)
+    ref_out = nn_ext.multiple_attention_pooling_2d(nchw, n).reshape(Bq * n, D)
+    (ref_gy,) = torch.autograd.grad((ref_out * up.double()).sum(), [y64])
+    assert rel_err(out, ref_out) < 1e-5 and rel_err(gy, ref_gy) < 1e-5
+    # ---- GEMM-form 3x3 convolution (csrc/conv_cols.cu + ops._Conv3x3Gemm), both variants, both strides
+    for stride, full in ((2, True), (1, False), (1, True)):
+        conv = torch.nn.Conv2d(40, 33, 3, stride)
+        x = torch.randn(3, 40, 9, 8, generator=g, requires_grad=True)
+        yv = ops._Conv3x3Gemm.apply(x, conv.weight, conv.bias, stride, True, full)
+        upc = torch.randn(yv.shape, generator=g)
+        got = torch.autograd.grad((yv * upc).sum(), [x, conv.weight, conv.bias])
+        x64 = x.detach().double().requires_grad_(True)
+        w64, b64 = conv.weight.detach().double().requires_grad_(True), conv.bias.detach().double().requires_grad_(True)
+        y64 = torch.relu(F.conv2d(x64, w64, b64, stride))
+        ref = torch.autograd.grad((y64 * upc.double()).sum(), [x64, w64, b64])
+        assert rel_err(yv, y64) < 1e-5
+        for a, r in zip(got, ref):
+            assert l2_rel_err(a, r) < 1e-4, (stride, full)
+
+
+def test_emulated_set_attention_block_and_optimizer(emu):
+    """csrc/sab.cu (one kernel per direction for a whole set-attention block) vs the module's PyTorch ops; the flat
+    RMSprop kernel vs torch.optim.RMSprop."""
+    from torch_scae_b200 import ops, set_transformer
+    torch.manual_seed(3)
+    import copy
+    mab = set_transformer.MAB(d=16, n_heads=1, layer_norm=True)
+    with torch.no_grad():
+        for p in mab.parameters():                          # non-trivial LayerNorm affine parameters and biases
+            p.add_(torch.randn_like(p) * 0.3)
+    for presence in (torch.rand(5, 11), (torch.rand(5, 11) > 0.4).float(), None):
+        x = torch.randn(5, 11, 16, requires_grad=True)
+        att = mab.mqkv
+        params = (att.q_projector.weight, att.q_projector.bias, att.k_projector.weight, att.k_projector.bias,
+                  att.v_projector.weight, att.v_projector.bias, att.o_projector.weight, att.o_projector.bias,
+                  mab.fc.weight, mab.fc.bias, mab.ln0.weight, mab.ln0.bias, mab.ln1.weight, mab.ln1.bias)
+        up = torch.randn(5, 11, 16)
+        y = ops._SetAttentionBlock.apply(x, presence, float(mab.ln0.eps), float(mab.ln1.eps), *params)
+        got = torch.autograd.grad((y * up).sum(), [x, *params])
+        ref_mod = copy.deepcopy(mab).double()                  # the module's PyTorch ops, in fp64
+        x64 = x.detach().double().requires_grad_(True)
+        ref_y = ref_mod(x64, x64, presence.double() if presence is not None else None)
+        rm = ref_mod.mqkv
+        ref_params = (rm.q_projector.weight, rm.q_projector.bias, rm.k_projector.weight, rm.k_projector.bias,
+                      rm.v_projector.weight, rm.v_projector.bias, rm.o_projector.weight, rm.o_projector.bias,
+                      ref_mod.fc.weight, ref_mod.fc.bias, ref_mod.ln0.weight, ref_mod.ln0.bias, ref_mod.ln1.weight,
+                      ref_mod.ln1.bias)
+        ref = torch.autograd.grad((ref_y * up.double()).sum(), [x64, *ref_params])
+        assert rel_err(y, ref_y) < 2e-5
+        # the key-bias gradient is identically zero (softmax is invariant to a per-row constant): errors are measured
+        # against the gradient's own scale, floored at a fraction of the largest gradient of the block
+        floor = 1e-2 * max(float(r.abs().max()) for r in ref)
+        for a, r in zip(got, ref):
+            assert float((a.double() - r).abs().max()) / max(float(r.abs().max()), floor) < 1e-4
+    # RMSprop with momentum on a flat buffer
+    from torch_scae_b200 import _lib
+    lib = _lib.load()
+    p = torch.randn(1000)
+    grad = torch.randn(1000)
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.RMSprop([ref_p], lr=3e-3, momentum=0.9, eps=1e-4)
+    sq, buf = torch.zeros(1000), torch.zeros(1000)
+    for _ in range(3):
+        ref_p.grad = grad.clone()
+        opt.step()
+        _lib.check(lib.scae_rmsprop_step(p.data_ptr(), grad.data_ptr(), sq.data_ptr(), buf.data_ptr(), 1000, 3e-3, 0.99,
+                                         1e-4, 0.9, None), 'scae_rmsprop_step')
+    assert rel_err(p, ref_p) < 1e-6
