@@ -293,3 +293,59 @@ def test_emulated_set_attention_block_and_optimizer(emu):
         _lib.check(lib.scae_rmsprop_step(p.data_ptr(), grad.data_ptr(), sq.data_ptr(), buf.data_ptr(), 1000, 3e-3, 0.99,
                                          1e-4, 0.9, None), 'scae_rmsprop_step')
     assert rel_err(p, ref_p) < 1e-6
+
+
+BASELINE_SHAPES = {
+    # BASELINE.json configs[4]: SVHN/CIFAR-shaped colour templates, 24 part capsules
+    'color': dict(image_shape=(3, 32, 32), n_classes=10, n_part_caps=24, n_obj_caps=32,
+                  scae_params=dict(reconstruct_alternatives=False)),
+    # BASELINE.json configs[3]: likelihood-stress, 64x64 images, 21x21 templates, 64 part / 32 object capsules
+    'stress': dict(image_shape=(1, 64, 64), n_classes=10, n_part_caps=64, n_obj_caps=32,
+                   pcae_template_generator_params=dict(template_size=(21, 21)),
+                   scae_params=dict(reconstruct_alternatives=False)),
+}
+
+
+@pytest.mark.parametrize('name', ['color', 'stress'])
+def test_emulated_whole_model_at_the_other_baseline_shapes(emu, name):
+    """One train step of the whole SCAE at the colour and likelihood-stress shapes of BASELINE.json (B = 2): loss, log
+    entries and gradients against the CPU oracle model (oracle/scae_model.py, the reference's op sequence).  These
+    shapes take the chunked template kernels (64 templates of 21x21 do not fit shared memory at once), three-channel
+    texels, and the single-stage capsule backward."""
+    import numpy as np
+    from oracle import scae_model
+    from torch_scae_b200 import factory
+    params = BASELINE_SHAPES[name]
+    torch.manual_seed(1)
+    np.random.seed(1)
+    model = factory.make_scae(params)
+    with torch.no_grad():
+        for pname, p in model.named_parameters():
+            if 'templates_alpha' in pname or 'cpr_static' in pname or 'caps_bias_list' in pname:
+                p.copy_(0.1 * torch.randn_like(p))
+    cfg = factory.prepare_model_params(**params)
+    B = 2
+    C, H, W = params['image_shape']
+    M, O = params['n_part_caps'], params['n_obj_caps']
+    image = torch.rand(B, C, H, W)
+    label = torch.randint(0, 10, (B,))
+    noise = dict(part_presence=(torch.rand(B, M) - .5) * 4, caps=(torch.rand(B, O, 1) - .5) * 4,
+                 vote=(torch.rand(B, O, M) - .5) * 4)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    ref_res = scae_model.scae_forward(sd, cfg, image, noise, training=True)
+    ref_loss, ref_log = scae_model.scae_loss(ref_res, cfg, image, label)
+    ref_loss.backward()
+
+    model.train()
+    res = model(image, noise=noise)
+    loss, log = model.loss(res, image, label)
+    loss.backward()
+    assert rel_err(loss, ref_loss) < 1e-5
+    for k in ref_log:
+        assert rel_err(log[k], ref_log[k]) < 1e-5, k
+    named = dict(model.named_parameters())
+    for k in ('part_decoder.templates_alpha', 'part_decoder.bg_value', 'part_decoder.bg_mixing_logit',
+              'template_generator.template_logits', 'obj_decoder.capsule_layer.cpr_static', 'obj_encoder.fc1.weight'):
+        assert rel_err(named[k].grad, sd[k].grad) < 1e-4, k
+    for k in ('part_encoder.att_conv.weight', 'part_encoder.encoder.network.0.weight'):
+        assert l2_rel_err(named[k].grad, sd[k].grad) < 2e-3, k
