@@ -110,14 +110,15 @@ class GraphedTrainStep:
                                for _ in range(2)]
             self._ready = [torch.cuda.Event() for _ in range(2)]
             self._consumed = [torch.cuda.Event() for _ in range(2)]
-            self._staged, self._stage_idx = [], 0
+            self._staged, self._stage_idx, self._has_label = [], 0, [False, False]
         if len(self._staged) == 2:
             raise RuntimeError('both staging buffers hold batches that no step has consumed yet')
         k = self._stage_idx
         self._copy_stream.wait_event(self._consumed[k])     # no-op until a step has read this buffer
         with torch.cuda.stream(self._copy_stream):
             self._stage_img[k].copy_(image, non_blocking=True)
-            if label is not None and self._stage_lab[k] is not None:
+            self._has_label[k] = label is not None and self._stage_lab[k] is not None
+            if self._has_label[k]:
                 self._stage_lab[k].copy_(label, non_blocking=True)
             self._ready[k].record(self._copy_stream)
         self._staged.append(k)
@@ -128,7 +129,7 @@ class GraphedTrainStep:
         cur = torch.cuda.current_stream()
         cur.wait_event(self._ready[k])
         self.static_image.copy_(self._stage_img[k], non_blocking=True)
-        if self._stage_lab[k] is not None:
+        if self._has_label[k]:                           # a batch staged without labels keeps the previous ones
             self.static_label.copy_(self._stage_lab[k], non_blocking=True)
         self._consumed[k].record(cur)
 
