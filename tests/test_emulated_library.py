@@ -34,7 +34,7 @@ def emu(emulated_library, monkeypatch):
     def host_ptr(t):
         if t is None:
             return None
-        assert t.is_contiguous() and not t.is_cuda
+        assert t.is_contiguous() and t.device.type == 'cpu'
         return t.data_ptr()
     monkeypatch.setattr(_lib, '_lib', lib)
     monkeypatch.setattr(_lib, 'ptr', host_ptr)
@@ -349,3 +349,44 @@ def test_emulated_whole_model_at_the_other_baseline_shapes(emu, name):
         assert rel_err(named[k].grad, sd[k].grad) < 1e-4, k
     for k in ('part_encoder.att_conv.weight', 'part_encoder.encoder.network.0.weight'):
         assert l2_rel_err(named[k].grad, sd[k].grad) < 2e-3, k
+
+
+@pytest.mark.parametrize('case', ['enc', 'hard'])
+def test_emulated_whole_model_through_every_fused_path(emu, monkeypatch, case):
+    """As test_emulated_whole_model_vs_reference_golden, but with the modules' own routing switched to the kernels
+    everywhere (tensors report ``is_cuda`` for the duration of the test): fused capsule head of the part encoder,
+    GEMM-form convolutions, set-attention blocks, LayerNorm, split-K linears with the colsum kernel, pose transform, loss
+    head -- the train step's whole kernel inventory on the CPU, against the reference's golden loss and gradients."""
+    from conftest import load_golden, sub
+    from golden.cases import scae_case_params
+    from torch_scae_b200 import factory
+    monkeypatch.setattr(torch.Tensor, 'is_cuda', property(lambda self: True), raising=False)
+    g = load_golden('scae_' + case)
+    model = factory.make_scae(scae_case_params(case))
+    model.load_state_dict(sub(g, 'param.'), strict=True)
+    model.train()
+    image, label = g['image'], g['label']
+    noise = dict(part_presence=g['noise_part_presence'], caps=g['noise_caps'], vote=g['noise_vote'])
+    before = emu.scae_launch_count()
+    res = model(image, noise=noise)
+    loss, log = model.loss(res, image, label)
+    loss.backward()
+    launches = emu.scae_launch_count() - before
+    assert launches >= 25, launches                       # (the two likelihood paths alone are 9 launches)
+    assert rel_err(loss, g['loss']) < 1e-5
+    for k, ref in sub(g, 'log.').items():
+        assert rel_err(log[k], ref) < 1e-5, k
+    assert float(model.calculate_accuracy(res, label)) == float(g['accuracy'])
+    grads = {name: p.grad for name, p in model.named_parameters()}
+    layer = model.obj_decoder.capsule_layer
+    for mod_name, mod in (('mlps', layer.mlps), ('caps_mlps', layer.caps_mlps)):
+        for suffix, p in mod._named():
+            for i in range(mod.n):
+                grads[f'obj_decoder.capsule_layer.{mod_name}.{i}.{suffix}'] = p.grad[i]
+    for k, ref in sub(g, 'g_param.').items():
+        got = grads[k]
+        if float(ref.abs().max()) == 0.0:
+            assert got is None or float(got.abs().max()) == 0.0, k
+            continue
+        e = l2_rel_err(got, ref) if k.startswith('part_encoder.') else rel_err(got, ref)
+        assert e < (2e-3 if k.startswith('part_encoder.') else 1e-4), (k, e)
