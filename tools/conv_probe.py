@@ -1,7 +1,6 @@
 """Times the CNN part encoder (fwd+bwd, strict fp32) in NCHW vs channels_last to pick the faster layout."""
 import os
 import sys
-import time
 
 import torch
 
