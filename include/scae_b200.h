@@ -255,6 +255,8 @@ int scae_conv_cols_supported(int B, int C, int H, int W, int stride);
 int scae_im2col3x3(const float* x, float* cols, int B, int C, int H, int W, int stride, scae_stream_t stream);
 /* dcols[B * L, C * 9] -> dx[B, C, H, W]: the adjoint of im2col (the data gradient's scatter, written as a gather) */
 int scae_col2im3x3(const float* dcols, float* dx, int B, int C, int H, int W, int stride, scae_stream_t stream);
+/* in[batch, R, Cc] -> out[batch, Cc, R]: NCHW <-> rows (channels-last) for the operands / results of those GEMMs. */
+int scae_transpose_batched(const float* in, float* out, int batch, int R, int Cc, scae_stream_t stream);
 
 /* One set-attention block of the object encoder (reference set_transformer.py:74-153: MAB(x, x) with single-head QKV
  * attention, residual, presence mask, LayerNorm, feed-forward + residual, LayerNorm) on x[B, N, 16], N <= 64, as one

@@ -390,3 +390,17 @@ def test_emulated_whole_model_through_every_fused_path(emu, monkeypatch, case):
             continue
         e = l2_rel_err(got, ref) if k.startswith('part_encoder.') else rel_err(got, ref)
         assert e < (2e-3 if k.startswith('part_encoder.') else 1e-4), (k, e)
+
+
+@pytest.mark.parametrize('B,C,H,W', [(3, 128, 9, 9), (2, 5, 3, 11), (1, 33, 1, 1), (4, 40, 5, 5)])
+def test_emulated_nchw_rows_transposes(emu, B, C, H, W):
+    """scae_transpose_batched behind ops._NchwToRows: (B,C,H,W) -> (B*H*W, C) and back in the backward; pure data
+    movement, so exact."""
+    from torch_scae_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+    rows = ops._NchwToRows.apply(x)
+    assert torch.equal(rows, x.permute(0, 2, 3, 1).reshape(B * H * W, C))
+    up = torch.randn(B * H * W, C, generator=g)
+    (gx,) = torch.autograd.grad((rows * up).sum(), [x])
+    assert torch.equal(gx, up.view(B, H, W, C).permute(0, 3, 1, 2))

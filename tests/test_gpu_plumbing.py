@@ -456,3 +456,15 @@ def test_conv_gemm_paths_are_taken():
         torch.cuda.synchronize()
         got = {k for k in timer.summary() if k in ('scae_im2col3x3', 'scae_col2im3x3')}
         assert got == expect, (cin, hw, stride, got)
+
+
+@pytest.mark.parametrize('B,C,H,W', [(64, 128, 9, 9), (3, 5, 3, 11), (1024, 128, 5, 5)])
+def test_nchw_rows_transposes(B, C, H, W):
+    """scae_transpose_batched behind ops._NchwToRows (the GEMM operands' layout): exact data movement both ways."""
+    from torch_scae_b200 import ops
+    x = torch.randn(B, C, H, W, device='cuda', requires_grad=True)
+    rows = ops._NchwToRows.apply(x)
+    assert torch.equal(rows, x.permute(0, 2, 3, 1).reshape(B * H * W, C))
+    up = torch.randn(B * H * W, C, device='cuda')
+    (gx,) = torch.autograd.grad((rows * up).sum(), [x])
+    assert torch.equal(gx, up.view(B, H, W, C).permute(0, 3, 1, 2))

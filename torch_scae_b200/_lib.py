@@ -113,6 +113,7 @@ SYMBOLS = {
     'scae_conv_cols_supported': (c_int, [c_int] * 5),
     'scae_im2col3x3': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'scae_col2im3x3': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'scae_transpose_batched': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'scae_attnpool_cl_supported': (c_int, [c_long, c_int, c_int, c_int]),
     'scae_attnpool_cl_fwd': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),
     'scae_attnpool_cl_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),

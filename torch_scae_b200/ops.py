@@ -173,6 +173,30 @@ class _ConvBiasAct(torch.autograd.Function):
         return gx, gw, g_bias if ctx.needs_input_grad[2] else None, None, None
 
 
+def _transpose_batched(x, batch, R, Cc):
+    """x viewed as [batch, R, Cc] (contiguous fp32) -> new tensor [batch, Cc, R] through scae_transpose_batched."""
+    lib = _lib.load()
+    out = torch.empty(batch, Cc, R, device=x.device, dtype=torch.float32)
+    check(_timed('scae_transpose_batched', lib.scae_transpose_batched, ptr(x), ptr(out), batch, R, Cc, _stream()),
+          'scae_transpose_batched')
+    return out
+
+
+class _NchwToRows(torch.autograd.Function):
+    """(B, C, H, W) -> (B*H*W, C): the rows = positions matrix of a feature map, and back in the backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, C, H, W = x.shape
+        ctx.shape = (B, C, H, W)
+        return _transpose_batched(x.contiguous(), B, C, H * W).view(B * H * W, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, H, W = ctx.shape
+        return _transpose_batched(g.contiguous(), B, H * W, C).view(B, C, H, W)
+
+
 def _split_k_wgrad(g2d, cols, cap=32, min_rows=256):
     """g2d^T @ cols for tall operands (rows, C_out) / (rows, K): few output tiles and a very long reduction, so the
     rows are cut into up to ``cap`` chunks reduced by one batched GEMM and summed (60 vs 44 TFLOP/s on B200 for the
@@ -204,7 +228,7 @@ class _Conv3x3Gemm(torch.autograd.Function):
                   'scae_im2col3x3')
             w2d_t = weight.reshape(Co, C * 9).t()
             y2d = torch._addmm_activation(bias, cols, w2d_t) if relu else torch.addmm(bias, cols, w2d_t)
-            y = y2d.view(B, Ho, Wo, Co).permute(0, 3, 1, 2).contiguous()
+            y = _transpose_batched(y2d, B, Ho * Wo, Co).view(B, Co, Ho, Wo)
         elif relu and os.environ.get('SCAE_B200_CUDNN_FUSED_RELU', '0') == '1':
             y = torch.cudnn_convolution_relu(x, weight, bias, (stride, stride), (0, 0), (1, 1), 1).contiguous()
         else:
@@ -229,7 +253,7 @@ class _Conv3x3Gemm(torch.autograd.Function):
         ws = _workspace(ws_bytes, g.device)
         check(_timed('scae_bias_act_bwd', lib.scae_bias_act_bwd, ptr(g), ptr(y), ptr(gx_pre) if relu else None,
                      ptr(g_bias), B, Co, Ho * Wo, int(relu), ptr(ws), ws_bytes, _stream()), 'scae_bias_act_bwd')
-        g2d = gx_pre.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Co)
+        g2d = _transpose_batched(gx_pre, B, Co, Ho * Wo).view(B * Ho * Wo, Co)
         gx = gw = None
         if ctx.needs_input_grad[0]:
             dcols = g2d @ weight.reshape(Co, C * 9)
@@ -377,7 +401,7 @@ def attention_conv_pool(feature_map, conv, n_caps):
     G = Ctot // n_caps
     if B == 0 or not _lib.load().scae_attnpool_cl_supported(B * n_caps, n_caps, G - 1, S):
         return None
-    x2d = feature_map.permute(0, 2, 3, 1).reshape(B * S, Cin)
+    x2d = _NchwToRows.apply(feature_map)
     y = _PositionsGemm.apply(x2d, conv.weight.reshape(Ctot, Cin))
     pooled = _AttentionPoolCL.apply(y.view(B, S, Ctot), n_caps, G - 1).view(B, n_caps, G - 1)
     return (pooled + conv.bias.view(n_caps, G)[:, :-1]).reshape(B, n_caps * (G - 1), 1, 1)
