@@ -36,6 +36,9 @@ SCAE_CASES = dict(
     soft=dict(vote_type='soft', presence_type='soft', stop_grad_caps_target=False),
     hard=dict(vote_type='hard', presence_type='hard', recon_mse_weight=0.5, part_caps_sparsity_weight=0.1,
               posterior_sparsity_loss_type='kl'),
+    # the other sparsity-loss types of object_decoder.py:431-493: entropy on the prior, l2 on the posterior
+    sparse=dict(prior_sparsity_loss_type='entropy', posterior_sparsity_loss_type='l2',
+                prior_within_example_sparsity_weight=1.3, prior_between_example_sparsity_weight=0.6),
 )
 
 
