@@ -43,5 +43,15 @@ SCAE_CASES = dict(
 
 
 
+# whole-model cases that also change the model outside the SCAE wrapper: colour images, temperature-mode decoder with a
+# learnt output scale (part_decoder.py:215-223)
+SCAE_MODEL_OVERRIDES = dict(
+    color_temp=dict(image_shape=(3, 20, 20), pcae_decoder_params=dict(use_alpha_channel=False, learn_output_scale=True)),
+)
+SCAE_CASES['color_temp'] = dict(vote_type='soft', presence_type='enc')
+
+
 def scae_case_params(case):
-    return tiny_model_params(**SCAE_CASES[case])
+    params = tiny_model_params(**SCAE_CASES[case])
+    params.update(SCAE_MODEL_OVERRIDES.get(case, {}))
+    return params

@@ -22,7 +22,7 @@ sys.path.insert(0, HERE)
 from _reference_loader import load_reference  # noqa: E402
 
 load_reference()
-from cases import CAPSULE_CASES, DECODER_CASES, SCAE_CASES, tiny_model_params  # noqa: E402
+from cases import CAPSULE_CASES, DECODER_CASES, SCAE_CASES, scae_case_params, tiny_model_params  # noqa: E402
 from torch_scae import cv_ops, factory  # noqa: E402
 from torch_scae.object_decoder import CapsuleLayer, CapsuleObjectDecoder  # noqa: E402
 from torch_scae.part_decoder import TemplateBasedImageDecoder  # noqa: E402
@@ -167,7 +167,7 @@ def make_capsule(name, c, seed):
 def make_scae(name, scae_kwargs, seed):
     torch.manual_seed(seed)
     np.random.seed(seed)
-    params = tiny_model_params(**scae_kwargs)
+    params = scae_case_params(name)
     model = factory.make_scae(params)
     with torch.no_grad():                       # zero-initialised tensors would hide wiring mistakes
         for k, p in model.named_parameters():
@@ -175,7 +175,7 @@ def make_scae(name, scae_kwargs, seed):
                     'caps_bias_list' in k or 'bg_' in k:
                 p.copy_(torch.randn_like(p) * 0.3)
     model.train()
-    image = torch.rand(3, 1, 20, 20)
+    image = torch.rand(3, *params['image_shape'])
     label = torch.randint(0, 10, (3,))
     with _RecordRand() as rr:
         res = model(image)

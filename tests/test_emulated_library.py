@@ -148,7 +148,7 @@ def _colsum(ops, x):
     return out
 
 
-@pytest.mark.parametrize('case', ['enc', 'soft', 'hard', 'sparse'])
+@pytest.mark.parametrize('case', ['enc', 'soft', 'hard', 'sparse', 'color_temp'])
 def test_emulated_whole_model_vs_reference_golden(emu, case):
     """The whole SCAE (PyTorch modules on the CPU + both likelihood paths through the emulated library) against the
     golden vectors recorded from the reference itself (tests/golden/make_golden.py): loss, every log entry, outputs and
@@ -351,7 +351,7 @@ def test_emulated_whole_model_at_the_other_baseline_shapes(emu, name):
         assert l2_rel_err(named[k].grad, sd[k].grad) < 2e-3, k
 
 
-@pytest.mark.parametrize('case', ['enc', 'hard', 'sparse'])
+@pytest.mark.parametrize('case', ['enc', 'hard', 'sparse', 'color_temp'])
 def test_emulated_whole_model_through_every_fused_path(emu, monkeypatch, case):
     """As test_emulated_whole_model_vs_reference_golden, but with the modules' own routing switched to the kernels
     everywhere (tensors report ``is_cuda`` for the duration of the test): fused capsule head of the part encoder,

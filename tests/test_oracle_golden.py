@@ -18,7 +18,7 @@ from oracle import template_likelihood as tl
 
 DECODER = ['alpha_c1', 'alpha_c3_nopres', 'temp_c3_bgimage', 'temp_c1']
 CAPSULE = ['default', 'similarity_plain', 'wide']
-SCAE = ['enc', 'soft', 'hard', 'sparse']
+SCAE = ['enc', 'soft', 'hard', 'sparse', 'color_temp']
 CAPSULE_FLAGS = dict(
     default=dict(similarity=False, learn_vote_scale=True, allow_deformations=True),
     similarity_plain=dict(similarity=True, learn_vote_scale=False, allow_deformations=False),
