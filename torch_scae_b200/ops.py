@@ -319,7 +319,8 @@ class _AttentionPool(torch.autograd.Function):
         (h,) = ctx.saved_tensors
         groups, D, S = ctx.dims
         gh = torch.empty_like(h)
-        check(_timed('scae_attnpool_bwd', lib.scae_attnpool_bwd, ptr(h), ptr(g.contiguous()), ptr(gh), groups, D, S,
+        g = g.contiguous()                   # (a named reference: the buffer must outlive the call)
+        check(_timed('scae_attnpool_bwd', lib.scae_attnpool_bwd, ptr(h), ptr(g), ptr(gh), groups, D, S,
                      _stream()), 'scae_attnpool_bwd')
         return gh, None, None, None
 
@@ -355,7 +356,8 @@ class _AttentionPoolCL(torch.autograd.Function):
         n, D = ctx.dims
         B, S, _ = y.shape
         gy = torch.empty_like(y)
-        check(_timed('scae_attnpool_cl_bwd', lib.scae_attnpool_cl_bwd, ptr(y), ptr(g.contiguous()), ptr(gy), B * n, n,
+        g = g.contiguous()
+        check(_timed('scae_attnpool_cl_bwd', lib.scae_attnpool_cl_bwd, ptr(y), ptr(g), ptr(gy), B * n, n,
                      D, S, _stream()), 'scae_attnpool_cl_bwd')
         return gy, None, None
 
@@ -425,7 +427,8 @@ class _PoseTransform(torch.autograd.Function):
         lib = _lib.load()
         (t,) = ctx.saved_tensors
         gt = torch.empty_like(t)
-        check(_timed('scae_pose_transform', lib.scae_pose_transform, ptr(t), ptr(g.contiguous()), ptr(gt),
+        g = g.contiguous()
+        check(_timed('scae_pose_transform', lib.scae_pose_transform, ptr(t), ptr(g), ptr(gt),
                      t.numel() // 6, int(ctx.similarity), _stream()), 'scae_pose_transform')
         return gt, None
 
