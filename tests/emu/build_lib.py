@@ -75,7 +75,8 @@ def rewrite_launches(src):
         end_args = _matching(src, k + 3, '(', ')')
         args = src[k + 4:end_args - 1]
         assert src[end_args] == ';', src[end_args - 40:end_args + 5]
-        out += src[at:j] + f'emu_launch(dim3({cfg[0]}), dim3({cfg[1]}), [&] {{ {kernel}({args}); }});'
+        smem = cfg[2] if len(cfg) > 2 else '0'
+        out += src[at:j] + f'emu_launch(dim3({cfg[0]}), dim3({cfg[1]}), [&] {{ {kernel}({args}); }}, (size_t)({smem}));'
         at = end_args + 1
 
 
@@ -85,13 +86,15 @@ def rewrite(src):
                   r'\1* \2 = reinterpret_cast<\1*>(emu_dynamic_smem);', src)
 
 
-def build(build_dir, sm_count=2):
-    """-> path of the emulated shared library"""
+def build(build_dir, sm_count=2, extra_flags=(), link_flags=()):
+    """-> path of the emulated shared library.  ``extra_flags`` / ``link_flags``: e.g. ('-g', '-fsanitize=address',
+    '-DEMU_EXACT_SMEM') and ('-fsanitize=address',) for the memcheck build, ('-g', '-fsanitize=thread') for the race
+    check (tests/emu/README.md)."""
     from torch_scae_b200.build import SOURCES
     os.makedirs(build_dir, exist_ok=True)
     flags = ['-x', 'c++', '-std=c++20', '-O1', '-fPIC', '-pthread', '-ffp-contract=off', '-D_GNU_SOURCE',
              f'-DEMU_SM_COUNT={sm_count}', '-I', os.path.join(EMU, 'stubs'), '-I', EMU, '-I', CSRC,
-             '-I', os.path.join(ROOT, 'include'), '-include', 'simt.h', '-include', 'ptx_emu.h', '-w']
+             '-I', os.path.join(ROOT, 'include'), '-include', 'simt.h', '-include', 'ptx_emu.h', '-w', *extra_flags]
 
     def compile_one(name):
         text = rewrite(open(os.path.join(CSRC, name)).read())
@@ -106,11 +109,14 @@ def build(build_dir, sm_count=2):
     with concurrent.futures.ThreadPoolExecutor(8) as pool:
         objs = list(pool.map(compile_one, SOURCES))
     lib = os.path.join(build_dir, 'libscae_b200_emu.so')
-    subprocess.run(['g++', '-shared', '-pthread', '-o', lib, *objs], check=True)
+    subprocess.run(['g++', '-shared', '-pthread', *link_flags, '-o', lib, *objs], check=True)
     return lib
 
 
 if __name__ == '__main__':
     import sys
     sys.path.insert(0, ROOT)
-    print(build(sys.argv[1] if len(sys.argv) > 1 else '/tmp/scae_emu_build'))
+    mode = sys.argv[2] if len(sys.argv) > 2 else ''
+    flags = {'asan': (('-g', '-fsanitize=address', '-fno-omit-frame-pointer', '-DEMU_EXACT_SMEM'), ('-fsanitize=address',)),
+             'tsan': (('-g', '-fsanitize=thread'), ('-fsanitize=thread',)), '': ((), ())}[mode]
+    print(build(sys.argv[1] if len(sys.argv) > 1 else '/tmp/scae_emu_build', extra_flags=flags[0], link_flags=flags[1]))

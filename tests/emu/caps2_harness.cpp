@@ -74,7 +74,7 @@ int main(int argc, char** argv) {
 
   // ---- forward: one CTA per image (caps2_fwd) ----
   const Caps2FwdLayout LF = caps2_fwd_layout(O, V, a.noise_vote != nullptr);
-  if ((size_t)LF.total > sizeof(emu_dynamic_smem) / sizeof(float)) return 3;
+  if ((size_t)LF.total > kEmuSmemFloats) return 3;
   emu_launch(B, threads_fwd, [&] {
     if (sim) caps2_fwd_kernel<true>(a, o, LF);
     else caps2_fwd_kernel<false>(a, o, LF);
@@ -100,7 +100,7 @@ int main(int argc, char** argv) {
   up.g_mixing_logit = in["g_mixing_logit"].as<float>();
   const int stages = cfg[7];
   const Caps2BwdLayout LB = caps2_bwd_layout(O, V, a.noise_vote != nullptr, up.g_posterior_mixing_prob != nullptr, stages);
-  if ((size_t)LB.total > sizeof(emu_dynamic_smem) / sizeof(float)) return 3;
+  if ((size_t)LB.total > kEmuSmemFloats) return 3;
   if (V * 8 + O * 4 > kSmallMax * threads_bwd) return 4;
   float* g_all = f("g_all_param", (size_t)B * O * A);
   float* g_presence = a.presence ? f("g_presence", (size_t)B * V) : nullptr;

@@ -1,17 +1,26 @@
-"""Race check of the kernels under the emulation (TEST INFRASTRUCTURE, run by hand): every emulated CUDA thread is a
-real thread, so ThreadSanitizer sees a shared-memory access that is not ordered by a barrier -- a missing
-__syncthreads / __syncwarp -- as a data race.
+"""Sanitizer passes over the kernels under the emulation (TEST INFRASTRUCTURE, run by hand).
 
-    sed -e "s/'-O1'/'-O1', '-g', '-fsanitize=thread'/" \\
-        -e "s/\\['g++', '-shared', '-pthread',/['g++', '-shared', '-pthread', '-fsanitize=thread',/" \\
-        tests/emu/build_lib.py > /tmp/build_tsan.py && python /tmp/build_tsan.py /tmp/scae_emu_tsan   # (copy it next to build_lib.py first)
+Race check -- every emulated CUDA thread is a real thread, so ThreadSanitizer reports a shared-memory access that no
+barrier orders (a missing __syncthreads / __syncwarp) as a data race:
+
+    python tests/emu/build_lib.py /tmp/scae_emu_tsan tsan
     LD_PRELOAD=$(gcc -print-file-name=libtsan.so) TSAN_OPTIONS="report_signal_unsafe=0 exitcode=0 history_size=4" \\
-        python tests/emu/tsan_run.py /tmp/scae_emu_tsan/libscae_b200_emu.so 2> tsan.txt
+        python tests/emu/sanitizer_run.py /tmp/scae_emu_tsan/libscae_b200_emu.so 2> tsan.txt
 
-Round 1 result: template, capsule (general and TMA-staged, with the deferred asynchronous copies), loss-head, pooling,
-im2col / col2im, transpose and LayerNorm kernels are clean.  The set-attention kernels report races for ragged N only:
-threads beyond 4 N are clamped to the last token, recompute it redundantly and read its rows across warps behind a
-__syncwarp; their results are discarded (no stores, no contribution to the parameter gradients), so the race is benign.
+Memory check -- with -DEMU_EXACT_SMEM every launch gets its dynamic shared memory as a heap block of exactly the size
+it asked for, so AddressSanitizer catches overruns of a kernel's shared-memory layout as well as out-of-bounds global
+accesses (the CPU counterpart of compute-sanitizer memcheck):
+
+    python tests/emu/build_lib.py /tmp/scae_emu_asan asan
+    LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 \\
+        python tests/emu/sanitizer_run.py /tmp/scae_emu_asan/libscae_b200_emu.so 2> asan.txt
+
+Round 1 result (the shapes below and both hot paths again at the MNIST / stress shapes with their real launch
+configurations): no memory errors; no races in the template, capsule (general and TMA-staged, with the deferred
+asynchronous copies), loss-head, pooling, im2col / col2im, transpose and LayerNorm kernels.  The set-attention kernels
+report races for ragged N only: threads beyond 4 N are clamped to the last token, recompute it redundantly and read its
+rows across warps behind a __syncwarp; their results are discarded (no stores, no contribution to the parameter
+gradients), so the race is benign.
 """
 import sys, ctypes
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')

@@ -9,6 +9,8 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -52,7 +54,9 @@ inline std::barrier<>* emu_cta_barrier = nullptr;
 #define __launch_bounds__(...)
 #define __shared__ static
 // dynamic shared memory (common.cuh's SCAE_DYNAMIC_SMEM): one host buffer, CTAs run one after another
-alignas(16) inline float emu_dynamic_smem[64 * 1024];
+constexpr size_t kEmuSmemFloats = 64 * 1024;
+alignas(16) inline float emu_smem_storage[kEmuSmemFloats];
+inline float* emu_dynamic_smem = emu_smem_storage;   // (with -DEMU_EXACT_SMEM: a heap block of exactly the launch's size)
 #define SCAE_DYNAMIC_SMEM(name) float* name = emu_dynamic_smem
 template <class T>
 inline T min(T a, T b) {
@@ -172,10 +176,34 @@ inline void (*emu_thread_exit_hook)() = nullptr;
 // (tests/emu/build_lib.py rewrites the launches of whole .cu files this way).  A thread whose body returns leaves the
 // CTA and warp barriers, so kernels with early exits do not dead-lock the threads that go on.
 template <class F>
-void emu_launch(dim3 grid, dim3 block, F body) {
+void emu_launch(dim3 grid, dim3 block, F body, size_t smem_bytes = (size_t)-1) {
   gridDim = grid;
   blockDim = block;
   const int n_threads = (int)block.x;
+#ifdef EMU_EXACT_SMEM
+  // memcheck mode (build with AddressSanitizer): dynamic shared memory is a heap block of exactly the size the launch
+  // asked for, so an overrun of the kernel's shared-memory layout lands in a redzone
+  struct Exact {
+    float* saved = emu_dynamic_smem;
+    void* block = nullptr;
+    explicit Exact(size_t bytes) {
+      if (bytes != (size_t)-1) {
+        block = aligned_alloc(16, (bytes + 15) / 16 * 16 + 16);
+        emu_dynamic_smem = static_cast<float*>(block);
+      }
+    }
+    ~Exact() {
+      emu_dynamic_smem = saved;
+      free(block);
+    }
+  } exact(smem_bytes);
+#else
+  if (smem_bytes != (size_t)-1 && smem_bytes > sizeof(emu_smem_storage)) {
+    fprintf(stderr, "emu_launch: %zu bytes of dynamic shared memory requested, %zu available\n", smem_bytes,
+            sizeof(emu_smem_storage));
+    abort();
+  }
+#endif
   for (unsigned by = 0; by < grid.y; ++by) {
     for (unsigned bx = 0; bx < grid.x; ++bx) {
       std::barrier<> cta_bar(n_threads);
