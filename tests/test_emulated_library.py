@@ -230,9 +230,12 @@ def test_emulated_loss_head_attention_head_and_gemm_convolutions(emu):
     (ref_gy,) = torch.autograd.grad((ref_out * up.double()).sum(), [y64])
     assert rel_err(out, ref_out) < 1e-5 and rel_err(gy, ref_gy) < 1e-5
     # ---- GEMM-form 3x3 convolution (csrc/conv_cols.cu + ops._Conv3x3Gemm), both variants, both strides
-    for stride, full in ((2, True), (1, False), (1, True)):
-        conv = torch.nn.Conv2d(40, 33, 3, stride)
-        x = torch.randn(3, 40, 9, 8, generator=g, requires_grad=True)
+    # (the 31x31 / 15x15 maps are those of the 64x64 likelihood-stress config: 130 KB / 98 KB shared-memory tiles)
+    for stride, full, cin, hw in ((2, True, 40, (9, 8)), (1, False, 40, (9, 8)), (1, True, 40, (9, 8)),
+                                  (2, True, 32, (31, 31)), (1, False, 32, (15, 15))):
+        assert emu.scae_conv_cols_supported(3, cin, hw[0], hw[1], stride) == 1
+        conv = torch.nn.Conv2d(cin, 33, 3, stride)
+        x = torch.randn(3, cin, *hw, generator=g, requires_grad=True)
         yv = ops._Conv3x3Gemm.apply(x, conv.weight, conv.bias, stride, True, full)
         upc = torch.randn(yv.shape, generator=g)
         got = torch.autograd.grad((yv * upc).sum(), [x, conv.weight, conv.bias])
