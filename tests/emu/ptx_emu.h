@@ -10,7 +10,9 @@
 #pragma once
 #define SCAE_PTX_SM100_CUH_   // keeps the real header out
 
+#include <barrier>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -22,6 +24,35 @@ namespace scae {
 inline float ex2_approx(float x) { return exp2f(x); }
 inline float lg2_approx(float x) { return log2f(x); }
 inline float rcp_approx(float x) { return 1.0f / x; }
+inline float sin_approx(float x) { return sinf(x); }
+inline float cos_approx(float x) { return cosf(x); }
+
+// REDUX over the lanes of `mask`: like the shuffles, every live lane of the warp publishes between two warp barriers
+// (the kernels call these from converged code only)
+inline unsigned emu_redux(unsigned mask, unsigned v, bool want_max) {
+  emu_my_warp->slot[emu_lane] = v;
+  emu_my_warp->bar.arrive_and_wait();
+  unsigned r = want_max ? 0u : 0xffffffffu;
+  for (int l = 0; l < 32; ++l)
+    if (mask >> l & 1u) r = want_max ? std::max(r, emu_my_warp->slot[l]) : std::min(r, emu_my_warp->slot[l]);
+  emu_my_warp->bar.arrive_and_wait();
+  return r;
+}
+inline unsigned redux_max_u32(unsigned mask, unsigned v) { return emu_redux(mask, v, true); }
+inline unsigned redux_min_u32(unsigned mask, unsigned v) { return emu_redux(mask, v, false); }
+
+// bar.sync id, n: one reusable std::barrier per id, created by the first thread that arrives; reset for every CTA
+inline std::mutex emu_named_mutex;
+inline std::unique_ptr<std::barrier<>> emu_named_barriers[16];
+inline void named_bar_sync(unsigned id, unsigned n_threads) {
+  std::barrier<>* b;
+  {
+    std::lock_guard<std::mutex> lock(emu_named_mutex);
+    if (!emu_named_barriers[id]) emu_named_barriers[id].reset(new std::barrier<>((std::ptrdiff_t)n_threads));
+    b = emu_named_barriers[id].get();
+  }
+  b->arrive_and_wait();
+}
 
 struct emu_copy {
   void* dst;
@@ -37,6 +68,13 @@ inline std::mutex emu_async_mutex;
 inline std::map<unsigned, emu_mbarrier> emu_mbarriers;            // keyed by shared-memory byte offset
 inline thread_local std::vector<emu_copy> emu_pending_stores;     // bulk groups are per thread
 
+// a phase completes as soon as every expected arrival has happened and every expected byte has landed
+inline void emu_try_complete(emu_mbarrier& b) {
+  if (b.pending == 0 && b.tx == 0) {
+    b.phase ^= 1;
+    b.pending = b.count;
+  }
+}
 inline unsigned smem_u32(const void* p) {
   return (unsigned)((const char*)p - (const char*)emu_dynamic_smem);
 }
@@ -53,6 +91,13 @@ inline void mbar_expect_tx(unsigned bar, unsigned bytes) {      // arrive + expe
   emu_mbarrier& b = emu_mbarriers.at(bar);
   b.tx += bytes;
   b.pending -= 1;
+  emu_try_complete(b);   // (expect_tx(0): nothing to wait for)
+}
+inline void mbar_arrive(unsigned bar) {
+  std::lock_guard<std::mutex> lock(emu_async_mutex);
+  emu_mbarrier& b = emu_mbarriers.at(bar);
+  b.pending -= 1;
+  emu_try_complete(b);
 }
 inline void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
   if ((reinterpret_cast<uintptr_t>(smem_dst) | reinterpret_cast<uintptr_t>(gsrc) | bytes) & 15u) {
@@ -68,14 +113,14 @@ inline void mbar_wait(unsigned bar, unsigned parity) {
       std::lock_guard<std::mutex> lock(emu_async_mutex);
       emu_mbarrier& b = emu_mbarriers.at(bar);
       if ((unsigned)b.phase != parity) return;                  // the phase with this parity has completed
-      for (const emu_copy& c : b.queued) {                      // the queued copies land now
-        memcpy(c.dst, c.src, c.bytes);
-        b.tx -= c.bytes;
-      }
-      b.queued.clear();
-      if (b.pending == 0 && b.tx == 0) {
-        b.phase ^= 1;
-        b.pending = b.count;
+      if (!b.queued.empty()) {
+        for (const emu_copy& c : b.queued) {                    // the queued copies land now
+          memcpy(c.dst, c.src, c.bytes);
+          b.tx -= c.bytes;
+        }
+        b.queued.clear();
+        emu_try_complete(b);
+        if ((unsigned)b.phase != parity) return;
       }
     }
     std::this_thread::yield();
@@ -122,6 +167,12 @@ inline void emu_async_thread_exit() {
 
 // every emulated thread completes its outstanding asynchronous copies when its kernel body returns
 inline const bool emu_async_hook_installed = (emu_thread_exit_hook = emu_async_thread_exit, true);
+// named barriers and mbarriers belong to one CTA
+inline void emu_async_cta_start() {
+  for (auto& b : emu_named_barriers) b.reset();
+  emu_mbarriers.clear();
+}
+inline const bool emu_cta_hook_installed = (emu_cta_start_hook = emu_async_cta_start, true);
 
 // optimisation barrier: nothing to hide from on the host
 inline unsigned keep(unsigned v) { return v; }

@@ -171,6 +171,8 @@ inline unsigned __match_any_sync(unsigned, unsigned value) {
 
 // called by every emulated thread when its kernel body returns (ptx_emu.h flushes pending bulk stores there)
 inline void (*emu_thread_exit_hook)() = nullptr;
+// called once before the threads of every emulated CTA start (ptx_emu.h resets named barriers / mbarriers there)
+inline void (*emu_cta_start_hook)() = nullptr;
 
 // kernel<<<grid, block, smem, stream>>>(args...) -> emu_launch(grid, block, [&] { kernel(args...); })
 // (tests/emu/build_lib.py rewrites the launches of whole .cu files this way).  A thread whose body returns leaves the
@@ -208,6 +210,7 @@ void emu_launch(dim3 grid, dim3 block, F body, size_t smem_bytes = (size_t)-1) {
     for (unsigned bx = 0; bx < grid.x; ++bx) {
       std::barrier<> cta_bar(n_threads);
       emu_cta_barrier = &cta_bar;
+      if (emu_cta_start_hook) emu_cta_start_hook();
       std::vector<std::unique_ptr<emu_warp>> warps;
       for (int w = 0; w * 32 < n_threads; ++w) warps.emplace_back(new emu_warp(std::min(32, n_threads - w * 32)));
       for (auto& w : warps)

@@ -29,7 +29,7 @@ CONFIGS = dict(
 )
 
 
-def run(name, cfg, B, iters, flush, no_flush=False):
+def run(name, cfg, B, iters, flush, no_flush=False, only='all'):
     dev = 'cuda'
     M, C, h, w, H, W, O = (cfg[k] for k in ('M', 'C', 'h', 'w', 'H', 'W', 'O'))
     V, A = M, 8 * M + 7
@@ -56,13 +56,18 @@ def run(name, cfg, B, iters, flush, no_flush=False):
     up_post, up_cp = n(B, O, V), n(B, O)
 
     def once():
-        lp, ll = ops.TemplateMixtureLogProb.apply(templates, pose, presence, None, x, alpha, bg_value, bg_logit, None,
-                                                  None, (H, W))
-        if not no_flush:
-            flush.add_(1.0)
-        ll.sum().backward()
-        if not no_flush:
-            flush.add_(1.0)
+        if only in ('all', 'tmpl'):
+            lp, ll = ops.TemplateMixtureLogProb.apply(templates, pose, presence, None, x, alpha, bg_value, bg_logit, None,
+                                                      None, (H, W))
+            if not no_flush:
+                flush.add_(1.0)
+            ll.sum().backward()
+            if not no_flush:
+                flush.add_(1.0)
+        if only == 'tmpl':
+            for t in (templates, pose, presence, alpha, bg_value, bg_logit):
+                t.grad = None
+            return
         res = dict(zip(ops.CAPS_RETURNS, ops.CapsuleVoteLikelihood.apply(
             all_param, cpr_static, *biases, dummy, px, ppres, noise_caps, noise_vote, flags)))
         if not no_flush:
@@ -98,11 +103,12 @@ def main():
     ap.add_argument('--batches', default='1024,8192')
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--no-flush', action='store_true')
+    ap.add_argument('--only', default='all', choices=('all', 'caps', 'tmpl'))
     args = ap.parse_args()
     flush = torch.empty(128 * 1024 * 1024, device='cuda')    # 512 MB > 126 MB L2
     for name in args.configs.split(','):
         for B in (int(b) for b in args.batches.split(',')):
-            run(name, CONFIGS[name], B, args.iters, flush, args.no_flush)
+            run(name, CONFIGS[name], B, args.iters, flush, args.no_flush, args.only)
 
 
 if __name__ == '__main__':

@@ -73,6 +73,35 @@ __device__ __forceinline__ void pose_affine_fast(const float t[6], PoseAffine& o
   o.a[5] = o.ty;
 }
 
+// The same with MUFU sine / cosine: theta = 2 pi t, reduced exactly first (t - rint(t) is exact in fp32, |.| <= 1/2), so
+// the hardware approximation (absolute error about 5e-7 on [-pi, pi]) never sees a large argument.  7 instructions
+// against sincospif's ~25; used by the persistent capsule kernels (caps_ll3.cu).
+template <bool kSimilarity>
+__device__ __forceinline__ void pose_affine_mufu(const float t[6], PoseAffine& o) {
+  o.sx = sigmoid_fast(t[0]) + 1e-2f;
+  o.sy = sigmoid_fast(t[1]) + 1e-2f;
+  o.sh = tanh5_fast(t[3]);
+  o.tx = tanh5_fast(t[4]);
+  o.ty = tanh5_fast(t[5]);
+  const float th = (t[2] - rintf(t[2])) * kTwoPi;
+  o.s = sin_approx(th);
+  o.c = cos_approx(th);
+  if (kSimilarity) {
+    o.a[0] = o.sx * o.c;
+    o.a[1] = -o.sx * o.s;
+    o.a[3] = o.sx * o.s;
+    o.a[4] = o.sx * o.c;
+  } else {
+    const float shsy = o.sh * o.sy;
+    o.a[0] = fmaf(shsy, o.s, o.sx * o.c);
+    o.a[1] = fmaf(shsy, o.c, -o.sx * o.s);
+    o.a[3] = o.sy * o.s;
+    o.a[4] = o.sy * o.c;
+  }
+  o.a[2] = o.tx;
+  o.a[5] = o.ty;
+}
+
 // vote = [r00 r01 r02; r10 r11 r12; 0 0 1] . [a00 a01 a02; a10 a11 a12; 0 0 1], rows 0-1 (object_decoder.py:185-191,:413)
 __device__ __forceinline__ void compose_vote(const float* r, const float* A_, float* vt) {
   vt[0] = r[0] * A_[0] + r[1] * A_[3];
@@ -117,6 +146,10 @@ __device__ __forceinline__ void bulk_run_edges_out(float* g, const float* base, 
 __device__ __forceinline__ int fast_div(int p, float inv) { return (int)(((float)p + 0.5f) * inv); }
 
 bool caps_force_v1();
+bool caps_force_v2();   // development switch: skip caps_ll3.cu (A/B timing)
+
+// Persistent, warp-specialised fast path (caps_ll3.cu); same contract as caps2_*.
+int caps3_fwd(const scae_caps_args* a, const scae_caps_outputs* out, cudaStream_t stream, bool* handled);
 
 // Fast-path entry points (caps_ll2.cu).  *handled = false means "shape or request not covered, use the general path".
 int caps2_fwd(const scae_caps_args* a, const scae_caps_outputs* out, cudaStream_t stream, bool* handled);

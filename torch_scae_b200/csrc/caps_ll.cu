@@ -665,8 +665,13 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_fwd(const sca
   if (rc != SCAE_OK) return rc;
   SCAE_REQUIRE(out != nullptr, SCAE_EINVAL, "caps fwd: outputs is NULL");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!caps_force_v1()) {   // fast path (caps_ll2.cu) when the image's working set fits in shared memory
+  if (!caps_force_v1()) {   // fast paths when the image's working set fits in shared memory: caps_ll3.cu, then caps_ll2.cu
     bool handled = false;
+    if (!caps_force_v2()) {
+      rc = caps3_fwd(a, out, stream, &handled);
+      if (handled) note_fast_path();
+      if (rc != SCAE_OK || handled) return rc;
+    }
     rc = caps2_fwd(a, out, stream, &handled);
     if (handled) note_fast_path();
     if (rc != SCAE_OK || handled) return rc;

@@ -825,6 +825,11 @@ bool caps_force_v1() {
   return e != nullptr && strcmp(e, "v1") == 0;
 }
 
+bool caps_force_v2() {
+  const char* e = getenv("SCAE_CAPS_IMPL");
+  return e != nullptr && strcmp(e, "v2") == 0;
+}
+
 // Shared-memory carve-out hint: just enough for `ctas` resident CTAs (each also pays 1 KB of system-reserved shared
 // memory), so that what is left of the 256 KB unified array serves as L1 for the batch-shared parameters.
 static int carveout_percent(size_t smem_bytes, int ctas) {

@@ -25,6 +25,35 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// sin / cos of an angle in radians, |x| <= pi for full accuracy (MUFU.SIN / MUFU.COS after the hardware's 1/2pi scaling)
+__device__ __forceinline__ float sin_approx(float x) {
+  float y;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float cos_approx(float x) {
+  float y;
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---- warp-level integer reductions over the lanes of `mask` (REDUX); every lane of `mask` must call with that mask ----
+__device__ __forceinline__ unsigned redux_max_u32(unsigned mask, unsigned v) {
+  unsigned r;
+  asm volatile("redux.sync.max.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(mask));
+  return r;
+}
+__device__ __forceinline__ unsigned redux_min_u32(unsigned mask, unsigned v) {
+  unsigned r;
+  asm volatile("redux.sync.min.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(mask));
+  return r;
+}
+
+// ---- named barrier among `n_threads` (a multiple of 32) threads of the CTA; id 0 is __syncthreads' ---------------------
+__device__ __forceinline__ void named_bar_sync(unsigned id, unsigned n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+
 // ---- mbarrier + bulk (TMA) copies, 1-D --------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -36,6 +65,10 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// plain arrival (release at CTA scope): counts one of the barrier's expected arrivals
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   unsigned done;
