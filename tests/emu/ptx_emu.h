@@ -78,6 +78,12 @@ inline void emu_try_complete(emu_mbarrier& b) {
 inline unsigned smem_u32(const void* p) {
   return (unsigned)((const char*)p - (const char*)emu_dynamic_smem);
 }
+// shared memory by 32-bit address = byte offset into the emulated dynamic shared memory
+inline float lds_f32(unsigned addr) { return *reinterpret_cast<const float*>((const char*)emu_dynamic_smem + addr); }
+inline unsigned lds_u32(unsigned addr) { return *reinterpret_cast<const unsigned*>((const char*)emu_dynamic_smem + addr); }
+inline float4 lds_f32x4(unsigned addr) { return *reinterpret_cast<const float4*>((const char*)emu_dynamic_smem + addr); }
+inline void sts_f32(unsigned addr, float v) { *reinterpret_cast<float*>((char*)emu_dynamic_smem + addr) = v; }
+inline void sts_u32(unsigned addr, unsigned v) { *reinterpret_cast<unsigned*>((char*)emu_dynamic_smem + addr) = v; }
 inline void mbar_init(unsigned bar, unsigned count) {
   std::lock_guard<std::mutex> lock(emu_async_mutex);
   emu_mbarrier& b = emu_mbarriers[bar];
@@ -125,6 +131,20 @@ inline void mbar_wait(unsigned bar, unsigned parity) {
     }
     std::this_thread::yield();
   }
+}
+inline bool mbar_test(unsigned bar, unsigned parity) {
+  std::lock_guard<std::mutex> lock(emu_async_mutex);
+  emu_mbarrier& b = emu_mbarriers.at(bar);
+  if ((unsigned)b.phase != parity) return true;
+  if (!b.queued.empty()) {                                      // like a wait, a test lets the queued copies land
+    for (const emu_copy& c : b.queued) {
+      memcpy(c.dst, c.src, c.bytes);
+      b.tx -= c.bytes;
+    }
+    b.queued.clear();
+    emu_try_complete(b);
+  }
+  return (unsigned)b.phase != parity;
 }
 inline void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
   if ((reinterpret_cast<uintptr_t>(gdst) | reinterpret_cast<uintptr_t>(smem_src) | bytes) & 15u) {
@@ -177,5 +197,7 @@ inline const bool emu_cta_hook_installed = (emu_cta_start_hook = emu_async_cta_s
 // optimisation barrier: nothing to hide from on the host
 inline unsigned keep(unsigned v) { return v; }
 inline float keep(float v) { return v; }
+inline int keep(int v) { return v; }
+inline size_t keep(size_t v) { return v; }
 
 }  // namespace scae

@@ -54,6 +54,30 @@ __device__ __forceinline__ void named_bar_sync(unsigned id, unsigned n_threads) 
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
+// ---- shared memory by 32-bit address (what smem_u32 returns): the persistent capsule kernels do their own address
+// arithmetic so that a pair's accesses are one base register plus immediates -------------------------------------------
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(unsigned addr) {   // 16-byte aligned
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // ---- mbarrier + bulk (TMA) copies, 1-D --------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -79,6 +103,16 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
+}
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 // global -> shared, completion counted in bytes on `bar`; dst, src and bytes multiples of 16
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned bar) {
@@ -117,6 +151,14 @@ __device__ __forceinline__ unsigned keep(unsigned v) {
 }
 __device__ __forceinline__ float keep(float v) {
   asm volatile("" : "+f"(v));
+  return v;
+}
+__device__ __forceinline__ int keep(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ size_t keep(size_t v) {
+  asm volatile("" : "+l"(v));
   return v;
 }
 
