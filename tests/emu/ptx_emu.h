@@ -158,6 +158,7 @@ inline void bulk_wait_read_all() {
   for (const emu_copy& c : emu_pending_stores) memcpy(c.dst, c.src, c.bytes);
   emu_pending_stores.clear();
 }
+inline void bulk_wait_all() { bulk_wait_read_all(); }
 inline void emu_flush_bulk_stores_at_exit() { bulk_wait_read_all(); }
 
 // cp.async: 4-byte copies queued per thread in groups; a group lands when cp_async_wait<N> leaves at most N younger

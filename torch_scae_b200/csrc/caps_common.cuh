@@ -150,6 +150,10 @@ bool caps_force_v2();   // development switch: skip caps_ll3.cu (A/B timing)
 
 // Persistent, warp-specialised fast path (caps_ll3.cu); same contract as caps2_*.
 int caps3_fwd(const scae_caps_args* a, const scae_caps_outputs* out, cudaStream_t stream, bool* handled);
+int caps3_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_caps_upstream* up, float* g_all_param,
+              float* g_shared, float* g_dummy_vote, float* g_x, float* g_presence, void* workspace,
+              size_t workspace_bytes, cudaStream_t stream, bool* handled);
+size_t caps3_bwd_workspace_bytes(const scae_caps_args* a);
 
 // Fast-path entry points (caps_ll2.cu).  *handled = false means "shape or request not covered, use the general path".
 int caps2_fwd(const scae_caps_args* a, const scae_caps_outputs* out, cudaStream_t stream, bool* handled);

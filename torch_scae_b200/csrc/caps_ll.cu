@@ -694,7 +694,8 @@ extern "C" __attribute__((visibility("default"))) size_t scae_caps_ll_bwd_worksp
   if (a == nullptr || a->B <= 0 || a->O <= 0 || a->V <= 0) return 0;
   const size_t n = (size_t)a->O * (8 * a->V + 7);
   const size_t general = (caps_split(a->B) * n + (size_t)a->B * a->V * 6) * sizeof(float);
-  const size_t fast = caps2_bwd_workspace_bytes(a);
+  const size_t fast = caps2_bwd_workspace_bytes(a) > caps3_bwd_workspace_bytes(a) ? caps2_bwd_workspace_bytes(a)
+                                                                                 : caps3_bwd_workspace_bytes(a);
   return general > fast ? general : fast;
 }
 
@@ -715,6 +716,12 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_bwd(const sca
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!caps_force_v1()) {   // fast path (caps_ll2.cu): training-step upstream set, working set fits in shared memory
     bool handled = false;
+    if (!caps_force_v2()) {
+      rc = caps3_bwd(a, saved, up, g_all_param, g_shared, g_dummy_vote, g_x, g_presence, workspace, workspace_bytes, stream,
+                     &handled);
+      if (handled) note_fast_path();
+      if (rc != SCAE_OK || handled) return rc;
+    }
     rc = caps2_bwd(a, saved, up, g_all_param, g_shared, g_dummy_vote, g_x, g_presence, workspace, workspace_bytes, stream,
                    &handled);
     if (handled) note_fast_path();

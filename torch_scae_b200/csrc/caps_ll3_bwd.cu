@@ -1,0 +1,625 @@
+// Hot path 2 (sm_100a), persistent backward kernel of the capsule part-pose mixture likelihood (see caps_ll3.cu for the
+// forward and the design notes; reference object_decoder.py:160-236, :257-372; formulas: oracle/manual_backward.py::
+// capsule_forward_backward, transcribed from caps_ll2.cu).
+//
+// One persistent CTA per SM, 20 warps (96 registers), every thread keeps the same (object group k, part v) for all its
+// images: thread t = k V + v owns the pairs t, t + T, ... (NP of them).  Per image:
+//
+//   main pass    per pair: recompute the forward (MUFU forms), the pair's gradients; the gradient row is written IN PLACE
+//                over the staged all_param block (MLP-ReLU mask and deformation regulariser applied) and leaves through
+//                ONE bulk store; the 7 per-object sums over the parts go to a [7][P] tile; the batch sums that become the
+//                gradients of cpr_static / bias_vote / bias_scale accumulate in REGISTERS (the thread sees the same
+//                pairs in every image);
+//   pre-pass     of the NEXT image (its stage has landed): the thread's share of S[v] = sum_o posterior * upstream, so
+//                that the image needs only one barrier;
+//   barrier      the image's only one (named, all threads);
+//   phase B      two threads per (object, slot) sum the [7][P] tile; warp 0 turns the PREVIOUS image's sums into the 7
+//                capsule-level gradients (transform backward; one lane per object) and writes them straight to global
+//                memory after that image's bulk store has completed; lane 0 issues this image's bulk store.
+//
+// The last warp stages: bulk copies (TMA) of every per-image input into a ring of S stages and the per-object tile of
+// the next image (capsule transform with its intermediates for the backward, capsule presence).
+//
+// Deterministic: fixed summation orders everywhere; the per-CTA batch sums are reduced by launch_reduce_rows.
+#include <stdlib.h>
+#include <string.h>
+
+#include "caps_common.cuh"
+
+namespace scae {
+
+constexpr int kB3MaxStages = 4;
+constexpr int kB3Save = 12;    // floats per object kept for the capsule-level backward
+constexpr int kB3SaveBufs = 4; // image j's tile is written in iteration j-1 and read in iteration j+1
+constexpr unsigned kB3Bar = 1;
+
+__host__ __device__ inline int b3_round4(int n) { return (n + 3) & ~3; }
+
+struct Caps3BwdLayout {
+  int S, G, NP, T, Tpad;
+  int stage0, stage_stride;                                     // floats
+  int prm, post, gpost, nz, xs, ps, lse, nc, gcp, carg, glc, R, OS;   // offsets inside a stage
+  int RED7, SPART, OBJ7, OSAVE, BIAS, OBJSUM, CST, total;       // CTA-wide tiles
+  // byte strides / offsets the hot loop uses straight from the constant bank
+  unsigned strideA4, V4, T4, P4, strideR, strideO, post4, gpost4, nz4;
+};
+
+static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_upstream* up, int G, int NP, int S) {
+  const int O = a->O, V = a->V, A = 8 * V + 7, P = O * V;
+  Caps3BwdLayout L;
+  L.S = S, L.G = G, L.NP = NP, L.T = G * V, L.Tpad = (L.T + 31) & ~31;
+  int at = 32;   // [0, 32) floats: mbarriers full[4], bdone[2]
+  auto take = [&](int n) {
+    const int here = at;
+    at += b3_round4(n);
+    return here;
+  };
+  L.stage0 = at;
+  L.prm = take(O * A + 4) - L.stage0;
+  L.post = take(P + 4) - L.stage0;
+  L.gpost = take(up->g_posterior_mixing_prob ? P + 4 : 0) - L.stage0;
+  L.nz = take(a->noise_vote ? P + 4 : 0) - L.stage0;
+  L.xs = take(V * 6 + 4) - L.stage0;
+  L.ps = take(a->presence ? V + 4 : 0) - L.stage0;
+  L.lse = take(V + 4) - L.stage0;
+  L.nc = take(a->noise_caps ? O + 4 : 0) - L.stage0;
+  L.gcp = take(up->g_caps_presence ? O + 4 : 0) - L.stage0;
+  L.carg = take(up->g_caps_presence ? O + 4 : 0) - L.stage0;
+  L.glc = take(up->g_presence_logit_per_caps ? O + 4 : 0) - L.stage0;
+  L.R = take(O * 8) - L.stage0;
+  L.OS = take(O * 4) - L.stage0;
+  L.stage_stride = at - L.stage0;
+  at = L.stage0 + S * L.stage_stride;
+  L.RED7 = take(7 * P);
+  L.SPART = take(2 * L.T);
+  L.OBJ7 = take(2 * O * 8);
+  L.OSAVE = take(kB3SaveBufs * O * kB3Save);
+  L.BIAS = take(O * 8);
+  L.OBJSUM = take(O * 8);
+  L.CST = take(8 * L.T * NP);   // [NP][8][T]: cpr_static (6), bias_vote, bias_scale + 0.5 of the thread's pairs
+  L.total = at;
+  L.strideA4 = 4u * (unsigned)(G * A), L.V4 = 4u * (unsigned)V, L.T4 = 4u * (unsigned)L.T, L.P4 = 4u * (unsigned)P;
+  L.strideR = 32u * (unsigned)G, L.strideO = 16u * (unsigned)G;
+  L.post4 = 4u * (unsigned)L.post, L.gpost4 = 4u * (unsigned)L.gpost, L.nz4 = 4u * (unsigned)L.nz;
+  return L;
+}
+
+__device__ __forceinline__ unsigned b3_full(unsigned bar0, int s) { return bar0 + 8u * (unsigned)s; }
+__device__ __forceinline__ unsigned b3_bdone(unsigned bar0, int p) { return bar0 + 8u * (unsigned)(kB3MaxStages + p); }
+
+struct Caps3BwdOut {
+  float* g_all_param;   // [B,O,A] final: ReLU mask and regulariser applied
+  float* g_presence;    // [B,V] nullable
+  float* partials;      // [grid][O*A] per-CTA batch sums of the pre-activation gradient
+};
+
+// ---- staging (one warp): lane r < 11 owns one contiguous per-image input --------------------------------------------------
+struct B3Run {
+  const float* g;
+  float* base;
+  int n;
+};
+
+__device__ __forceinline__ void caps3_bwd_issue(const scae_caps_args& a, const scae_caps_saved& sv,
+                                                const scae_caps_upstream& up, const Caps3BwdLayout& L, float* smem,
+                                                unsigned bar0, int s, int b, int lane) {
+  const int O = a.O, V = a.V, A = 8 * V + 7, P = O * V;
+  float* st = smem + L.stage0 + s * L.stage_stride;
+  B3Run run = {nullptr, nullptr, 0};
+  switch (lane) {
+    case 0: run = {a.all_param + (size_t)b * O * A, st + L.prm, O * A}; break;
+    case 1: run = {sv.posterior_mixing_prob + (size_t)b * P, st + L.post, P}; break;
+    case 2: if (up.g_posterior_mixing_prob) run = {up.g_posterior_mixing_prob + (size_t)b * P, st + L.gpost, P}; break;
+    case 3: if (a.noise_vote) run = {a.noise_vote + (size_t)b * P, st + L.nz, P}; break;
+    case 4: run = {a.x + (size_t)b * V * 6, st + L.xs, V * 6}; break;
+    case 5: if (a.presence) run = {a.presence + (size_t)b * V, st + L.ps, V}; break;
+    case 6: run = {sv.log_prob_per_point + (size_t)b * V, st + L.lse, V}; break;
+    case 7: if (a.noise_caps) run = {a.noise_caps + (size_t)b * O, st + L.nc, O}; break;
+    case 8: if (up.g_caps_presence) run = {up.g_caps_presence + (size_t)b * O, st + L.gcp, O}; break;
+    case 9:
+      if (up.g_caps_presence) run = {reinterpret_cast<const float*>(sv.caps_presence_arg) + (size_t)b * O, st + L.carg, O};
+      break;
+    case 10: if (up.g_presence_logit_per_caps) run = {up.g_presence_logit_per_caps + (size_t)b * O, st + L.glc, O}; break;
+    default: break;
+  }
+  BulkRun br = {0, 0, 0, 0};
+  if (run.n) br = bulk_run(run.g, run.n);
+  unsigned bytes = 4u * (unsigned)br.body;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+  if (lane == 0) mbar_expect_tx(b3_full(bar0, s), bytes);
+  __syncwarp();
+  if (br.body) bulk_g2s(run.base + br.off + br.head, run.g + br.head, 4u * (unsigned)br.body, b3_full(bar0, s));
+  if (run.n) {   // the run's (at most 3 + 3) edge floats
+    for (int q = 0; q < br.head; ++q) run.base[br.off + q] = __ldg(run.g + q);
+    for (int q = 0; q < br.tail; ++q) run.base[br.off + br.head + br.body + q] = __ldg(run.g + br.head + br.body + q);
+  }
+}
+
+// per-object work of image b in stage s (one warp, lane = object):
+//   R[o]     = {capsule -> viewer affine (6), capsule presence probability, -}
+//   OS[o]    = {upstream gradient of caps_presence, its arg-max part (int bits), -, -}
+//   SAVE[o]  = {sx, sy, sh, tx, ty, cos, sin, presence probability, upstream gradient of the presence logit,
+//               bit c: raw parameter 6V + c is positive (the MLP's ReLU was active), -, -}
+template <bool kSim>
+__device__ __forceinline__ void caps3_bwd_object_tile(const scae_caps_args& a, const scae_caps_upstream& up,
+                                                      const Caps3BwdLayout& L, float* smem, int s, int b, int img,
+                                                      int lane) {
+  const int O = a.O, V = a.V, A = 8 * V + 7;
+  float* st = smem + L.stage0 + s * L.stage_stride;
+  const float* prm = st + L.prm + bulk_run(a.all_param + (size_t)b * O * A, O * A).off;
+  const float* nc = a.noise_caps ? st + L.nc + bulk_run(a.noise_caps + (size_t)b * O, O).off : nullptr;
+  const float* gcp = up.g_caps_presence ? st + L.gcp + bulk_run(up.g_caps_presence + (size_t)b * O, O).off : nullptr;
+  const float* carg = up.g_caps_presence ? st + L.carg + bulk_run(up.g_caps_presence + (size_t)b * O, O).off : nullptr;
+  const float* glc = up.g_presence_logit_per_caps ? st + L.glc + bulk_run(up.g_presence_logit_per_caps + (size_t)b * O, O).off : nullptr;
+  const float* BIAS = smem + L.BIAS;
+  float* R = st + L.R;
+  float* OS = st + L.OS;
+  float* SAVE = smem + L.OSAVE + (img % kB3SaveBufs) * O * kB3Save;
+  for (int oo = lane; oo < O; oo += 32) {
+    const float* row = prm + oo * A + 6 * V;
+    const float4 b0 = *reinterpret_cast<const float4*>(BIAS + oo * 8), b1 = *reinterpret_cast<const float4*>(BIAS + oo * 8 + 4);
+    float raw[7];
+#pragma unroll
+    for (int p = 0; p < 7; ++p) raw[p] = row[p];
+    const float t[6] = {raw[0] + b0.x, raw[1] + b0.y, raw[2] + b0.z, raw[3] + b0.w, raw[4] + b1.x, raw[5] + b1.y};
+    PoseAffine r;
+    pose_affine_mufu<kSim>(t, r);
+    float lc = raw[6] + b1.z;
+    if (nc) lc += nc[oo];
+    const float pc = sigmoid_fast(lc);
+    float4* dst = reinterpret_cast<float4*>(R + oo * 8);
+    dst[0] = make_float4(r.a[0], r.a[1], r.a[2], r.a[3]);
+    dst[1] = make_float4(r.a[4], r.a[5], pc, 0.0f);
+    *reinterpret_cast<float4*>(OS + oo * 4) = make_float4(gcp ? gcp[oo] : 0.0f, gcp ? carg[oo] : __int_as_float(-1), 0.0f, 0.0f);
+    unsigned mask = 0;
+#pragma unroll
+    for (int p = 0; p < 7; ++p) mask |= raw[p] > 0.0f ? 1u << p : 0u;
+    float4* sd = reinterpret_cast<float4*>(SAVE + oo * kB3Save);
+    sd[0] = make_float4(r.sx, r.sy, r.sh, r.tx);
+    sd[1] = make_float4(r.ty, r.c, r.s, pc);
+    sd[2] = make_float4(glc ? glc[oo] : 0.0f, __uint_as_float(mask), 0.0f, 0.0f);
+  }
+}
+
+template <bool kSim, int NP, int kMaxT, int kMinB>
+__global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps_args a, const scae_caps_saved sv,
+                                                                 const scae_caps_upstream up, const Caps3BwdOut out,
+                                                                 const Caps3BwdLayout L) {
+  SCAE_DYNAMIC_SMEM(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int O = a.O, V = a.V, A = 8 * V + 7, P = O * V;
+  const int S = L.S, G = L.G, T = L.T, Tpad = L.Tpad;
+  const unsigned bar0 = smem_u32(smem);
+  const int n_mine = ((int)blockIdx.x < a.B) ? (a.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const bool deform = (a.flags & SCAE_CAPS_ALLOW_DEFORM) != 0;
+  const bool learn = (a.flags & SCAE_CAPS_LEARN_VOTE_SCALE) != 0;
+  const bool relu = (a.flags & SCAE_CAPS_RELU_GRAD) != 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(b3_full(bar0, s), 1);
+    }
+    mbar_init(b3_bdone(bar0, 0), (unsigned)Tpad);
+    mbar_init(b3_bdone(bar0, 1), (unsigned)Tpad);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < O * 8; i += Tpad) {
+    const int oo = i >> 3, c = i & 7;
+    smem[L.BIAS + i] = c < 6 ? __ldg(a.bias_cvr + oo * 6 + c) : c == 6 ? __ldg(a.bias_caps + oo) : 0.0f;
+    smem[L.OBJSUM + i] = 0.0f;
+  }
+  __syncthreads();
+  const bool stager = warp == (Tpad >> 5) - 1;
+  if (stager && n_mine > 0) {
+    for (int i = 0; i < S && i < n_mine; ++i) caps3_bwd_issue(a, sv, up, L, smem, bar0, i, blockIdx.x + i * gridDim.x, lane);
+    mbar_wait(b3_full(bar0, 0), 0);
+    __syncwarp();
+    caps3_bwd_object_tile<kSim>(a, up, L, smem, 0, blockIdx.x, 0, lane);
+  }
+
+  // ---- per-thread constants ----------------------------------------------------------------------------------------------
+  const bool active = tid < T;
+  const float inv_V = 1.0f / (float)V;
+  const int k = keep(active ? fast_div(tid, inv_V) : -1);
+  const int v = keep(active ? tid - k * V : 0);
+  float acc[NP][8];   // batch sums of the pre-activation gradient: 6 cpr slots, vote logit, scale
+  unsigned vmask = 0;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int oj = k + G * j;
+    const bool ok = active && oj < O;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.0f;
+    if (ok) {
+      vmask |= 1u << j;
+      // the pair's batch-shared parameters: thread-private shared-memory slots [j][c][tid] (conflict-free)
+      const int p = oj * V + v;
+      float* cs = smem + L.CST + j * 8 * T + tid;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) cs[c * T] = __ldg(a.cpr_static + (size_t)p * 6 + c);
+      cs[6 * T] = __ldg(a.bias_vote + p);
+      cs[7 * T] = __ldg(a.bias_scale + p) + 0.5f;
+    }
+  }
+  vmask = keep(vmask);
+  const unsigned d_off = keep((unsigned)(4 * (active ? k * A + 6 * v : 0)));
+  const unsigned l_off = keep((unsigned)(4 * (active ? k * A + 6 * V + 7 + v : 0)));
+  const unsigned strideA = L.strideA4, V4 = L.V4, T4 = L.T4, P4 = L.P4, strideR = L.strideR, strideO = L.strideO;
+  const unsigned cst_addr = keep(bar0 + 4u * (unsigned)(L.CST + tid));
+  const unsigned r_off = keep((unsigned)(4 * (L.R + (active ? k * 8 : 0))));
+  const unsigned os_off = keep((unsigned)(4 * (L.OS + (active ? k * 4 : 0))));
+  const unsigned red_addr = keep(bar0 + 4u * (unsigned)(L.RED7 + tid));
+  const unsigned stage_bytes = (unsigned)(4 * L.stage_stride);
+  const unsigned OAmod = (unsigned)(O * A) & 3u, Pmod = (unsigned)P & 3u, V6mod = (unsigned)(V * 6) & 3u, Vmod = (unsigned)V & 3u;
+  const bool have_gpost = up.g_posterior_mixing_prob != nullptr;
+  __syncthreads();   // the first image's object tile (written by the stager above) is visible
+
+  // the thread's share of S[v] = sum_o posterior * upstream for image `img` in stage `sn` -> SPART[img & 1]
+  auto pre_pass = [&](int img, int sn, unsigned par_n) {
+    const int bn = blockIdx.x + img * gridDim.x;
+    mbar_wait(b3_full(bar0, sn), par_n);
+    float part = 0.0f;
+    if (have_gpost) {
+      const unsigned stn = bar0 + 4u * (unsigned)L.stage0 + (unsigned)sn * stage_bytes;
+      const unsigned po = 4u * (((unsigned)bn * Pmod) & 3u) + 4u * (unsigned)tid;
+#pragma unroll
+      for (int j = 0; j < NP; ++j)
+        if (vmask >> j & 1u)
+          part = fmaf(lds_f32(stn + L.post4 + po + (unsigned)j * T4),
+                      lds_f32(stn + L.gpost4 + po + (unsigned)j * T4), part);
+    }
+    if (active) smem[L.SPART + (img & 1) * T + tid] = part;
+  };
+  if (n_mine > 0) pre_pass(0, 0, 0);
+  __syncthreads();
+
+  // the capsule-level gradients of image `img` (warp 0, one lane per object) from the sums phase B left in OBJ7
+  auto object_chain = [&](int img) {
+    const int bi = blockIdx.x + img * gridDim.x;
+    const float* G7 = smem + L.OBJ7 + (img & 1) * O * 8;
+    const float* SAVE = smem + L.OSAVE + (img % kB3SaveBufs) * O * kB3Save;
+    float* OBJSUM = smem + L.OBJSUM;
+    for (int oo = lane; oo < O; oo += 32) {
+      const float4 g0 = *reinterpret_cast<const float4*>(G7 + oo * 8), g1 = *reinterpret_cast<const float4*>(G7 + oo * 8 + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(SAVE + oo * kB3Save);
+      const float4 s1 = *reinterpret_cast<const float4*>(SAVE + oo * kB3Save + 4);
+      const float4 s2 = *reinterpret_cast<const float4*>(SAVE + oo * kB3Save + 8);
+      PoseAffine r;
+      r.sx = s0.x, r.sy = s0.y, r.sh = s0.z, r.tx = s0.w, r.ty = s1.x, r.c = s1.y, r.s = s1.z;
+      const float pc = s1.w;
+      const float g7[6] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y};
+      float gt[7];
+      pose_affine_bwd<kSim>(g7, r, gt);
+      gt[6] = g1.z * pc * (1.0f - pc) + s2.x;
+      const unsigned mask = __float_as_uint(s2.y);
+      float* grow = out.g_all_param + ((size_t)bi * O + oo) * A + 6 * V;
+#pragma unroll
+      for (int p = 0; p < 7; ++p) {
+        OBJSUM[oo * 8 + p] += gt[p];
+        grow[p] = (relu && !(mask >> p & 1u)) ? 0.0f : gt[p];
+      }
+    }
+  };
+
+  int s = 0;
+  unsigned parity = 0;
+  for (int i = 0; i < n_mine; ++i) {
+    const int b = keep((int)(blockIdx.x + i * gridDim.x));
+    const int par = i & 1;
+    const unsigned st = keep(bar0 + 4u * (unsigned)L.stage0 + (unsigned)s * stage_bytes);
+    const unsigned prm = keep(st + 4u * (unsigned)L.prm + 4u * (((unsigned)b * OAmod) & 3u));
+    const unsigned pbase = keep(4u * (((unsigned)b * Pmod) & 3u) + 4u * (unsigned)tid);   // the thread's first pair in a [P] run
+    const int sn = s + 1 == S ? 0 : s + 1;
+    const unsigned par_n = s + 1 == S ? parity ^ 1u : parity;
+
+    // ---- per-part values -------------------------------------------------------------------------------------------------
+    float xv[6];
+    {
+      const unsigned xa = st + 4u * (unsigned)L.xs + 4u * (((unsigned)b * V6mod) & 3u) + 24u * (unsigned)v;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) xv[c] = lds_f32(xa + 4 * c);
+    }
+    const float pres = a.presence ? lds_f32(st + 4u * (unsigned)L.ps + 4u * (((unsigned)b * Vmod) & 3u) + 4u * (unsigned)v) : 1.0f;
+    const float gll = up.g_ll_per_example ? __ldg(up.g_ll_per_example + b) : 0.0f;
+    const float greg = up.g_reg_per_example ? __ldg(up.g_reg_per_example + b) : 0.0f;
+    const float gllp = gll * pres;
+    float Sv = 0.0f;   // S[v]: the G partials the pre-pass left (same order in every thread of the part)
+    {
+      const float* sp = smem + L.SPART + par * T + v;
+      for (int kk = 0; kk < G; ++kk) Sv += sp[kk * V];
+    }
+    if (k == 0 && active && out.g_presence)
+      out.g_presence[(size_t)b * V + v] = gll * lds_f32(st + 4u * (unsigned)L.lse + 4u * (((unsigned)b * Vmod) & 3u) + 4u * (unsigned)v);
+    // the [7][P] tile is single-buffered: every thread must have finished the previous image's phase B
+    if (i > 0) mbar_wait(b3_bdone(bar0, par ^ 1), (unsigned)(((i - 1) >> 1) & 1));
+
+    // ---- main pass: the thread's pairs -------------------------------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (!(vmask >> j & 1u)) continue;
+      const unsigned da = prm + d_off + (unsigned)j * strideA;   // row[6 v + c]
+      const unsigned la = prm + l_off + (unsigned)j * strideA;   // row[6 V + 7 + v]; the scale slot 4 V bytes further
+      const size_t e = (size_t)b * P + tid + (size_t)j * T;      // the pair in a (B,O,V) tensor
+      const unsigned ca = cst_addr + (unsigned)j * 8u * T4;
+      float raw[6], t[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        raw[c] = lds_f32(da + 4 * c);
+        t[c] = (deform ? raw[c] : 0.0f) + lds_f32(ca + (unsigned)c * T4);
+      }
+      PoseAffine pa;
+      pose_affine_mufu<kSim>(t, pa);
+      const float4 r0 = lds_f32x4(st + r_off + (unsigned)j * strideR), r1 = lds_f32x4(st + r_off + (unsigned)j * strideR + 16);
+      const float4 os = lds_f32x4(st + os_off + (unsigned)j * strideO);
+      const float r[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+      const float pc = r1.z;
+      float vt[6];
+      compose_vote(r, pa.a, vt);
+      const float raw_lv = lds_f32(la), raw_u = lds_f32(la + V4);
+      float lv = raw_lv + lds_f32(ca + 6u * T4);
+      if (a.noise_vote) lv += lds_f32(st + L.nz4 + pbase + (unsigned)j * T4);
+      const float pv = sigmoid_fast(lv);
+      const float vp = pc * pv;
+      const float u05 = raw_u + lds_f32(ca + 7u * T4);
+      float sc = 1.0f, dsc = 0.0f;   // scale and d scale / d u
+      if (learn) {
+        const float z = ex2_approx(-fabsf(u05) * kLog2eF);   // softplus(x) = max(x, 0) + log1p(e^-|x|); its slope = sigmoid(x)
+        sc = fmaxf(u05, 0.0f) + log1p_unit(z) + 1e-2f;
+        const float rz = rcp_approx(1.0f + z);
+        dsc = u05 >= 0.0f ? rz : z * rz;
+      }
+      float diff[6], q = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        diff[c] = xv[c] - vt[c];
+        q = fmaf(diff[c], diff[c], q);
+      }
+      const float pst = lds_f32(st + L.post4 + pbase + (unsigned)j * T4);
+      const float h = have_gpost ? lds_f32(st + L.gpost4 + pbase + (unsigned)j * T4) : 0.0f;
+      const float g_pl = pst * (h - Sv) + gllp * pst;
+      float g_vp = 0.0f;
+      if (up.g_vote_presence) g_vp += __ldg(up.g_vote_presence + e);
+      if (__float_as_int(os.y) == v) g_vp += os.x;
+      float g_ml = g_pl;
+      if (up.g_mixing_logit) g_ml += __ldg(up.g_mixing_logit + (size_t)b * (P + V) + tid + (size_t)j * T);
+      if (!(vp < kLogSafeEps)) g_vp = fmaf(g_ml, rcp_approx(vp), g_vp);
+      const float inv_sc = rcp_approx(sc);
+      const float inv2 = inv_sc * inv_sc;
+      const float coef = g_pl * inv2;
+      float gv[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        gv[c] = coef * diff[c];
+        if (up.g_vote) gv[c] += __ldg(up.g_vote + e * 6 + c);
+      }
+      float g_sc = g_pl * inv_sc * fmaf(q, inv2, -6.0f);
+      if (up.g_scale) g_sc += __ldg(up.g_scale + e);
+      const float g_u = g_sc * dsc;
+      float g_lv = g_vp * vp * (1.0f - pv);
+      if (up.g_presence_logit_per_vote) g_lv += __ldg(up.g_presence_logit_per_vote + e);
+      // vote = R . A: gradient w.r.t. A (-> this pair's cpr parameters) and w.r.t. R (-> summed over the parts in phase B)
+      const float* A_ = pa.a;
+      float ga[6];
+      ga[0] = r[0] * gv[0] + r[3] * gv[3];
+      ga[1] = r[0] * gv[1] + r[3] * gv[4];
+      ga[2] = r[0] * gv[2] + r[3] * gv[5];
+      ga[3] = r[1] * gv[0] + r[4] * gv[3];
+      ga[4] = r[1] * gv[1] + r[4] * gv[4];
+      ga[5] = r[1] * gv[2] + r[4] * gv[5];
+      const unsigned ra = red_addr + (unsigned)j * T4;
+      sts_f32(ra + 0 * P4, gv[0] * A_[0] + gv[1] * A_[1] + gv[2] * A_[2]);
+      sts_f32(ra + 1 * P4, gv[0] * A_[3] + gv[1] * A_[4] + gv[2] * A_[5]);
+      sts_f32(ra + 2 * P4, gv[2]);
+      sts_f32(ra + 3 * P4, gv[3] * A_[0] + gv[4] * A_[1] + gv[5] * A_[2]);
+      sts_f32(ra + 4 * P4, gv[3] * A_[3] + gv[4] * A_[4] + gv[5] * A_[5]);
+      sts_f32(ra + 5 * P4, gv[5]);
+      sts_f32(ra + 6 * P4, g_vp * pv);
+      float gt[6];
+      pose_affine_bwd<kSim>(ga, pa, gt);
+      // gradient rows in place; the batch sums (-> cpr_static and bias gradients) take the pre-activation gradient
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        acc[j][c] += gt[c];
+        float g = deform ? fmaf(greg, raw[c], gt[c]) : 0.0f;
+        if (relu && !(raw[c] > 0.0f)) g = 0.0f;
+        sts_f32(da + 4 * c, g);
+      }
+      acc[j][6] += g_lv;
+      acc[j][7] += g_u;
+      sts_f32(la, (relu && !(raw_lv > 0.0f)) ? 0.0f : g_lv);
+      sts_f32(la + V4, (relu && !(raw_u > 0.0f)) ? 0.0f : g_u);
+    }
+    fence_proxy_async();   // the gradient block is read by the bulk store issued after the barrier
+
+    // ---- staging (last warp): the next image's object tile (its loads were issued at least one phase ago) -----------------
+    if (stager && i + 1 < n_mine) {
+      mbar_wait(b3_full(bar0, sn), par_n);
+      __syncwarp();
+      caps3_bwd_object_tile<kSim>(a, up, L, smem, sn, blockIdx.x + (i + 1) * gridDim.x, i + 1, lane);
+    }
+    // ---- pre-pass of the next image ---------------------------------------------------------------------------------------
+    if (i + 1 < n_mine) pre_pass(i + 1, sn, par_n);
+    named_bar_sync(kB3Bar, (unsigned)Tpad);   // the image's only barrier
+
+    // ---- phase B ------------------------------------------------------------------------------------------------------------
+    if (warp == 0) {
+      // the previous image's bulk store has long completed: its 7 capsule-level slots per row can now be overwritten
+      if (lane == 0) {
+        bulk_wait_all();
+        const BulkRun r0 = bulk_run(a.all_param + (size_t)b * O * A, O * A);
+        float* gdst = out.g_all_param + (size_t)b * O * A;   // congruent to the source modulo 16 bytes (checked on the host)
+        if (r0.body) {
+          bulk_s2g(gdst + r0.head, smem + L.stage0 + s * L.stage_stride + L.prm + r0.off + r0.head, 4u * (unsigned)r0.body);
+          bulk_commit();
+        }
+      }
+      __syncwarp();
+      {
+        const BulkRun r0 = bulk_run(a.all_param + (size_t)b * O * A, O * A);
+        bulk_run_edges_out(out.g_all_param + (size_t)b * O * A, smem + L.stage0 + s * L.stage_stride + L.prm, r0, lane);
+      }
+    }
+    // two threads per (object, slot): each sums half of the object's V entries of RED7[slot] (uniform trip count: the
+    // shuffle needs every lane)
+    for (int base = 0; base < 7 * O; base += Tpad >> 1) {
+      const int it = base + (tid >> 1), half = tid & 1;
+      const bool on = it < 7 * O;
+      const int oo = on ? it / 7 : 0, c = on ? it - oo * 7 : 0;
+      const int Vh = (V + 1) >> 1;
+      const int v0 = half * Vh, v1 = min(V, v0 + Vh);
+      float s0 = 0.0f, s1 = 0.0f;
+      if (on) {
+        const float* src = smem + L.RED7 + c * P + oo * V;
+        int vv = v0;
+        for (; vv + 2 <= v1; vv += 2) {
+          s0 += src[vv];
+          s1 += src[vv + 1];
+        }
+        if (vv < v1) s0 += src[vv];
+      }
+      float sum = s0 + s1;
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (on && half == 0) smem[L.OBJ7 + par * O * 8 + oo * 8 + c] = sum;
+    }
+    mbar_arrive(b3_bdone(bar0, par));
+    if (warp == 0) {
+      if (i > 0) object_chain(i - 1);
+      if (i + S < n_mine) {
+        if (lane == 0) bulk_wait_read_all();   // this image's gradient block has been read out of its stage ...
+        __syncwarp();
+        caps3_bwd_issue(a, sv, up, L, smem, bar0, s, blockIdx.x + (i + S) * gridDim.x, lane);   // ... which takes image i + S
+      }
+    }
+    if (++s == S) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+
+  // ---- epilogue: the last image's capsule-level gradients, then the per-CTA batch sums ------------------------------------
+  if (n_mine > 0) {
+    named_bar_sync(kB3Bar, (unsigned)Tpad);
+    if (warp == 0) {
+      if (lane == 0) bulk_wait_all();
+      __syncwarp();
+      object_chain(n_mine - 1);
+    }
+  }
+  __syncthreads();
+  {
+    float* dst = out.partials + (size_t)blockIdx.x * O * A;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      if (!(vmask >> j & 1u)) continue;
+      float* row = dst + (size_t)(k + G * j) * A;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) row[6 * v + c] = acc[j][c];
+      row[6 * V + 7 + v] = acc[j][6];
+      row[7 * V + 7 + v] = acc[j][7];
+    }
+    for (int idx = tid; idx < O * 7; idx += Tpad) {
+      const int oo = idx / 7, c = idx - oo * 7;
+      dst[(size_t)oo * A + 6 * V + c] = smem[L.OBJSUM + oo * 8 + c];
+    }
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+// (tests/emu runs everything ABOVE this line on the CPU under a SIMT emulation: keep device code above, launches below)
+
+static int b3_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+struct Caps3BwdPlan {
+  int NP, threads;
+  Caps3BwdLayout L;
+  size_t smem;
+};
+
+// G object groups x V parts threads, NP = ceil(O / G) pairs each; 20 warps at most (96 registers per thread)
+static bool caps3_plan_bwd(const scae_caps_args* a, const scae_caps_upstream* up, Caps3BwdPlan* plan) {
+  const int O = a->O, V = a->V;
+  const int budget = max_smem_optin();
+  const int force_np = b3_env_int("SCAE_CAPS3_BWD_NP", 0), force_s = b3_env_int("SCAE_CAPS3_BWD_STAGES", 0);
+  double best_eff = 0.0;
+  int best_T = 0;
+  bool found = false;
+  for (int NP : {2, 1, 4}) {
+    if (force_np && NP != force_np) continue;
+    const int G = (O + NP - 1) / NP;
+    const int T = G * V, threads = (T + 31) & ~31;
+    if (threads > 640) continue;
+    const double eff = (double)O / ((double)G * NP);
+    int S = force_s >= 2 && force_s <= kB3MaxStages ? force_s : 3;   // 2 are enough to keep one image in flight; 3 give slack
+    Caps3BwdLayout L = caps3_bwd_layout(a, up, G, NP, S);
+    while (S > 2 && (size_t)L.total * sizeof(float) > (size_t)budget) L = caps3_bwd_layout(a, up, G, NP, --S);
+    if ((size_t)L.total * sizeof(float) > (size_t)budget) continue;
+    if (found && (eff < best_eff - 1e-9 || (eff < best_eff + 1e-9 && T <= best_T))) continue;
+    plan->NP = NP, plan->threads = threads, plan->L = L, plan->smem = (size_t)L.total * sizeof(float);
+    best_eff = eff, best_T = T;
+    found = true;
+  }
+  return found;
+}
+
+static int caps3_bwd_grid(const scae_caps_args* a) {
+  const int sms = sm_count();
+  return a->B < sms ? a->B : sms;
+}
+
+size_t caps3_bwd_workspace_bytes(const scae_caps_args* a) {
+  return (size_t)caps3_bwd_grid(a) * a->O * (8 * a->V + 7) * sizeof(float);
+}
+
+int caps3_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_caps_upstream* up, float* g_all_param,
+              float* g_shared, float* g_dummy_vote, float* g_x, float* g_presence, void* workspace,
+              size_t workspace_bytes, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  if ((long)a->O * a->V >= (1L << 22)) return SCAE_OK;
+  // upstream gradients that need the vote-weighted sums over objects, and part-side input gradients, stay on the
+  // general path (caps_ll.cu); a training step with vote_type = presence_type = 'enc' produces none of them
+  if (up->g_soft_winner || up->g_soft_winner_presence || up->g_winner || up->g_winner_presence ||
+      up->g_mixing_log_prob || g_x)
+    return SCAE_OK;
+  const void* need16[] = {a->all_param, a->cpr_static, a->x, g_all_param, saved->posterior_mixing_prob,
+                          saved->log_prob_per_point};
+  for (const void* p : need16)
+    if (!aligned16(p)) return SCAE_OK;
+  const void* opt16[] = {a->noise_vote, a->noise_caps, a->presence, up->g_posterior_mixing_prob, up->g_caps_presence,
+                         up->g_presence_logit_per_caps, up->g_caps_presence ? saved->caps_presence_arg : nullptr};
+  for (const void* p : opt16)
+    if (p && !aligned16(p)) return SCAE_OK;
+  Caps3BwdPlan plan;
+  if (!caps3_plan_bwd(a, up, &plan)) return SCAE_OK;
+  const int O = a->O, V = a->V, A = 8 * V + 7, n = O * A;
+  // Edge floats of a misaligned run are stored by the issuing warp (warp 0, after the barrier of image i) and first read
+  // in iteration i + S - 1 before its barrier: only a ring of three or more stages puts a barrier in between.
+  const bool edges = ((O * A) | (O * V) | (V * 6) | V | O) & 3;
+  if (edges && plan.L.S < 3) return SCAE_OK;
+  const int grid = caps3_bwd_grid(a);
+  if (workspace_bytes < (size_t)grid * n * sizeof(float)) return SCAE_OK;
+  const bool sim = (a->flags & SCAE_CAPS_SIMILARITY) != 0;
+  void (*kern)(const scae_caps_args, const scae_caps_saved, const scae_caps_upstream, const Caps3BwdOut,
+               const Caps3BwdLayout) = nullptr;
+  if (plan.NP == 1) kern = sim ? caps3_bwd_kernel<true, 1, 640, 1> : caps3_bwd_kernel<false, 1, 640, 1>;
+  else if (plan.NP == 2) kern = sim ? caps3_bwd_kernel<true, 2, 640, 1> : caps3_bwd_kernel<false, 2, 640, 1>;
+  else kern = sim ? caps3_bwd_kernel<true, 4, 512, 1> : caps3_bwd_kernel<false, 4, 512, 1>;
+  if (plan.NP == 4 && plan.threads > 512) return SCAE_OK;
+  SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  float* partials = static_cast<float*>(workspace);
+  Caps3BwdOut out{g_all_param, g_presence, partials};
+  kern<<<grid, plan.threads, plan.smem, stream>>>(*a, *saved, *up, out, plan.L);
+  note_launch();
+  SCAE_CUDA_TRY(cudaGetLastError());
+  int rc = launch_reduce_rows(partials, g_shared, grid, n, stream);
+  if (rc != SCAE_OK) return rc;
+  if (g_dummy_vote) SCAE_CUDA_TRY(cudaMemsetAsync(g_dummy_vote, 0, (size_t)V * 6 * sizeof(float), stream));
+  *handled = true;
+  return SCAE_OK;
+}
+
+}  // namespace scae

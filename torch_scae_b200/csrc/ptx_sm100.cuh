@@ -130,6 +130,8 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsig
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk stores of this thread have COMPLETED (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- cp.async (Ampere-style 4-byte asynchronous copies; the general capsule path stages ragged rows with them) -------
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
