@@ -36,12 +36,12 @@ constexpr unsigned kB3Bar = 1;
 __host__ __device__ inline int b3_round4(int n) { return (n + 3) & ~3; }
 
 struct Caps3BwdLayout {
-  int S, G, NP, T, Tpad;
+  int S, G, NP, T, Tpad, Vp;
   int stage0, stage_stride;                                     // floats
   int prm, post, gpost, nz, xs, ps, lse, nc, gcp, carg, glc, R, OS;   // offsets inside a stage
   int RED7, SPART, OBJ7, OSAVE, BIAS, OBJSUM, CST, total;       // CTA-wide tiles
   // byte strides / offsets the hot loop uses straight from the constant bank
-  unsigned strideA4, V4, T4, P4, strideR, strideO, post4, gpost4, nz4;
+  unsigned strideA4, V4, T4, P4, strideR, strideO, post4, gpost4, nz4, red_plane, red_step;
 };
 
 static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_upstream* up, int G, int NP, int S) {
@@ -70,7 +70,8 @@ static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_
   L.OS = take(O * 4) - L.stage0;
   L.stage_stride = at - L.stage0;
   at = L.stage0 + S * L.stage_stride;
-  L.RED7 = take(7 * P);
+  L.Vp = V | 1;                 // odd row pitch of the [7][O][Vp] tile: the row sums of phase B are conflict-free
+  L.RED7 = take(7 * O * L.Vp);
   L.SPART = take(2 * L.T);
   L.OBJ7 = take(2 * O * 8);
   L.OSAVE = take(kB3SaveBufs * O * kB3Save);
@@ -80,6 +81,7 @@ static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_
   L.total = at;
   L.strideA4 = 4u * (unsigned)(G * A), L.V4 = 4u * (unsigned)V, L.T4 = 4u * (unsigned)L.T, L.P4 = 4u * (unsigned)P;
   L.strideR = 32u * (unsigned)G, L.strideO = 16u * (unsigned)G;
+  L.red_plane = 4u * (unsigned)(O * L.Vp), L.red_step = 4u * (unsigned)(G * L.Vp);
   L.post4 = 4u * (unsigned)L.post, L.gpost4 = 4u * (unsigned)L.gpost, L.nz4 = 4u * (unsigned)L.nz;
   return L;
 }
@@ -182,7 +184,9 @@ __device__ __forceinline__ void caps3_bwd_object_tile(const scae_caps_args& a, c
   }
 }
 
-template <bool kSim, int NP, int kMaxT, int kMinB>
+// kExtras: some per-pair upstream gradient beyond the training set (vote_presence, vote, scale, presence_logit_per_vote,
+// mixing_logit) is given; without it no pointer is tested in the pair loop
+template <bool kSim, int NP, int kMaxT, int kMinB, bool kExtras>
 __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps_args a, const scae_caps_saved sv,
                                                                  const scae_caps_upstream up, const Caps3BwdOut out,
                                                                  const Caps3BwdLayout L) {
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
   }
   __syncthreads();
   const bool stager = warp == (Tpad >> 5) - 1;
+  const int chain_warp = Tpad > 32 ? 1 : 0;
   if (stager && n_mine > 0) {
     for (int i = 0; i < S && i < n_mine; ++i) caps3_bwd_issue(a, sv, up, L, smem, bar0, i, blockIdx.x + i * gridDim.x, lane);
     mbar_wait(b3_full(bar0, 0), 0);
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
   const unsigned cst_addr = keep(bar0 + 4u * (unsigned)(L.CST + tid));
   const unsigned r_off = keep((unsigned)(4 * (L.R + (active ? k * 8 : 0))));
   const unsigned os_off = keep((unsigned)(4 * (L.OS + (active ? k * 4 : 0))));
-  const unsigned red_addr = keep(bar0 + 4u * (unsigned)(L.RED7 + tid));
+  const unsigned red_addr = keep(bar0 + 4u * (unsigned)(L.RED7 + (active ? k * L.Vp + v : 0)));
   const unsigned stage_bytes = (unsigned)(4 * L.stage_stride);
   const unsigned OAmod = (unsigned)(O * A) & 3u, Pmod = (unsigned)P & 3u, V6mod = (unsigned)(V * 6) & 3u, Vmod = (unsigned)V & 3u;
   const bool have_gpost = up.g_posterior_mixing_prob != nullptr;
@@ -379,10 +384,10 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       const float h = have_gpost ? lds_f32(st + L.gpost4 + pbase + (unsigned)j * T4) : 0.0f;
       const float g_pl = pst * (h - Sv) + gllp * pst;
       float g_vp = 0.0f;
-      if (up.g_vote_presence) g_vp += __ldg(up.g_vote_presence + e);
+      if (kExtras && up.g_vote_presence) g_vp += __ldg(up.g_vote_presence + e);
       if (__float_as_int(os.y) == v) g_vp += os.x;
       float g_ml = g_pl;
-      if (up.g_mixing_logit) g_ml += __ldg(up.g_mixing_logit + (size_t)b * (P + V) + tid + (size_t)j * T);
+      if (kExtras && up.g_mixing_logit) g_ml += __ldg(up.g_mixing_logit + (size_t)b * (P + V) + tid + (size_t)j * T);
       if (!(vp < kLogSafeEps)) g_vp = fmaf(g_ml, rcp_approx(vp), g_vp);
       const float inv_sc = rcp_approx(sc);
       const float inv2 = inv_sc * inv_sc;
@@ -391,13 +396,13 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         gv[c] = coef * diff[c];
-        if (up.g_vote) gv[c] += __ldg(up.g_vote + e * 6 + c);
+        if (kExtras && up.g_vote) gv[c] += __ldg(up.g_vote + e * 6 + c);
       }
       float g_sc = g_pl * inv_sc * fmaf(q, inv2, -6.0f);
-      if (up.g_scale) g_sc += __ldg(up.g_scale + e);
+      if (kExtras && up.g_scale) g_sc += __ldg(up.g_scale + e);
       const float g_u = g_sc * dsc;
       float g_lv = g_vp * vp * (1.0f - pv);
-      if (up.g_presence_logit_per_vote) g_lv += __ldg(up.g_presence_logit_per_vote + e);
+      if (kExtras && up.g_presence_logit_per_vote) g_lv += __ldg(up.g_presence_logit_per_vote + e);
       // vote = R . A: gradient w.r.t. A (-> this pair's cpr parameters) and w.r.t. R (-> summed over the parts in phase B)
       const float* A_ = pa.a;
       float ga[6];
@@ -407,14 +412,14 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       ga[3] = r[1] * gv[0] + r[4] * gv[3];
       ga[4] = r[1] * gv[1] + r[4] * gv[4];
       ga[5] = r[1] * gv[2] + r[4] * gv[5];
-      const unsigned ra = red_addr + (unsigned)j * T4;
-      sts_f32(ra + 0 * P4, gv[0] * A_[0] + gv[1] * A_[1] + gv[2] * A_[2]);
-      sts_f32(ra + 1 * P4, gv[0] * A_[3] + gv[1] * A_[4] + gv[2] * A_[5]);
-      sts_f32(ra + 2 * P4, gv[2]);
-      sts_f32(ra + 3 * P4, gv[3] * A_[0] + gv[4] * A_[1] + gv[5] * A_[2]);
-      sts_f32(ra + 4 * P4, gv[3] * A_[3] + gv[4] * A_[4] + gv[5] * A_[5]);
-      sts_f32(ra + 5 * P4, gv[5]);
-      sts_f32(ra + 6 * P4, g_vp * pv);
+      const unsigned ra = red_addr + (unsigned)j * L.red_step, RP = L.red_plane;
+      sts_f32(ra + 0 * RP, gv[0] * A_[0] + gv[1] * A_[1] + gv[2] * A_[2]);
+      sts_f32(ra + 1 * RP, gv[0] * A_[3] + gv[1] * A_[4] + gv[2] * A_[5]);
+      sts_f32(ra + 2 * RP, gv[2]);
+      sts_f32(ra + 3 * RP, gv[3] * A_[0] + gv[4] * A_[1] + gv[5] * A_[2]);
+      sts_f32(ra + 4 * RP, gv[3] * A_[3] + gv[4] * A_[4] + gv[5] * A_[5]);
+      sts_f32(ra + 5 * RP, gv[5]);
+      sts_f32(ra + 6 * RP, g_vp * pv);
       float gt[6];
       pose_affine_bwd<kSim>(ga, pa, gt);
       // gradient rows in place; the batch sums (-> cpr_static and bias gradients) take the pre-activation gradient
@@ -440,37 +445,31 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     }
     // ---- pre-pass of the next image ---------------------------------------------------------------------------------------
     if (i + 1 < n_mine) pre_pass(i + 1, sn, par_n);
+    if (tid == 0) bulk_wait_all();   // the previous image's bulk store (issued a whole pass ago) has completed
     named_bar_sync(kB3Bar, (unsigned)Tpad);   // the image's only barrier
 
     // ---- phase B ------------------------------------------------------------------------------------------------------------
-    if (warp == 0) {
-      // the previous image's bulk store has long completed: its 7 capsule-level slots per row can now be overwritten
-      if (lane == 0) {
-        bulk_wait_all();
-        const BulkRun r0 = bulk_run(a.all_param + (size_t)b * O * A, O * A);
-        float* gdst = out.g_all_param + (size_t)b * O * A;   // congruent to the source modulo 16 bytes (checked on the host)
-        if (r0.body) {
-          bulk_s2g(gdst + r0.head, smem + L.stage0 + s * L.stage_stride + L.prm + r0.off + r0.head, 4u * (unsigned)r0.body);
-          bulk_commit();
-        }
+    if (warp == 0) {   // this image's gradient block leaves
+      const BulkRun r0 = bulk_run(a.all_param + (size_t)b * O * A, O * A);
+      float* gdst = out.g_all_param + (size_t)b * O * A;   // congruent to the source modulo 16 bytes (checked on the host)
+      float* gsrc = smem + L.stage0 + s * L.stage_stride + L.prm;
+      if (lane == 0 && r0.body) {
+        bulk_s2g(gdst + r0.head, gsrc + r0.off + r0.head, 4u * (unsigned)r0.body);
+        bulk_commit();
       }
-      __syncwarp();
-      {
-        const BulkRun r0 = bulk_run(a.all_param + (size_t)b * O * A, O * A);
-        bulk_run_edges_out(out.g_all_param + (size_t)b * O * A, smem + L.stage0 + s * L.stage_stride + L.prm, r0, lane);
-      }
+      bulk_run_edges_out(gdst, gsrc, r0, lane);
     }
-    // two threads per (object, slot): each sums half of the object's V entries of RED7[slot] (uniform trip count: the
-    // shuffle needs every lane)
+    // two threads per (object, slot), taken from the top warps down (warps 0 and 1 are busy above): each sums half of the
+    // object's V entries of RED7[slot]; uniform trip count: the shuffle needs every lane
     for (int base = 0; base < 7 * O; base += Tpad >> 1) {
-      const int it = base + (tid >> 1), half = tid & 1;
+      const int it = base + ((Tpad - 1 - tid) >> 1), half = tid & 1;
       const bool on = it < 7 * O;
-      const int oo = on ? it / 7 : 0, c = on ? it - oo * 7 : 0;
+      const int c = on ? it / O : 0, oo = on ? it - c * O : 0;
       const int Vh = (V + 1) >> 1;
       const int v0 = half * Vh, v1 = min(V, v0 + Vh);
       float s0 = 0.0f, s1 = 0.0f;
       if (on) {
-        const float* src = smem + L.RED7 + c * P + oo * V;
+        const float* src = smem + L.RED7 + (c * O + oo) * L.Vp;
         int vv = v0;
         for (; vv + 2 <= v1; vv += 2) {
           s0 += src[vv];
@@ -482,14 +481,16 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       if (on && half == 0) smem[L.OBJ7 + par * O * 8 + oo * 8 + c] = sum;
     }
-    mbar_arrive(b3_bdone(bar0, par));
-    if (warp == 0) {
+    mbar_arrive(b3_bdone(bar0, par));   // this thread is done with the [7][O][Vp] tile
+    if (warp == 0 && i + S < n_mine) {   // once the block has been read out of the stage, the stage takes image i + S
+      if (lane == 0) bulk_wait_read_all();
+      __syncwarp();
+      caps3_bwd_issue(a, sv, up, L, smem, bar0, s, blockIdx.x + (i + S) * gridDim.x, lane);
+    }
+    if (warp == chain_warp) {
+      // the previous image's bulk store completed before this image's barrier (lane 0 of warp 0 waited for it), so its
+      // 7 capsule-level slots per row can be overwritten now
       if (i > 0) object_chain(i - 1);
-      if (i + S < n_mine) {
-        if (lane == 0) bulk_wait_read_all();   // this image's gradient block has been read out of its stage ...
-        __syncwarp();
-        caps3_bwd_issue(a, sv, up, L, smem, bar0, s, blockIdx.x + (i + S) * gridDim.x, lane);   // ... which takes image i + S
-      }
     }
     if (++s == S) {
       s = 0;
@@ -499,12 +500,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
 
   // ---- epilogue: the last image's capsule-level gradients, then the per-CTA batch sums ------------------------------------
   if (n_mine > 0) {
+    if (tid == 0) bulk_wait_all();
     named_bar_sync(kB3Bar, (unsigned)Tpad);
-    if (warp == 0) {
-      if (lane == 0) bulk_wait_all();
-      __syncwarp();
-      object_chain(n_mine - 1);
-    }
+    if (warp == chain_warp) object_chain(n_mine - 1);
   }
   __syncthreads();
   {
@@ -604,9 +602,14 @@ int caps3_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_
   const bool sim = (a->flags & SCAE_CAPS_SIMILARITY) != 0;
   void (*kern)(const scae_caps_args, const scae_caps_saved, const scae_caps_upstream, const Caps3BwdOut,
                const Caps3BwdLayout) = nullptr;
-  if (plan.NP == 1) kern = sim ? caps3_bwd_kernel<true, 1, 640, 1> : caps3_bwd_kernel<false, 1, 640, 1>;
-  else if (plan.NP == 2) kern = sim ? caps3_bwd_kernel<true, 2, 640, 1> : caps3_bwd_kernel<false, 2, 640, 1>;
-  else kern = sim ? caps3_bwd_kernel<true, 4, 512, 1> : caps3_bwd_kernel<false, 4, 512, 1>;
+  const bool extras = up->g_vote_presence || up->g_mixing_logit || up->g_vote || up->g_scale || up->g_presence_logit_per_vote;
+#define B3_PICK(NP_, MAXT_)                                                                                     \
+  (sim ? (extras ? caps3_bwd_kernel<true, NP_, MAXT_, 1, true> : caps3_bwd_kernel<true, NP_, MAXT_, 1, false>)  \
+       : (extras ? caps3_bwd_kernel<false, NP_, MAXT_, 1, true> : caps3_bwd_kernel<false, NP_, MAXT_, 1, false>))
+  if (plan.NP == 1) kern = B3_PICK(1, 640);
+  else if (plan.NP == 2) kern = B3_PICK(2, 640);
+  else kern = B3_PICK(4, 512);
+#undef B3_PICK
   if (plan.NP == 4 && plan.threads > 512) return SCAE_OK;
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
