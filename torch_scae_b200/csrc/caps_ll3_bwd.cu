@@ -35,20 +35,24 @@ constexpr unsigned kB3Bar = 1;
 
 __host__ __device__ inline int b3_round4(int n) { return (n + 3) & ~3; }
 
+constexpr int kB3PG = 3;        // slots of the posterior ring
+constexpr int kB3Tin = 12;      // floats per object of the object-tile inputs: 7 raw parameters, noise, 3 upstream values
+
 struct Caps3BwdLayout {
   int S, G, NP, T, Tpad, Vp;
-  int stage0, stage_stride;                                     // floats
-  int prm, post, gpost, nz, xs, ps, lse, nc, gcp, carg, glc, R, OS;   // offsets inside a stage
-  int RED7, SPART, OBJ7, OSAVE, BIAS, OBJSUM, CST, total;       // CTA-wide tiles
+  int stage0, stage_stride;                      // floats; the in-place ring: S stages
+  int prm, nz, xs, ps, lse, R, OS;               // offsets inside a stage
+  int pg0, pg_stride, gpost;                     // the posterior ring: kB3PG slots of {posterior, its upstream gradient}
+  int RED7, SPART, OBJ7, OSAVE, TIN, SC, BIAS, OBJSUM, CST, total;   // CTA-wide tiles
   // byte strides / offsets the hot loop uses straight from the constant bank
-  unsigned strideA4, V4, T4, P4, strideR, strideO, post4, gpost4, nz4, red_plane, red_step;
+  unsigned strideA4, V4, T4, strideR, strideO, nz4, gpost4, red_plane, red_step;
 };
 
 static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_upstream* up, int G, int NP, int S) {
   const int O = a->O, V = a->V, A = 8 * V + 7, P = O * V;
   Caps3BwdLayout L;
   L.S = S, L.G = G, L.NP = NP, L.T = G * V, L.Tpad = (L.T + 31) & ~31;
-  int at = 32;   // [0, 32) floats: mbarriers full[4], bdone[2]
+  int at = 32;   // [0, 32) floats: mbarriers full[4], bdone[2], pgfull[3], ready[2]
   auto take = [&](int n) {
     const int here = at;
     at += b3_round4(n);
@@ -56,38 +60,41 @@ static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_
   };
   L.stage0 = at;
   L.prm = take(O * A + 4) - L.stage0;
-  L.post = take(P + 4) - L.stage0;
-  L.gpost = take(up->g_posterior_mixing_prob ? P + 4 : 0) - L.stage0;
   L.nz = take(a->noise_vote ? P + 4 : 0) - L.stage0;
   L.xs = take(V * 6 + 4) - L.stage0;
   L.ps = take(a->presence ? V + 4 : 0) - L.stage0;
   L.lse = take(V + 4) - L.stage0;
-  L.nc = take(a->noise_caps ? O + 4 : 0) - L.stage0;
-  L.gcp = take(up->g_caps_presence ? O + 4 : 0) - L.stage0;
-  L.carg = take(up->g_caps_presence ? O + 4 : 0) - L.stage0;
-  L.glc = take(up->g_presence_logit_per_caps ? O + 4 : 0) - L.stage0;
   L.R = take(O * 8) - L.stage0;
   L.OS = take(O * 4) - L.stage0;
   L.stage_stride = at - L.stage0;
   at = L.stage0 + S * L.stage_stride;
+  L.pg0 = at;
+  take(P + 4);
+  L.gpost = take(up->g_posterior_mixing_prob ? P + 4 : 0) - L.pg0;
+  L.pg_stride = at - L.pg0;
+  at = L.pg0 + kB3PG * L.pg_stride;
   L.Vp = V | 1;                 // odd row pitch of the [7][O][Vp] tile: the row sums of phase B are conflict-free
   L.RED7 = take(7 * O * L.Vp);
   L.SPART = take(2 * L.T);
   L.OBJ7 = take(2 * O * 8);
   L.OSAVE = take(kB3SaveBufs * O * kB3Save);
+  L.TIN = take(O * kB3Tin + 4);   // + the image's two upstream scalars
+  L.SC = take(2 * 4);             // {g_ll, g_reg} of the image, by image parity
   L.BIAS = take(O * 8);
   L.OBJSUM = take(O * 8);
   L.CST = take(8 * L.T * NP);   // [NP][8][T]: cpr_static (6), bias_vote, bias_scale + 0.5 of the thread's pairs
   L.total = at;
-  L.strideA4 = 4u * (unsigned)(G * A), L.V4 = 4u * (unsigned)V, L.T4 = 4u * (unsigned)L.T, L.P4 = 4u * (unsigned)P;
+  L.strideA4 = 4u * (unsigned)(G * A), L.V4 = 4u * (unsigned)V, L.T4 = 4u * (unsigned)L.T;
   L.strideR = 32u * (unsigned)G, L.strideO = 16u * (unsigned)G;
   L.red_plane = 4u * (unsigned)(O * L.Vp), L.red_step = 4u * (unsigned)(G * L.Vp);
-  L.post4 = 4u * (unsigned)L.post, L.gpost4 = 4u * (unsigned)L.gpost, L.nz4 = 4u * (unsigned)L.nz;
+  L.nz4 = 4u * (unsigned)L.nz, L.gpost4 = 4u * (unsigned)L.gpost;
   return L;
 }
 
 __device__ __forceinline__ unsigned b3_full(unsigned bar0, int s) { return bar0 + 8u * (unsigned)s; }
 __device__ __forceinline__ unsigned b3_bdone(unsigned bar0, int p) { return bar0 + 8u * (unsigned)(kB3MaxStages + p); }
+__device__ __forceinline__ unsigned b3_pgfull(unsigned bar0, int p) { return bar0 + 8u * (unsigned)(kB3MaxStages + 2 + p); }
+__device__ __forceinline__ unsigned b3_ready(unsigned bar0, int p) { return bar0 + 8u * (unsigned)(kB3MaxStages + 2 + kB3PG + p); }
 
 struct Caps3BwdOut {
   float* g_all_param;   // [B,O,A] final: ReLU mask and regulariser applied
@@ -95,47 +102,81 @@ struct Caps3BwdOut {
   float* partials;      // [grid][O*A] per-CTA batch sums of the pre-activation gradient
 };
 
-// ---- staging (one warp): lane r < 11 owns one contiguous per-image input --------------------------------------------------
+// ---- staging (one warp): each lane owns one contiguous per-image input ----------------------------------------------------
 struct B3Run {
   const float* g;
   float* base;
   int n;
 };
 
-__device__ __forceinline__ void caps3_bwd_issue(const scae_caps_args& a, const scae_caps_saved& sv,
-                                                const scae_caps_upstream& up, const Caps3BwdLayout& L, float* smem,
-                                                unsigned bar0, int s, int b, int lane) {
-  const int O = a.O, V = a.V, A = 8 * V + 7, P = O * V;
-  float* st = smem + L.stage0 + s * L.stage_stride;
-  B3Run run = {nullptr, nullptr, 0};
-  switch (lane) {
-    case 0: run = {a.all_param + (size_t)b * O * A, st + L.prm, O * A}; break;
-    case 1: run = {sv.posterior_mixing_prob + (size_t)b * P, st + L.post, P}; break;
-    case 2: if (up.g_posterior_mixing_prob) run = {up.g_posterior_mixing_prob + (size_t)b * P, st + L.gpost, P}; break;
-    case 3: if (a.noise_vote) run = {a.noise_vote + (size_t)b * P, st + L.nz, P}; break;
-    case 4: run = {a.x + (size_t)b * V * 6, st + L.xs, V * 6}; break;
-    case 5: if (a.presence) run = {a.presence + (size_t)b * V, st + L.ps, V}; break;
-    case 6: run = {sv.log_prob_per_point + (size_t)b * V, st + L.lse, V}; break;
-    case 7: if (a.noise_caps) run = {a.noise_caps + (size_t)b * O, st + L.nc, O}; break;
-    case 8: if (up.g_caps_presence) run = {up.g_caps_presence + (size_t)b * O, st + L.gcp, O}; break;
-    case 9:
-      if (up.g_caps_presence) run = {reinterpret_cast<const float*>(sv.caps_presence_arg) + (size_t)b * O, st + L.carg, O};
-      break;
-    case 10: if (up.g_presence_logit_per_caps) run = {up.g_presence_logit_per_caps + (size_t)b * O, st + L.glc, O}; break;
-    default: break;
-  }
+// the lane's run (n = 0: none) -> shared memory, completion on mbarrier `bar`: interior by bulk copy, edges through registers
+__device__ __forceinline__ void caps3_bwd_issue_runs(const B3Run& run, unsigned bar, int lane) {
   BulkRun br = {0, 0, 0, 0};
   if (run.n) br = bulk_run(run.g, run.n);
   unsigned bytes = 4u * (unsigned)br.body;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
-  if (lane == 0) mbar_expect_tx(b3_full(bar0, s), bytes);
+  if (lane == 0) mbar_expect_tx(bar, bytes);
   __syncwarp();
-  if (br.body) bulk_g2s(run.base + br.off + br.head, run.g + br.head, 4u * (unsigned)br.body, b3_full(bar0, s));
+  if (br.body) bulk_g2s(run.base + br.off + br.head, run.g + br.head, 4u * (unsigned)br.body, bar);
   if (run.n) {   // the run's (at most 3 + 3) edge floats
     for (int q = 0; q < br.head; ++q) run.base[br.off + q] = __ldg(run.g + q);
     for (int q = 0; q < br.tail; ++q) run.base[br.off + br.head + br.body + q] = __ldg(run.g + br.head + br.body + q);
   }
+}
+
+// in-place stage s <- image b: all_param block (becomes the gradient block), noise rows, part poses / presences / lse
+__device__ __forceinline__ void caps3_bwd_issue(const scae_caps_args& a, const scae_caps_saved& sv,
+                                                const Caps3BwdLayout& L, float* smem, unsigned bar0, int s, int b,
+                                                int lane) {
+  const int O = a.O, V = a.V, A = 8 * V + 7, P = O * V;
+  float* st = smem + L.stage0 + s * L.stage_stride;
+  B3Run run = {nullptr, nullptr, 0};
+  switch (lane) {
+    case 0: run = {a.all_param + (size_t)b * O * A, st + L.prm, O * A}; break;
+    case 1: if (a.noise_vote) run = {a.noise_vote + (size_t)b * P, st + L.nz, P}; break;
+    case 2: run = {a.x + (size_t)b * V * 6, st + L.xs, V * 6}; break;
+    case 3: if (a.presence) run = {a.presence + (size_t)b * V, st + L.ps, V}; break;
+    case 4: run = {sv.log_prob_per_point + (size_t)b * V, st + L.lse, V}; break;
+    default: break;
+  }
+  caps3_bwd_issue_runs(run, b3_full(bar0, s), lane);
+}
+
+// posterior ring slot <- image b: saved posterior and its upstream gradient (what the pre-pass needs one image ahead)
+__device__ __forceinline__ void caps3_bwd_issue_pg(const scae_caps_saved& sv, const scae_caps_upstream& up,
+                                                   const Caps3BwdLayout& L, float* smem, unsigned bar0, int slot, int b,
+                                                   int P, int lane) {
+  float* pg = smem + L.pg0 + slot * L.pg_stride;
+  B3Run run = {nullptr, nullptr, 0};
+  if (lane == 0) run = {sv.posterior_mixing_prob + (size_t)b * P, pg, P};
+  else if (lane == 1 && up.g_posterior_mixing_prob) run = {up.g_posterior_mixing_prob + (size_t)b * P, pg + L.gpost, P};
+  caps3_bwd_issue_runs(run, b3_pgfull(bar0, slot), lane);
+}
+
+// object-tile inputs of image b -> TIN[o] = {7 raw capsule-level parameters, noise, upstream gradient of caps_presence, its
+// arg-max part, upstream gradient of the presence logit} by 4-byte asynchronous copies (no registers held meanwhile);
+// lane = object, so the lane that copies a row is the one that reads it
+__device__ __forceinline__ void caps3_bwd_tile_inputs(const scae_caps_args& a, const scae_caps_saved& sv,
+                                                      const scae_caps_upstream& up, const Caps3BwdLayout& L, float* smem,
+                                                      int b, int lane) {
+  const int O = a.O, V = a.V, A = 8 * V + 7;
+  for (int oo = lane; oo < O; oo += 32) {
+    float* dst = smem + L.TIN + oo * kB3Tin;
+    const float* row = a.all_param + ((size_t)b * O + oo) * A + 6 * V;
+#pragma unroll
+    for (int p = 0; p < 7; ++p) cp_async4(dst + p, row + p);
+    const size_t bo = (size_t)b * O + oo;
+    if (a.noise_caps) cp_async4(dst + 7, a.noise_caps + bo);
+    if (up.g_caps_presence) {
+      cp_async4(dst + 8, up.g_caps_presence + bo);
+      cp_async4(dst + 9, reinterpret_cast<const float*>(sv.caps_presence_arg) + bo);
+    }
+    if (up.g_presence_logit_per_caps) cp_async4(dst + 10, up.g_presence_logit_per_caps + bo);
+  }
+  if (lane == 0 && up.g_ll_per_example) cp_async4(smem + L.TIN + O * kB3Tin, up.g_ll_per_example + b);
+  if (lane == 1 && up.g_reg_per_example) cp_async4(smem + L.TIN + O * kB3Tin + 1, up.g_reg_per_example + b);
+  cp_async_commit();
 }
 
 // per-object work of image b in stage s (one warp, lane = object):
@@ -145,43 +186,40 @@ __device__ __forceinline__ void caps3_bwd_issue(const scae_caps_args& a, const s
 //               bit c: raw parameter 6V + c is positive (the MLP's ReLU was active), -, -}
 template <bool kSim>
 __device__ __forceinline__ void caps3_bwd_object_tile(const scae_caps_args& a, const scae_caps_upstream& up,
-                                                      const Caps3BwdLayout& L, float* smem, int s, int b, int img,
-                                                      int lane) {
-  const int O = a.O, V = a.V, A = 8 * V + 7;
+                                                      const Caps3BwdLayout& L, float* smem, int s, int img, int lane) {
+  const int O = a.O;
   float* st = smem + L.stage0 + s * L.stage_stride;
-  const float* prm = st + L.prm + bulk_run(a.all_param + (size_t)b * O * A, O * A).off;
-  const float* nc = a.noise_caps ? st + L.nc + bulk_run(a.noise_caps + (size_t)b * O, O).off : nullptr;
-  const float* gcp = up.g_caps_presence ? st + L.gcp + bulk_run(up.g_caps_presence + (size_t)b * O, O).off : nullptr;
-  const float* carg = up.g_caps_presence ? st + L.carg + bulk_run(up.g_caps_presence + (size_t)b * O, O).off : nullptr;
-  const float* glc = up.g_presence_logit_per_caps ? st + L.glc + bulk_run(up.g_presence_logit_per_caps + (size_t)b * O, O).off : nullptr;
   const float* BIAS = smem + L.BIAS;
   float* R = st + L.R;
   float* OS = st + L.OS;
   float* SAVE = smem + L.OSAVE + (img % kB3SaveBufs) * O * kB3Save;
   for (int oo = lane; oo < O; oo += 32) {
-    const float* row = prm + oo * A + 6 * V;
+    const float* in = smem + L.TIN + oo * kB3Tin;
+    const float4 i0 = *reinterpret_cast<const float4*>(in), i1 = *reinterpret_cast<const float4*>(in + 4),
+                 i2 = *reinterpret_cast<const float4*>(in + 8);
     const float4 b0 = *reinterpret_cast<const float4*>(BIAS + oo * 8), b1 = *reinterpret_cast<const float4*>(BIAS + oo * 8 + 4);
-    float raw[7];
-#pragma unroll
-    for (int p = 0; p < 7; ++p) raw[p] = row[p];
+    const float raw[7] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z};
     const float t[6] = {raw[0] + b0.x, raw[1] + b0.y, raw[2] + b0.z, raw[3] + b0.w, raw[4] + b1.x, raw[5] + b1.y};
     PoseAffine r;
     pose_affine_mufu<kSim>(t, r);
     float lc = raw[6] + b1.z;
-    if (nc) lc += nc[oo];
+    if (a.noise_caps) lc += i1.w;
     const float pc = sigmoid_fast(lc);
     float4* dst = reinterpret_cast<float4*>(R + oo * 8);
     dst[0] = make_float4(r.a[0], r.a[1], r.a[2], r.a[3]);
     dst[1] = make_float4(r.a[4], r.a[5], pc, 0.0f);
-    *reinterpret_cast<float4*>(OS + oo * 4) = make_float4(gcp ? gcp[oo] : 0.0f, gcp ? carg[oo] : __int_as_float(-1), 0.0f, 0.0f);
+    const bool gc = up.g_caps_presence != nullptr;
+    *reinterpret_cast<float4*>(OS + oo * 4) = make_float4(gc ? i2.x : 0.0f, gc ? i2.y : __int_as_float(-1), 0.0f, 0.0f);
     unsigned mask = 0;
 #pragma unroll
     for (int p = 0; p < 7; ++p) mask |= raw[p] > 0.0f ? 1u << p : 0u;
     float4* sd = reinterpret_cast<float4*>(SAVE + oo * kB3Save);
     sd[0] = make_float4(r.sx, r.sy, r.sh, r.tx);
     sd[1] = make_float4(r.ty, r.c, r.s, pc);
-    sd[2] = make_float4(glc ? glc[oo] : 0.0f, __uint_as_float(mask), 0.0f, 0.0f);
+    sd[2] = make_float4(up.g_presence_logit_per_caps ? i2.z : 0.0f, __uint_as_float(mask), 0.0f, 0.0f);
   }
+  if (lane == 0) smem[L.SC + (img & 1) * 4] = up.g_ll_per_example ? smem[L.TIN + O * kB3Tin] : 0.0f;
+  if (lane == 1) smem[L.SC + (img & 1) * 4 + 1] = up.g_reg_per_example ? smem[L.TIN + O * kB3Tin + 1] : 0.0f;
 }
 
 // kExtras: some per-pair upstream gradient beyond the training set (vote_presence, vote, scale, presence_logit_per_vote,
@@ -206,6 +244,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     }
     mbar_init(b3_bdone(bar0, 0), (unsigned)Tpad);
     mbar_init(b3_bdone(bar0, 1), (unsigned)Tpad);
+    for (int p = 0; p < kB3PG; ++p) mbar_init(b3_pgfull(bar0, p), 1);
+    mbar_init(b3_ready(bar0, 0), 1);
+    mbar_init(b3_ready(bar0, 1), 1);
     fence_mbar_init();
   }
   for (int i = tid; i < O * 8; i += Tpad) {
@@ -217,10 +258,14 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
   const bool stager = warp == (Tpad >> 5) - 1;
   const int chain_warp = Tpad > 32 ? 1 : 0;
   if (stager && n_mine > 0) {
-    for (int i = 0; i < S && i < n_mine; ++i) caps3_bwd_issue(a, sv, up, L, smem, bar0, i, blockIdx.x + i * gridDim.x, lane);
-    mbar_wait(b3_full(bar0, 0), 0);
+    caps3_bwd_tile_inputs(a, sv, up, L, smem, blockIdx.x, lane);
+    for (int i = 0; i < kB3PG && i < n_mine; ++i)
+      caps3_bwd_issue_pg(sv, up, L, smem, bar0, i, blockIdx.x + i * gridDim.x, P, lane);
+    for (int i = 0; i < S && i < n_mine; ++i) caps3_bwd_issue(a, sv, L, smem, bar0, i, blockIdx.x + i * gridDim.x, lane);
+    cp_async_wait<0>();
+    caps3_bwd_object_tile<kSim>(a, up, L, smem, 0, 0, lane);
     __syncwarp();
-    caps3_bwd_object_tile<kSim>(a, up, L, smem, 0, blockIdx.x, 0, lane);
+    if (lane == 0) mbar_arrive(b3_ready(bar0, 0));
   }
 
   // ---- per-thread constants ----------------------------------------------------------------------------------------------
@@ -250,7 +295,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
   vmask = keep(vmask);
   const unsigned d_off = keep((unsigned)(4 * (active ? k * A + 6 * v : 0)));
   const unsigned l_off = keep((unsigned)(4 * (active ? k * A + 6 * V + 7 + v : 0)));
-  const unsigned strideA = L.strideA4, V4 = L.V4, T4 = L.T4, P4 = L.P4, strideR = L.strideR, strideO = L.strideO;
+  const unsigned strideA = L.strideA4, V4 = L.V4, T4 = L.T4, strideR = L.strideR, strideO = L.strideO;
+  const unsigned pg_bytes = (unsigned)(4 * L.pg_stride), pg_base = bar0 + 4u * (unsigned)L.pg0;
   const unsigned cst_addr = keep(bar0 + 4u * (unsigned)(L.CST + tid));
   const unsigned r_off = keep((unsigned)(4 * (L.R + (active ? k * 8 : 0))));
   const unsigned os_off = keep((unsigned)(4 * (L.OS + (active ? k * 4 : 0))));
@@ -261,22 +307,19 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
   __syncthreads();   // the first image's object tile (written by the stager above) is visible
 
   // the thread's share of S[v] = sum_o posterior * upstream for image `img` in stage `sn` -> SPART[img & 1]
-  auto pre_pass = [&](int img, int sn, unsigned par_n) {
-    const int bn = blockIdx.x + img * gridDim.x;
-    mbar_wait(b3_full(bar0, sn), par_n);
+  auto pre_pass = [&](int img) {
+    const int bn = blockIdx.x + img * gridDim.x, slot = img % kB3PG;
+    mbar_wait(b3_pgfull(bar0, slot), (unsigned)((img / kB3PG) & 1));
     float part = 0.0f;
     if (have_gpost) {
-      const unsigned stn = bar0 + 4u * (unsigned)L.stage0 + (unsigned)sn * stage_bytes;
-      const unsigned po = 4u * (((unsigned)bn * Pmod) & 3u) + 4u * (unsigned)tid;
+      const unsigned po = pg_base + (unsigned)slot * pg_bytes + 4u * (((unsigned)bn * Pmod) & 3u) + 4u * (unsigned)tid;
 #pragma unroll
       for (int j = 0; j < NP; ++j)
-        if (vmask >> j & 1u)
-          part = fmaf(lds_f32(stn + L.post4 + po + (unsigned)j * T4),
-                      lds_f32(stn + L.gpost4 + po + (unsigned)j * T4), part);
+        if (vmask >> j & 1u) part = fmaf(lds_f32(po + (unsigned)j * T4), lds_f32(po + L.gpost4 + (unsigned)j * T4), part);
     }
     if (active) smem[L.SPART + (img & 1) * T + tid] = part;
   };
-  if (n_mine > 0) pre_pass(0, 0, 0);
+  if (n_mine > 0) pre_pass(0);
   __syncthreads();
 
   // the capsule-level gradients of image `img` (warp 0, one lane per object) from the sums phase B left in OBJ7
@@ -316,7 +359,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     const unsigned prm = keep(st + 4u * (unsigned)L.prm + 4u * (((unsigned)b * OAmod) & 3u));
     const unsigned pbase = keep(4u * (((unsigned)b * Pmod) & 3u) + 4u * (unsigned)tid);   // the thread's first pair in a [P] run
     const int sn = s + 1 == S ? 0 : s + 1;
-    const unsigned par_n = s + 1 == S ? parity ^ 1u : parity;
+    const unsigned pgp = pg_base + (unsigned)(i % kB3PG) * pg_bytes + pbase;   // the thread's first pair in the posterior ring
+    if (stager && i + 1 < n_mine) caps3_bwd_tile_inputs(a, sv, up, L, smem, blockIdx.x + (i + 1) * gridDim.x, lane);
+    mbar_wait(b3_full(bar0, s), parity);   // the image's in-place stage has landed
 
     // ---- per-part values -------------------------------------------------------------------------------------------------
     float xv[6];
@@ -326,16 +371,12 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       for (int c = 0; c < 6; ++c) xv[c] = lds_f32(xa + 4 * c);
     }
     const float pres = a.presence ? lds_f32(st + 4u * (unsigned)L.ps + 4u * (((unsigned)b * Vmod) & 3u) + 4u * (unsigned)v) : 1.0f;
-    const float gll = up.g_ll_per_example ? __ldg(up.g_ll_per_example + b) : 0.0f;
-    const float greg = up.g_reg_per_example ? __ldg(up.g_reg_per_example + b) : 0.0f;
-    const float gllp = gll * pres;
+    float gllp = 0.0f, greg = 0.0f;   // upstream scalars of the image: read once the object tile is `ready`
     float Sv = 0.0f;   // S[v]: the G partials the pre-pass left (same order in every thread of the part)
     {
       const float* sp = smem + L.SPART + par * T + v;
       for (int kk = 0; kk < G; ++kk) Sv += sp[kk * V];
     }
-    if (k == 0 && active && out.g_presence)
-      out.g_presence[(size_t)b * V + v] = gll * lds_f32(st + 4u * (unsigned)L.lse + 4u * (((unsigned)b * Vmod) & 3u) + 4u * (unsigned)v);
     // the [7][P] tile is single-buffered: every thread must have finished the previous image's phase B
     if (i > 0) mbar_wait(b3_bdone(bar0, par ^ 1), (unsigned)(((i - 1) >> 1) & 1));
 
@@ -355,6 +396,14 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       }
       PoseAffine pa;
       pose_affine_mufu<kSim>(t, pa);
+      if (j == 0) {
+        mbar_wait(b3_ready(bar0, par), (unsigned)((i >> 1) & 1));   // the image's object tile and scalars are there
+        const float gll = smem[L.SC + par * 4];
+        greg = smem[L.SC + par * 4 + 1];
+        gllp = gll * pres;
+        if (k == 0 && out.g_presence)
+          out.g_presence[(size_t)b * V + v] = gll * lds_f32(st + 4u * (unsigned)L.lse + 4u * (((unsigned)b * Vmod) & 3u) + 4u * (unsigned)v);
+      }
       const float4 r0 = lds_f32x4(st + r_off + (unsigned)j * strideR), r1 = lds_f32x4(st + r_off + (unsigned)j * strideR + 16);
       const float4 os = lds_f32x4(st + os_off + (unsigned)j * strideO);
       const float r[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
@@ -380,8 +429,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
         diff[c] = xv[c] - vt[c];
         q = fmaf(diff[c], diff[c], q);
       }
-      const float pst = lds_f32(st + L.post4 + pbase + (unsigned)j * T4);
-      const float h = have_gpost ? lds_f32(st + L.gpost4 + pbase + (unsigned)j * T4) : 0.0f;
+      const float pst = lds_f32(pgp + (unsigned)j * T4);
+      const float h = have_gpost ? lds_f32(pgp + L.gpost4 + (unsigned)j * T4) : 0.0f;
       const float g_pl = pst * (h - Sv) + gllp * pst;
       float g_vp = 0.0f;
       if (kExtras && up.g_vote_presence) g_vp += __ldg(up.g_vote_presence + e);
@@ -437,14 +486,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     }
     fence_proxy_async();   // the gradient block is read by the bulk store issued after the barrier
 
-    // ---- staging (last warp): the next image's object tile (its loads were issued at least one phase ago) -----------------
-    if (stager && i + 1 < n_mine) {
-      mbar_wait(b3_full(bar0, sn), par_n);
-      __syncwarp();
-      caps3_bwd_object_tile<kSim>(a, up, L, smem, sn, blockIdx.x + (i + 1) * gridDim.x, i + 1, lane);
-    }
     // ---- pre-pass of the next image ---------------------------------------------------------------------------------------
-    if (i + 1 < n_mine) pre_pass(i + 1, sn, par_n);
+    if (i + 1 < n_mine) pre_pass(i + 1);
     if (tid == 0) bulk_wait_all();   // the previous image's bulk store (issued a whole pass ago) has completed
     named_bar_sync(kB3Bar, (unsigned)Tpad);   // the image's only barrier
 
@@ -458,6 +501,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
         bulk_commit();
       }
       bulk_run_edges_out(gdst, gsrc, r0, lane);
+      // the posterior ring slot of this image is free (every thread finished its main pass): it takes image i + kB3PG
+      if (i + kB3PG < n_mine)
+        caps3_bwd_issue_pg(sv, up, L, smem, bar0, i % kB3PG, blockIdx.x + (i + kB3PG) * gridDim.x, P, lane);
     }
     // two threads per (object, slot), taken from the top warps down (warps 0 and 1 are busy above): each sums half of the
     // object's V entries of RED7[slot]; uniform trip count: the shuffle needs every lane
@@ -485,7 +531,15 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     if (warp == 0 && i + S < n_mine) {   // once the block has been read out of the stage, the stage takes image i + S
       if (lane == 0) bulk_wait_read_all();
       __syncwarp();
-      caps3_bwd_issue(a, sv, up, L, smem, bar0, s, blockIdx.x + (i + S) * gridDim.x, lane);
+      caps3_bwd_issue(a, sv, L, smem, bar0, s, blockIdx.x + (i + S) * gridDim.x, lane);
+    }
+    if (stager && i + 1 < n_mine) {
+      // the next image's object tile, from the inputs copied during this pass; the other warps pick it up through `ready`
+      // (this dependent chain runs beside the capsule-level chain of warp 1 instead of delaying the barrier)
+      cp_async_wait<0>();
+      caps3_bwd_object_tile<kSim>(a, up, L, smem, sn, i + 1, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b3_ready(bar0, par ^ 1));
     }
     if (warp == chain_warp) {
       // the previous image's bulk store completed before this image's barrier (lane 0 of warp 0 waited for it), so its
@@ -551,7 +605,7 @@ static bool caps3_plan_bwd(const scae_caps_args* a, const scae_caps_upstream* up
     const int T = G * V, threads = (T + 31) & ~31;
     if (threads > 640) continue;
     const double eff = (double)O / ((double)G * NP);
-    int S = force_s >= 2 && force_s <= kB3MaxStages ? force_s : 3;   // 2 are enough to keep one image in flight; 3 give slack
+    int S = force_s >= 2 && force_s <= kB3MaxStages ? force_s : 3;
     Caps3BwdLayout L = caps3_bwd_layout(a, up, G, NP, S);
     while (S > 2 && (size_t)L.total * sizeof(float) > (size_t)budget) L = caps3_bwd_layout(a, up, G, NP, --S);
     if ((size_t)L.total * sizeof(float) > (size_t)budget) continue;
@@ -563,8 +617,8 @@ static bool caps3_plan_bwd(const scae_caps_args* a, const scae_caps_upstream* up
   return found;
 }
 
-static int caps3_bwd_grid(const scae_caps_args* a) {
-  const int sms = sm_count();
+static int caps3_bwd_grid(const scae_caps_args* a) {   // an upper bound: two CTAs per SM for the small shapes
+  const int sms = 2 * sm_count();
   return a->B < sms ? a->B : sms;
 }
 
@@ -593,26 +647,25 @@ int caps3_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_
   Caps3BwdPlan plan;
   if (!caps3_plan_bwd(a, up, &plan)) return SCAE_OK;
   const int O = a->O, V = a->V, A = 8 * V + 7, n = O * A;
-  // Edge floats of a misaligned run are stored by the issuing warp (warp 0, after the barrier of image i) and first read
-  // in iteration i + S - 1 before its barrier: only a ring of three or more stages puts a barrier in between.
-  const bool edges = ((O * A) | (O * V) | (V * 6) | V | O) & 3;
-  if (edges && plan.L.S < 3) return SCAE_OK;
-  const int grid = caps3_bwd_grid(a);
-  if (workspace_bytes < (size_t)grid * n * sizeof(float)) return SCAE_OK;
+  if (workspace_bytes < caps3_bwd_workspace_bytes(a)) return SCAE_OK;
   const bool sim = (a->flags & SCAE_CAPS_SIMILARITY) != 0;
   void (*kern)(const scae_caps_args, const scae_caps_saved, const scae_caps_upstream, const Caps3BwdOut,
                const Caps3BwdLayout) = nullptr;
   const bool extras = up->g_vote_presence || up->g_mixing_logit || up->g_vote || up->g_scale || up->g_presence_logit_per_vote;
-#define B3_PICK(NP_, MAXT_)                                                                                     \
-  (sim ? (extras ? caps3_bwd_kernel<true, NP_, MAXT_, 1, true> : caps3_bwd_kernel<true, NP_, MAXT_, 1, false>)  \
-       : (extras ? caps3_bwd_kernel<false, NP_, MAXT_, 1, true> : caps3_bwd_kernel<false, NP_, MAXT_, 1, false>))
-  if (plan.NP == 1) kern = B3_PICK(1, 640);
-  else if (plan.NP == 2) kern = B3_PICK(2, 640);
-  else kern = B3_PICK(4, 512);
+#define B3_PICK(NP_, MAXT_, MINB_)                                                                                      \
+  (sim ? (extras ? caps3_bwd_kernel<true, NP_, MAXT_, MINB_, true> : caps3_bwd_kernel<true, NP_, MAXT_, MINB_, false>)  \
+       : (extras ? caps3_bwd_kernel<false, NP_, MAXT_, MINB_, true> : caps3_bwd_kernel<false, NP_, MAXT_, MINB_, false>))
+  const bool two = !extras && plan.NP == 1 && plan.threads <= 416 && 2 * (plan.smem + 1024) <= 228u * 1024u;   // two CTAs per SM
+  if (two) kern = B3_PICK(1, 416, 2);
+  else if (plan.NP == 1) kern = B3_PICK(1, 640, 1);
+  else if (plan.NP == 2) kern = B3_PICK(2, 640, 1);
+  else kern = B3_PICK(4, 512, 1);
 #undef B3_PICK
   if (plan.NP == 4 && plan.threads > 512) return SCAE_OK;
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int grid = sm_count() * (two ? 2 : 1);
+  if (grid > a->B) grid = a->B;
   float* partials = static_cast<float*>(workspace);
   Caps3BwdOut out{g_all_param, g_presence, partials};
   kern<<<grid, plan.threads, plan.smem, stream>>>(*a, *saved, *up, out, plan.L);
