@@ -142,3 +142,30 @@ def test_flat_rmsprop_assign_mode_matches_torch_rmsprop():
     assert all(p.untyped_storage().data_ptr() == base for p in model.parameters())
     model.load_state_dict(ref.state_dict())
     assert all(p.untyped_storage().data_ptr() == base for p in model.parameters())
+
+
+def test_flat_bucket_parameter_unused_in_a_later_step():
+    """A parameter with a gradient in step 1 and none in step 2 must not see its old gradient again (torch.optim skips
+    p.grad None: parameter, square average and momentum stay put)."""
+    from torch_scae_b200 import ddp
+    torch.manual_seed(5)
+    ref = nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 3), nn.Linear(3, 2))
+    model = nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 3), nn.Linear(3, 2))
+    model.load_state_dict(ref.state_dict())
+    ropt = torch.optim.RMSprop(ref.parameters(), lr=1e-2, momentum=0.9, eps=1e-3)
+    bucket = ddp.FlatGradBucket(model, assign=True, flat_params=True)
+    opt = ddp.FlatRMSprop(bucket, lr=1e-2, momentum=0.9, eps=1e-3)
+    data, t3, t2 = torch.randn(8, 6), torch.randn(8, 3), torch.randn(8, 2)
+    for use_last in (True, False, False, True):
+        ropt.zero_grad()
+        out = ref(data) if use_last else ref[:3](data)
+        ((out - (t2 if use_last else t3)) ** 2).mean().backward()
+        ropt.step()
+        bucket.zero()
+        out = model(data) if use_last else model[:3](data)
+        ((out - (t2 if use_last else t3)) ** 2).mean().backward()
+        bucket.collect()
+        bucket.all_reduce_mean()
+        opt.step()
+        for (k, a), b in zip(ref.state_dict().items(), model.state_dict().values()):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), (k, use_last)

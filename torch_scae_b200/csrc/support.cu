@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, con
       float ss[4] = {sv.x, sv.y, sv.z, sv.w}, pp[4] = {pv.x, pv.y, pv.z, pv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        if (gg[k] != gg[k]) continue;   // NaN = "no gradient this step": parameter and state untouched (torch.optim skips p.grad None)
         ss[k] = fmaf(1.0f - alpha, gg[k] * gg[k], ss[k] * alpha);
         const float step = __fdiv_rn(gg[k], sqrtf(ss[k]) + eps);
         if (buf) {
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, con
     } else {
       for (long j = i; j < n; ++j) {
         const float gj = g[j];
+        if (gj != gj) continue;
         const float s = fmaf(1.0f - alpha, gj * gj, sq[j] * alpha);
         sq[j] = s;
         const float step = __fdiv_rn(gj, sqrtf(s) + eps);

@@ -60,13 +60,23 @@ class FlatGradBucket:
         """assign mode: gradients -> flat buffer (one multi-tensor copy); no-op otherwise."""
         if not self.assign:
             return
-        src, dst = [], []
+        src, dst, stale = [], [], []
         for p, view in zip(self.params, self.views):
-            if p.grad is not None and p.grad is not view:
+            if p.grad is None:
+                stale.append(view)                 # unused this step: its slot must not keep the previous gradient
+            elif p.grad is not view:
                 src.append(p.grad)
                 dst.append(view)
         if src:
             torch._foreach_copy_(dst, src)
+        if stale:
+            # torch.optim skips parameters without a gradient; the flat optimizer and the all-reduce see the whole
+            # buffer, so such slots must not keep the previous step's gradient.  Single process: they are marked NaN, which
+            # FlatRMSprop treats as "skip" (parameter, square average and momentum untouched, exactly like torch.optim);
+            # several ranks: zero, the value DDP reduces for an unused parameter.  One multi-tensor launch, graph-safe.
+            torch._foreach_zero_(stale)
+            if self.world == 1:
+                torch._foreach_add_(stale, float('nan'))
         for p, view in zip(self.params, self.views):
             if p.grad is not None:
                 p.grad = view                      # readers of .grad see the (reduced) bucket contents
@@ -110,12 +120,16 @@ class FlatRMSprop:
         b = self.bucket
         if not b.flat.is_cuda:
             # host-side logic tests (gloo): the same arithmetic with torch ops
-            self.square_avg.mul_(self.alpha).addcmul_(b.flat, b.flat, value=1 - self.alpha)
-            step = b.flat / (self.square_avg.sqrt() + self.eps)
+            live = ~torch.isnan(b.flat)                          # NaN = no gradient this step (FlatGradBucket.collect)
+            g = torch.where(live, b.flat, torch.zeros_like(b.flat))
+            sq = self.square_avg * self.alpha + (1 - self.alpha) * g * g
+            self.square_avg.copy_(torch.where(live, sq, self.square_avg))
+            step = g / (self.square_avg.sqrt() + self.eps)
             if self.momentum_buffer is not None:
-                self.momentum_buffer.mul_(self.momentum).add_(step)
+                buf = self.momentum_buffer * self.momentum + step
+                self.momentum_buffer.copy_(torch.where(live, buf, self.momentum_buffer))
                 step = self.momentum_buffer
-            b.flat_param.add_(step, alpha=-self.lr)
+            b.flat_param.add_(torch.where(live, step, torch.zeros_like(step)), alpha=-self.lr)
             return
         _lib.check(ops._timed('scae_rmsprop_step', lib.scae_rmsprop_step, _lib.ptr(b.flat_param), _lib.ptr(b.flat),
                               _lib.ptr(self.square_avg), _lib.ptr(self.momentum_buffer), b.flat.numel(), self.lr,
