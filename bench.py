@@ -2,12 +2,15 @@
 """SCAE train-step benchmark on synthetic MNIST-shaped data (BASELINE.json metric: train images/sec; likelihood-kernel
 achieved GB/s vs the measured HBM peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's fused sm_100a path
-    python bench.py --impl reference [--steps K] [--warmup W]        # the reference's CPU path (oracle port), host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config mnist32|mnist10|stress|color]   # the fused sm_100a path
+    python bench.py --impl reference [--steps K] [--warmup W]     # the UNMODIFIED reference (baseline/_ref) on the host cores
 
 A "step" = forward + SCAE.loss + backward + (gradient all-reduce) + RMSprop update on one batch of 1024 images per GPU
 (BASELINE.json configs[1]; weak scaling: 8 GPUs = configs[2]'s global batch 8192).  Timing: CUDA events on the
-launching stream bracketed by barrier + synchronize, max over ranks.  Prints ONE JSON line on rank 0.
+launching stream bracketed by barrier + synchronize, max over ranks.  Prints ONE JSON line on rank 0.  `extra` carries the
+other BASELINE configs (whole-step images/s of the 10-capsule, likelihood-stress and colour models), the class-default
+vote_type='soft' step, the strong-scaling point at global batch 8192 (N > 1) and the reference moved to the same GPU
+("gpu_before"); `cpu_baseline` the reference on the box's host cores with its two hot-path regions timed in isolation.
 """
 import argparse
 import json
@@ -32,9 +35,32 @@ def model_params(n_obj_caps):
                 scae_params=dict(reconstruct_alternatives=False))
 
 
-def workload_name(n_obj_caps, batch):
-    return (f'MNIST SCAE default (mnist.yaml: 1x40x40, 40 part caps, {n_obj_caps} obj caps, 11x11 templates), '
-            f'batch {batch} per GPU, fwd+loss+bwd+RMSprop, synthetic data')
+# BASELINE.json configs: name -> (factory parameters, kernel shape, description)
+CONFIGS = {
+    'mnist32': (model_params(32), dict(M=40, C=1, h=11, w=11, H=40, W=40, O=32),
+                'MNIST SCAE default (mnist.yaml: 1x40x40, 40 part caps, 32 obj caps, 11x11 templates)'),
+    'mnist10': (model_params(10), dict(M=40, C=1, h=11, w=11, H=40, W=40, O=10),
+                "MNIST SCAE with BASELINE.json's parenthetical 10 obj caps (1x40x40, 40 part caps, 11x11 templates)"),
+    'stress': (dict(image_shape=(1, 64, 64), n_classes=10, n_part_caps=64, n_obj_caps=32,
+                    pcae_template_generator_params=dict(template_size=(21, 21)),
+                    scae_params=dict(reconstruct_alternatives=False)),
+               dict(M=64, C=1, h=21, w=21, H=64, W=64, O=32),
+               'likelihood-stress SCAE (BASELINE configs[3]: 1x64x64, 64 part caps, 32 obj caps, 21x21 templates)'),
+    'color': (dict(image_shape=(3, 32, 32), n_classes=10, n_part_caps=24, n_obj_caps=32,
+                   scae_params=dict(reconstruct_alternatives=False)),
+              dict(M=24, C=3, h=11, w=11, H=32, W=32, O=32),
+              'SVHN/CIFAR-shaped colour SCAE (BASELINE configs[4]: 3x32x32, 24 part caps, 32 obj caps, 11x11 templates)'),
+}
+
+
+def config_of(args):
+    if args.config:
+        return args.config
+    return 'mnist10' if args.n_obj_caps == 10 else 'mnist32'
+
+
+def workload_name(config, batch):
+    return f'{CONFIGS[config][2]}, batch {batch} per GPU, fwd+loss+bwd+RMSprop, synthetic data'
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -66,8 +92,8 @@ def algorithmic_bytes(M=40, C=1, h=11, w=11, H=40, W=40, O=32, fused_color=False
 ISSUE_LANE_INSTR = dict(scae_tmpl_ll_fwd=50, scae_tmpl_ll_bwd=120)
 
 
-def issue_roof_ms(name, batch, sm_mhz, M=40, H=40, W=40, sms=148):
-    units = (M + 1) * H * W * batch
+def issue_roof_ms(name, batch, sm_mhz, M=40, H=40, W=40, C=1, sms=148, **_):
+    units = (M + 1) * H * W * C * batch
     return units * ISSUE_LANE_INSTR[name] / (sms * 128 * sm_mhz * 1e6) * 1e3
 
 
@@ -154,56 +180,135 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port) on the host cores
+# Reference arm: the UNMODIFIED reference (pip-installed into baseline/_ref by baseline/install_ref.sh, imported through
+# baseline/ref_loader.py) driven through its own public API -- factory.make_scae, SCAE.forward, SCAE.loss, RMSprop with
+# the experiment's hyper-parameters (base_experiment.py:47-53) -- on the host cores or, for the GPU "before" number, on
+# the same B200.  When baseline/_ref is absent (a checkout nobody ran build() on) the oracle port stands in and says so.
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_train_throughput(n_obj_caps, batch, steps, warmup, threads=None):
-    """images/s of fwd + loss + bwd + RMSprop of the oracle port (reference op sequence, per-capsule MLP loops,
-    materialised B x K x H x W tensors) on the host CPU."""
-    from oracle import scae_model
-    from torch_scae_b200 import factory
+def reference_stepper(config, batch, device):
+    """-> (step function, kind, model-or-None): one train step of the reference (kind 'reference') or the port ('port')."""
+    params, shape, _ = CONFIGS[config]
+    C, H, W = params['image_shape']
+    torch.manual_seed(42)
+    image = torch.rand(batch, C, H, W, device=device)
+    label = torch.randint(0, 10, (batch,), device=device)
+    try:
+        from baseline import ref_loader
+        ref_loader.load_reference()
+        from torch_scae import factory as ref_factory       # the reference's own factory (baseline/_ref)
+        model = ref_factory.make_scae(params).to(device).train()
+        opt = torch.optim.RMSprop(model.parameters(), lr=3e-5, momentum=0.9, eps=1e-2 / float(batch) ** 2)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            res = model(image=image)
+            loss, _ = model.loss(res, image, label)
+            loss.backward()
+            opt.step()
+        return step, 'reference', (model, image, label)
+    except ImportError:
+        from oracle import scae_model
+        from torch_scae_b200 import factory
+        cfg = factory.prepare_model_params(**params)
+        sd = {k: v.detach().clone().to(device).requires_grad_(v.is_floating_point())
+              for k, v in factory.make_scae(params).state_dict().items()}
+        opt = torch.optim.RMSprop([v for v in sd.values() if v.requires_grad], lr=3e-5, momentum=0.9,
+                                  eps=1e-2 / float(batch) ** 2)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            res = scae_model.scae_forward(sd, cfg, image, None, training=True)
+            loss, _ = scae_model.scae_loss(res, cfg, image, label)
+            loss.backward()
+            opt.step()
+        return step, 'port', None
+
+
+def cpu_train_throughput(config, batch, steps, warmup, threads=None):
+    """images/s of fwd + loss + bwd + RMSprop of the reference on the host CPU -> (images/s, ms/step, threads, kind, times)."""
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    torch.manual_seed(42)
-    params = model_params(n_obj_caps)
-    cfg = factory.prepare_model_params(**params)
-    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point())
-          for k, v in factory.make_scae(params).state_dict().items()}
-    leaves = [v for v in sd.values() if v.requires_grad]
-    opt = torch.optim.RMSprop(leaves, lr=3e-5, momentum=0.9, eps=1e-2 / float(batch) ** 2)
-    image = torch.rand(batch, 1, 40, 40)
-    label = torch.randint(0, 10, (batch,))
+    step, kind, _ = reference_stepper(config, batch, 'cpu')
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        opt.zero_grad(set_to_none=True)
-        res = scae_model.scae_forward(sd, cfg, image, None, training=True)
-        loss, _ = scae_model.scae_loss(res, cfg, image, label)
-        loss.backward()
-        opt.step()
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return batch * len(times) / total, 1000.0 * total / len(times), threads
+    return batch * len(times) / total, 1000.0 * total / len(times), threads, kind, times
+
+
+def cpu_hot_path_regions(config, batch, reps=3):
+    """the two regions the kernels replace, timed in isolation on the host CPU (reference code):
+    (a) TemplateBasedImageDecoder.forward + pdf.log_prob, forward + backward (part_decoder.py:152-243, distributions.py:41-48);
+    (b) CapsuleObjectDecoder.forward, forward + backward, with its per-capsule MLPs timed separately so that the post-MLP
+        region (object_decoder.py:160-236, :257-372) is the difference.  Returns None when only the port is available."""
+    step, kind, handle = reference_stepper(config, batch, 'cpu')
+    if kind != 'reference':
+        return None
+    model, image, label = handle
+    with torch.no_grad():
+        enc = model.part_encoder(image)
+        templates = model.template_generator(feature=enc.feature, batch_size=batch).templates
+        parts = torch.cat([enc.pose, 1. - enc.presence.unsqueeze(-1), enc.feature,
+                           templates.view(*templates.shape[:2], -1)], -1)
+        obj_encoding = model.obj_encoder(parts, enc.presence)
+    leaf = lambda t: t.detach().clone().requires_grad_(True)
+
+    def region_a():
+        t, p, pr = leaf(templates), leaf(enc.pose), leaf(enc.presence)
+        rec = model.part_decoder(templates=t, pose=p, presence=pr)
+        rec.pdf.log_prob(image).sum().backward()
+
+    def region_b():
+        h = leaf(obj_encoding)
+        res = model.obj_decoder(h, enc.pose.detach(), enc.presence.detach())
+        (res.log_prob + res.posterior_mixing_prob.sum() + res.caps_presence.sum()).backward()
+
+    layer = model.obj_decoder.capsule_layer
+
+    def region_b_mlps():
+        h = leaf(obj_encoding)
+        raw = torch.stack([layer.mlps[i](h[:, i]) for i in range(layer.n_caps)], 1)
+        ext = torch.cat([raw, torch.ones(batch, layer.n_caps, 1)], -1)
+        torch.stack([layer.caps_mlps[i](ext[:, i]) for i in range(layer.n_caps)], 1).sum().backward()
+
+    def best(fn):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts) * 1e3
+    a_ms, b_ms, mlp_ms = best(region_a), best(region_b), best(region_b_mlps)
+    return dict(batch=batch, template_decoder_log_prob_fwd_bwd_ms=round(a_ms, 1),
+                object_decoder_fwd_bwd_ms=round(b_ms, 1), object_decoder_mlps_fwd_bwd_ms=round(mlp_ms, 1),
+                object_decoder_post_mlp_fwd_bwd_ms=round(b_ms - mlp_ms, 1),
+                note='min of %d runs after one warm-up; post-MLP = object decoder - its per-capsule MLPs' % reps)
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    batch = args.cpu_batch
-    steps = args.steps if args.steps else 10
-    warmup = args.warmup if args.warmup is not None else 3
-    steps = min(steps, 20)
-    warmup = min(warmup, 3)
-    value, ms, threads = cpu_train_throughput(args.n_obj_caps, batch, steps, warmup)
-    sample = (f'{steps} timed steps of batch {batch} (bounded sample of the batch-{args.batch} workload; CPU throughput '
-              f'is batch-size independent, SURVEY.md section 6) after {warmup} warm-ups')
+    config = config_of(args)
+    batch = args.batch                                   # the GPU arm's per-GPU batch: same config on both arms
+    steps = min(args.steps if args.steps else 10, 20)    # bounded: ~3 s per 1024-image step on 8-16 host cores
+    warmup = min(args.warmup if args.warmup is not None else 3, 3)
+    value, ms, threads, kind, times = cpu_train_throughput(config, batch, steps, warmup)
+    times = sorted(times)
+    sample = (f'{steps} timed steps of batch {batch} after {warmup} warm-ups ({kind}: '
+              + ('the unmodified reference from baseline/_ref through its own factory / SCAE.forward / SCAE.loss'
+                 if kind == 'reference' else 'oracle port of the reference op sequence; baseline/_ref is absent')
+              + f'); min {1e3 * times[0]:.0f} / median {1e3 * times[len(times) // 2]:.0f} ms per step')
     line = dict(metric=METRIC, value=round(value, 2), unit=UNIT, impl='reference', n_gpus=args.gpus, steps=steps,
                 warmup=warmup, ms_per_step=round(ms, 3), higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='fp32', data='synthetic',
-                config=dict(workload=workload_name(args.n_obj_caps, args.batch), n_obj_caps=args.n_obj_caps,
-                            batch_per_step=batch),
-                cpu_baseline=dict(value=round(value, 2), unit=UNIT, cores=threads, kind='port', sample=sample),
+                config=dict(workload=workload_name(config, batch), n_obj_caps=CONFIGS[config][1]['O'],
+                            global_batch=batch, parallelism='cpu', device=f'host CPU, {threads} threads'),
+                cpu_baseline=dict(value=round(value, 2), unit=UNIT, cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=round(value, 2), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), file=RESULT_OUT, flush=True)
 
@@ -211,14 +316,74 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+class StepHarness:
+    """One model + flat gradient bucket + RMSprop + synthetic batch of a BASELINE config on this rank's GPU."""
+
+    def __init__(self, config, B, dev, rank, scae_overrides=None):
+        import copy
+        from torch_scae_b200 import ddp, factory
+        params = copy.deepcopy(CONFIGS[config][0])
+        if scae_overrides:
+            params['scae_params'] = dict(params.get('scae_params', {}), **scae_overrides)
+        self.config, self.B, self.dev = config, B, dev
+        torch.manual_seed(42)                                   # identical initial weights on every rank
+        self.model = factory.make_scae(params).to(dev).train()
+        ddp.broadcast_parameters(self.model)
+        # parameters, gradients and optimizer state live in flat buffers: gradients are assigned (not accumulated) and
+        # copied into the bucket by one multi-tensor launch, the all-reduce is one NCCL call on the bucket, and the
+        # RMSprop update (the reference's optimizer and hyper-parameters, base_experiment.py:47-53) is one kernel
+        self.bucket = ddp.FlatGradBucket(self.model, assign=True, flat_params=True)
+        self.opt = ddp.FlatRMSprop(self.bucket, lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2)
+        torch.manual_seed(42 + rank)                            # different synthetic shard per rank
+        C, H, W = params['image_shape']
+        self.host_image = torch.rand(B, C, H, W).pin_memory()
+        self.host_label = torch.randint(0, 10, (B,)).pin_memory()
+        self.image, self.label = self.host_image.to(dev), self.host_label.to(dev)
+        self.graphed, self.graph_note = None, 'disabled (--no-graph)'
+
+    def step(self, img=None, lab=None):
+        img = self.image if img is None else img
+        lab = self.label if lab is None else lab
+        self.bucket.zero()
+        res = self.model(img)
+        loss, _ = self.model.loss(res, img, lab)
+        loss.backward()
+        self.bucket.collect()
+        self.bucket.all_reduce_mean()
+        self.opt.step()
+        return loss
+
+    def capture(self, world):
+        """The whole step (zero, forward, loss, backward, optimizer; the all-reduce stays eager between two graphs when
+        world > 1) as a CUDA graph: torch_scae_b200/graph.py."""
+        from torch_scae_b200 import graph
+        try:
+            self.graphed = graph.GraphedTrainStep(self.model, self.opt, self.bucket, self.image, self.label)
+            self.graph_note = 'whole step captured' if world == 1 else 'fwd+bwd graph, eager NCCL all-reduce, optimizer graph'
+        except Exception as exc:                            # noqa: BLE001 - report and fall back to eager launches
+            self.graphed, self.graph_note = None, f'capture failed, eager launches: {type(exc).__name__}: {exc}'[:300]
+            torch.cuda.synchronize()
+
+    def run(self):
+        return self.graphed() if self.graphed is not None else self.step()
+
+    def release(self):
+        self.graphed = None
+        self.model = self.bucket = self.opt = None
+        torch.cuda.empty_cache()
+
+
 def run_gpu(args):
     import torch.distributed as dist
-    from torch_scae_b200 import ddp, factory, graph, ops
+    from torch_scae_b200 import ops
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the fused path has no CPU fallback (use --impl reference for the CPU arm)')
+    stray = [k for k in os.environ if k.startswith('SCAE_B200_') or k.startswith('SCAE_CAPS')]
+    if stray:     # development switches (A/B timing, bisecting) must not shape a benchmark number
+        raise SystemExit(f'bench.py: unset the development switches first: {stray}')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -229,32 +394,11 @@ def run_gpu(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
 
+    config = config_of(args)
+    shape = CONFIGS[config][1]
     B = args.batch
     steps = args.steps if args.steps else 50
     warmup = max(3, args.warmup if args.warmup is not None else 10)
-    torch.manual_seed(42)                                   # identical initial weights on every rank
-    model = factory.make_scae(model_params(args.n_obj_caps)).to(dev).train()
-    ddp.broadcast_parameters(model)
-    # parameters, gradients and optimizer state live in flat buffers: gradients are assigned (not accumulated) and
-    # copied into the bucket by one multi-tensor launch, the all-reduce is one NCCL call on the bucket, and the
-    # RMSprop update (the reference's optimizer and hyper-parameters, base_experiment.py:47-53) is one kernel
-    bucket = ddp.FlatGradBucket(model, assign=True, flat_params=True)
-    opt = ddp.FlatRMSprop(bucket, lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2)
-    torch.manual_seed(42 + rank)                            # different synthetic shard per rank
-    host_image = torch.rand(B, 1, 40, 40).pin_memory()
-    host_label = torch.randint(0, 10, (B,)).pin_memory()
-    image, label = host_image.to(dev), host_label.to(dev)
-    host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
-
-    def step(img, lab):
-        bucket.zero()
-        res = model(img)
-        loss, _ = model.loss(res, img, lab)
-        loss.backward()
-        bucket.collect()
-        bucket.all_reduce_mean()
-        opt.step()
-        return loss
 
     def barrier():
         if world > 1:
@@ -274,75 +418,94 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
+    h = StepHarness(config, B, dev, rank)
     for _ in range(warmup):
-        step(image, label)
-    assert bucket.check_views(), 'gradient views were replaced; flat bucket all-reduce would be stale'
-
-    # The whole step (zero, forward, loss, backward, optimizer; the all-reduce stays eager between two graphs when
-    # world > 1) replayed as a CUDA graph: torch_scae_b200/graph.py.  --no-graph keeps the eager launches.
-    graphed, graph_note = None, 'disabled (--no-graph)'
+        h.step()
+    assert h.bucket.check_views(), 'gradient views were replaced; flat bucket all-reduce would be stale'
     if not args.no_graph:
-        try:
-            graphed = graph.GraphedTrainStep(model, opt, bucket, image, label)
-            graph_note = 'whole step captured' if world == 1 else 'fwd+bwd graph, eager NCCL all-reduce, optimizer graph'
-        except Exception as exc:                            # noqa: BLE001 - report and fall back to eager launches
-            graphed, graph_note = None, f'capture failed, eager launches: {type(exc).__name__}: {exc}'[:300]
-            torch.cuda.synchronize()
+        h.capture(world)
+    graphed = h.graphed
+    host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     # (1) device-resident throughput.  The per-entry-point kernel timing brackets every C-ABI call with CUDA events on
     # the launching stream, which only exists for eager launches: with a captured step the headline is the graph replay
-    # and the kernel durations come from an eager pass over the same step right after it.
-    with ops.KernelTimer() as timer:
-        ms_eager = timed(lambda: step(image, label), steps if graphed is None else min(steps, 20))
-    kstats = timer.summary()
+    # and the kernel durations come from an eager pass over the same step right before it.
     eager_steps = steps if graphed is None else min(steps, 20)
-    ms_step = timed(lambda: graphed(), steps) if graphed is not None else ms_eager
+    with ops.KernelTimer() as timer:
+        ms_eager = timed(h.step, eager_steps)
+    kstats = timer.summary()
+    # >= 100 replays inside the timed region, whatever --steps says; `steps` is what the line reports
+    reps = max(steps, 100) if graphed is not None else steps
+    ms_step = timed(h.run, reps)
 
-    # (2) end to end: pinned host batch -> device every step, loss read back to the host every step
+    # (2) end to end: pinned host batch -> device every step, loss read back to the host every step.
     # With the captured step the input pipeline is double buffered: the pinned host batch of step i+1 is copied to a
     # device staging buffer on a side stream while step i runs (GraphedTrainStep.stage), like a prefetching data
     # loader; every timed step still moves one full batch host->device and reads its loss back.
     def e2e_step():
         if graphed is not None:
             loss = graphed()                                # consumes the staged batch
-            graphed.stage(host_image, host_label)           # next step's batch: H2D overlaps this step
+            graphed.stage(h.host_image, h.host_label)       # next step's batch: H2D overlaps this step
         else:
-            img = host_image.to(dev, non_blocking=True)
-            lab = host_label.to(dev, non_blocking=True)
-            loss = step(img, lab)
+            img = h.host_image.to(dev, non_blocking=True)
+            lab = h.host_label.to(dev, non_blocking=True)
+            loss = h.step(img, lab)
         host_loss.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()           # the user reads the loss every step
 
     if graphed is not None:
-        graphed.stage(host_image, host_label)               # batch of the first e2e step
+        graphed.stage(h.host_image, h.host_label)           # batch of the first e2e step
     for _ in range(3):
         e2e_step()
-    ms_e2e = timed(e2e_step, steps)
+    ms_e2e = timed(e2e_step, reps)
     clocks = sampler.summary() if rank == 0 else None
+    graph_note = h.graph_note
+    h2d = int(h.host_image.numel() * 4 + h.host_label.numel() * 8)
+    h.release()
+    graphed = None
 
-    # (3) O=10 variant (BASELINE.json's parenthetical) for the record, short run
+    # (3) the other BASELINE configs, the class-default vote type and the strong-scaling point: short whole-step runs
     extra = {}
-    if rank == 0 and not args.no_extra and world == 1:
-        del opt, bucket
-        graphed = None                                      # releases the captured graphs and their pool
-        m2 = factory.make_scae(model_params(10)).to(dev).train()
-        b2 = ddp.FlatGradBucket(m2, assign=True, flat_params=True)
-        o2 = ddp.FlatRMSprop(b2, lr=3e-5, momentum=0.9, eps=1e-2 / float(B) ** 2)
 
-        def step2():
-            b2.zero()
-            r = m2(image)
-            l, _ = m2.loss(r, image, label)
-            l.backward()
-            b2.collect()
-            o2.step()
+    def short_run(cfg, b, overrides=None, n=20):
+        hx = StepHarness(cfg, b, dev, rank, overrides)
         for _ in range(5):
-            step2()
-        ms2 = timed(step2, max(10, steps // 2))
-        extra['n_obj_caps_10'] = dict(value=round(B * 1000.0 / ms2, 1), unit=UNIT, ms_per_step=round(ms2, 3))
+            hx.step()
+        if not args.no_graph:
+            hx.capture(world)
+        for _ in range(3):
+            hx.run()
+        with ops.KernelTimer() as t2:
+            fast_before = ops.caps_fast_path_count()
+            hx.step()
+            fast_calls = ops.caps_fast_path_count() - fast_before
+        ms = timed(hx.run, n)
+        out = dict(value=round(b * world * 1000.0 / ms, 1), unit=UNIT, ms_per_step=round(ms, 3), batch_per_gpu=b,
+                   global_batch=b * world, cuda_graph=hx.graph_note.split(',')[0],
+                   capsule_calls_on_the_persistent_path=f'{fast_calls} of 2',
+                   kernels_ms={k: round(v[2] / v[0], 4) for k, v in t2.summary().items() if k.startswith('scae_tmpl_ll') or k.startswith('scae_caps_ll')})
+        hx.release()
+        return out
+
+    if not args.no_extra:
+        extra['configs'] = {}
+        for cfg in ('mnist32', 'mnist10', 'stress', 'color'):
+            if cfg == config:
+                continue
+            # colour: BASELINE configs[4] is batch 4096 on 8 GPUs = 512 per GPU
+            b = 512 if cfg == 'color' else 1024
+            extra['configs'][cfg] = dict(short_run(cfg, b), workload=CONFIGS[cfg][2])
+        if config == 'mnist32':
+            extra['vote_soft'] = dict(short_run('mnist32', B, dict(vote_type='soft')),
+                                      note="SCAE's class default vote_type='soft' (stacked_capsule_auto_encoder.py:31): the "
+                                           "decoder pose is the soft winner, so the capsule backward also receives "
+                                           "g_soft_winner")
+            if 8192 % world == 0:
+                extra['strong_8192'] = dict(short_run('mnist32', 8192 // world, n=10),
+                                            note='BASELINE configs[2] literally: global batch 8192 split over the ranks')
 
     if rank != 0:
         if world > 1:
@@ -350,7 +513,7 @@ def run_gpu(args):
         return
 
     peak, peak_src = measured_peaks()
-    bytes_per_image = algorithmic_bytes(O=args.n_obj_caps, fused_color=True)   # SCAE.forward colours in-kernel
+    bytes_per_image = algorithmic_bytes(fused_color=True, **shape)   # SCAE.forward colours in-kernel
     kernels = {}
     plumbing = {}
     launches = 0
@@ -366,7 +529,7 @@ def run_gpu(args):
                              algorithmic_bytes=bytes_per_image[name] * B, achieved_gbs=round(gbs, 1),
                              frac_of_hbm_peak=round(gbs / peak, 4), share_of_step=round(avg_ms / ms_step, 4))
         if name in ISSUE_LANE_INSTR:
-            t_issue = issue_roof_ms(name, B, (clocks or {}).get('sm_mhz') or 1965)
+            t_issue = issue_roof_ms(name, B, (clocks or {}).get('sm_mhz') or 1965, **shape)
             kernels[name].update(binding_roof='sm issue rate', issue_roof_ms=round(t_issue, 4),
                                  frac_of_issue_roof=round(t_issue / avg_ms, 3))
         else:
@@ -377,35 +540,67 @@ def run_gpu(args):
                     frac=kernels[dominant]['frac_of_hbm_peak'], traffic=traffic, peak_source=peak_src,
                     binding_roof=kernels[dominant]['binding_roof'],
                     frac_of_binding_roof=kernels[dominant].get('frac_of_issue_roof', kernels[dominant]['frac_of_hbm_peak']),
+                    hbm_bound_kernels={k: v['frac_of_hbm_peak'] for k, v in kernels.items() if v['binding_roof'] == 'hbm'},
                     note='path-1 kernels are fp32-issue / shared-memory bound by construction (the B x K x H x W tensor '
-                         'is never written); see DESIGN.md section 5 and the `kernels` object for all four entry points')
+                         'is never written); the HBM-shaped kernels are the two capsule ones (hbm_bound_kernels: in-step '
+                         'fraction at this batch, inputs partly L2-resident; profiles/ holds the L2-flushed B=8192 runs)')
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        v, ms_cpu, threads = cpu_train_throughput(args.n_obj_caps, args.cpu_batch, 12, 2)
-        cpu = dict(value=round(v, 2), unit=UNIT, cores=threads, kind='port',
-                   sample=f'12 timed steps of batch {args.cpu_batch} (fwd+loss+bwd+RMSprop) after 2 warm-ups, '
-                          f'{ms_cpu:.0f} ms/step; oracle port of the reference op sequence on the host CPU')
+        # (4) the reference on this box's host cores, BASELINE configs[0] (batch 128), bounded sample; its two hot-path
+        # regions in isolation; and the same reference moved to this GPU (the "before" number)
+        v, ms_cpu, threads, kind, times = cpu_train_throughput(config, args.cpu_batch, 12, 3)
+        times = sorted(times)
+        cpu = dict(value=round(v, 2), unit=UNIT, cores=threads, kind=kind,
+                   sample=f'12 timed steps of batch {args.cpu_batch} (fwd+loss+bwd+RMSprop) after 3 warm-ups, min '
+                          f'{1e3 * times[0]:.0f} / median {1e3 * times[len(times) // 2]:.0f} ms per step; '
+                          + ('the unmodified reference (baseline/_ref) through its own API' if kind == 'reference'
+                             else 'oracle port of the reference op sequence (baseline/_ref absent)')
+                          + ' on the host CPU',
+                   cpu_model=_cpu_model(), hot_path_regions=cpu_hot_path_regions(config, args.cpu_batch))
+        if not args.no_extra:
+            try:
+                step_ref, kind_ref, _ = reference_stepper(config, B, dev)
+                for _ in range(3):
+                    step_ref()
+                ms_ref = timed(step_ref, 5)
+                extra['gpu_before'] = dict(value=round(B * 1000.0 / ms_ref, 1), unit=UNIT, ms_per_step=round(ms_ref, 2),
+                                           kind=kind_ref, batch=B,
+                                           note='the reference moved to this GPU with .to(device), stock PyTorch CUDA ops, '
+                                                'eager, strict fp32; contains its per-step host->device helper copies '
+                                                '(SURVEY.md section 9), so it is a pessimistic "before"')
+            except Exception as exc:                        # noqa: BLE001
+                extra['gpu_before'] = dict(unavailable=f'{type(exc).__name__}: {exc}'[:200])
 
     value = B * world * 1000.0 / ms_step
     e2e_value = B * world * 1000.0 / ms_e2e
     line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=round(ms_step, 4), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
                 data='synthetic',
-                config=dict(workload=workload_name(args.n_obj_caps, B), n_obj_caps=args.n_obj_caps,
+                config=dict(workload=workload_name(config, B), n_obj_caps=shape['O'],
                             global_batch=B * world, parallelism=f'dp{world}', tf32=False, cuda_graph=graph_note,
-                            ms_per_step_eager=round(ms_eager, 4),
+                            ms_per_step_eager=round(ms_eager, 4), timed_replays=reps,
                             l2_policy='per-step working set (>190 MB of activations per 1024 images) exceeds the 126 MB L2',
                             note="BASELINE.json's parenthetical says 10 obj caps; the reference's mnist.yaml:4 says 32 "
-                                 "(used here); the 10-capsule variant is under extra.n_obj_caps_10"),
+                                 "(used here); the 10-capsule variant is under extra.configs.mnist10"),
                 e2e=dict(value=round(e2e_value, 1), unit=UNIT, ms_per_step=round(ms_e2e, 4),
-                         h2d_bytes_per_step=int(host_image.numel() * 4 + host_label.numel() * 8) * world,
-                         d2h_bytes_per_step=4 * world),
+                         h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=4 * world),
                 gpu_launches=launches, roofline=roofline, kernels=kernels, plumbing_kernels=plumbing, cpu_baseline=cpu,
                 clocks=clocks, extra=extra)
     print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _cpu_model():
+    try:
+        with open('/proc/cpuinfo') as f:
+            for ln in f:
+                if ln.startswith('model name'):
+                    return ln.split(':', 1)[1].strip()
+    except OSError:
+        pass
+    return 'unknown'
 
 
 RESULT_OUT = sys.stdout
@@ -430,6 +625,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=1024, help='images per GPU per step')
     ap.add_argument('--n-obj-caps', type=int, default=32)
+    ap.add_argument('--config', default=None, choices=sorted(CONFIGS), help='BASELINE config of the headline number')
     ap.add_argument('--cpu-batch', type=int, default=128, help='batch of the bounded CPU sample (BASELINE configs[0])')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true')

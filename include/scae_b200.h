@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SCAE_B200_ABI_VERSION 3
+#define SCAE_B200_ABI_VERSION 4
 
 #define SCAE_OK 0
 #define SCAE_EINVAL (-1)   /* bad shape / flag / NULL where a pointer is required / misaligned pointer */
@@ -48,6 +48,8 @@ unsigned long long scae_launch_count(void);
 /* Number of scae_caps_ll_fwd / _bwd calls (process-wide) that the TMA-staged fast path (csrc/caps_ll2.cu) served; the
  * others ran the general kernels (unsupported shape, misaligned pointers, extra upstream gradients). */
 unsigned long long scae_caps_fast_path_count(void);
+/* ... of which the persistent warp-specialised kernels (csrc/caps_ll3.cu, caps_ll3_bwd.cu) served this many. */
+unsigned long long scae_caps_persistent_path_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Hot path 1: template warp + per-pixel template-mixture Gaussian log-likelihood

@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_size_
 
 from .build import LIB_PATH
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 TMPL_MODE_ALPHA = 0
 TMPL_MODE_TEMPERATURE = 1
@@ -80,6 +80,7 @@ SYMBOLS = {
     'scae_build_arch': (c_char_p, []),
     'scae_launch_count': (c_ulonglong, []),
     'scae_caps_fast_path_count': (c_ulonglong, []),
+    'scae_caps_persistent_path_count': (c_ulonglong, []),
     'scae_tmpl_ll_fwd': (c_int, [POINTER(TmplArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'scae_tmpl_ll_bwd_workspace_bytes': (c_size_t, [POINTER(TmplArgs)]),
     'scae_tmpl_ll_bwd': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 11 + [c_size_t, c_void_p]),

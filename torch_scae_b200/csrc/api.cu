@@ -15,6 +15,8 @@ static std::atomic<unsigned long long> g_fast_path{0};   // process-wide: backwa
 
 void note_launch() { ++g_launches; }
 void note_fast_path() { g_fast_path.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<unsigned long long> g_persistent_path{0};
+void note_persistent_path() { g_persistent_path.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -148,6 +150,7 @@ SCAE_EXPORT const char* scae_build_arch(void) { return "sm_100a"; }
 SCAE_EXPORT unsigned long long scae_launch_count(void) { return scae::g_launches; }
 
 SCAE_EXPORT unsigned long long scae_caps_fast_path_count(void) { return scae::g_fast_path.load(); }
+SCAE_EXPORT unsigned long long scae_caps_persistent_path_count(void) { return scae::g_persistent_path.load(); }
 
 SCAE_EXPORT size_t scae_colsum_workspace_bytes(long rows, int cols) {
   if (!scae::colsum_shape_ok(rows, cols)) return 0;

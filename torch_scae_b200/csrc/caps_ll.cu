@@ -669,7 +669,7 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_fwd(const sca
     bool handled = false;
     if (!caps_force_v2()) {
       rc = caps3_fwd(a, out, stream, &handled);
-      if (handled) note_fast_path();
+      if (handled) note_fast_path(), note_persistent_path();
       if (rc != SCAE_OK || handled) return rc;
     }
     rc = caps2_fwd(a, out, stream, &handled);
@@ -719,7 +719,7 @@ extern "C" __attribute__((visibility("default"))) int scae_caps_ll_bwd(const sca
     if (!caps_force_v2()) {
       rc = caps3_bwd(a, saved, up, g_all_param, g_shared, g_dummy_vote, g_x, g_presence, workspace, workspace_bytes, stream,
                      &handled);
-      if (handled) note_fast_path();
+      if (handled) note_fast_path(), note_persistent_path();
       if (rc != SCAE_OK || handled) return rc;
     }
     rc = caps2_bwd(a, saved, up, g_all_param, g_shared, g_dummy_vote, g_x, g_presence, workspace, workspace_bytes, stream,

@@ -15,7 +15,8 @@ int cuda_fail(cudaError_t e, const char* what);   // records the message, return
 int sm_count();                                   // SM count of the current device (cached per device)
 int max_smem_optin();                             // max dynamic shared memory per block (opt-in) of the device
 void note_launch();                               // counts one kernel launch of this library (scae_launch_count())
-void note_fast_path();                            // counts one hot-path-2 call served by the bulk-copy fast path
+void note_fast_path();                            // counts one hot-path-2 call served by a bulk-copy fast path
+void note_persistent_path();                      // ... by the persistent kernels of caps_ll3*.cu in particular
 
 #define SCAE_CUDA_TRY(expr)                                        \
   do {                                                             \

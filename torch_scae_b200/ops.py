@@ -735,6 +735,12 @@ def _caps_args(all_param, cpr_static, biases, noise_caps, noise_vote, x, presenc
                     ptr(noise_caps), ptr(noise_vote), ptr(x), ptr(presence), ptr(dummy_vote), B, O, V, flags)
 
 
+def caps_fast_path_count():
+    """hot-path-2 calls served by the persistent kernels (csrc/caps_ll3*.cu) so far; bench.py and tests guard against
+    silent fall-backs to the older paths with it"""
+    return int(_lib.load().scae_caps_persistent_path_count())
+
+
 class CapsuleVoteLikelihood(torch.autograd.Function):
     """Everything CapsuleObjectDecoder.forward computes after the per-capsule MLPs, as one kernel per direction."""
 
