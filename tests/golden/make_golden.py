@@ -203,6 +203,36 @@ def make_scae(name, scae_kwargs, seed):
     return params
 
 
+def make_explicit_likelihood(seed=400):
+    """The reference's standalone CapsuleLikelihood on explicit vote tensors (object_decoder.py:243-372), as its own test
+    builds it (tests/test_object_decoder.py:62-112), outputs and gradients w.r.t. every input."""
+    from torch_scae.object_decoder import CapsuleLikelihood
+    torch.manual_seed(seed)
+    B, O, V, P = 3, 5, 7, 6
+    leaf = lambda *s: torch.rand(*s).requires_grad_(True)
+    vote, scale, vote_presence, dummy_vote = leaf(B, O, V, P), leaf(B, O, V), leaf(B, O, V), leaf(1, 1, V, P)
+    with torch.no_grad():
+        scale.add_(0.2)
+        vote_presence[0, 1, 2] = 0.0               # log_safe floor
+    x, presence = leaf(B, V, P), leaf(B, V)
+    res = CapsuleLikelihood(vote=vote, scale=scale, vote_presence=vote_presence, dummy_vote=dummy_vote)(x, presence)
+    out = dict(vote=_np(vote), scale=_np(scale), vote_presence=_np(vote_presence), dummy_vote=_np(dummy_vote), x=_np(x),
+               presence=_np(presence))
+    loss = 1.3 * res.log_prob
+    for k in ('winner', 'winner_presence', 'soft_winner', 'soft_winner_presence', 'posterior_mixing_prob',
+              'mixing_log_prob', 'mixing_logit'):
+        w = torch.randn_like(res[k])
+        out['weight.' + k] = _np(w)
+        loss = loss + 0.4 * (res[k] * w).sum()
+    for k, v in res.items():
+        out['out.' + k] = _np(v)
+    loss.backward()
+    for k, t in dict(vote=vote, scale=scale, vote_presence=vote_presence, dummy_vote=dummy_vote, x=x,
+                     presence=presence).items():
+        out['g_' + k] = _np(t.grad)
+    _save('capsule_likelihood_explicit', **out)
+
+
 def make_factory():
     cases = dict(
         mnist=dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=32),
@@ -224,4 +254,5 @@ if __name__ == '__main__':
         make_capsule(n, c, 200 + i)
     for i, (n, c) in enumerate(SCAE_CASES.items()):
         make_scae(n, c, 300 + i)
+    make_explicit_likelihood()
     make_factory()

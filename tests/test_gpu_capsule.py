@@ -156,6 +156,36 @@ def test_full_size_properties():
     assert rel_err(c['g_cpr_static'], 2 * a['g_cpr_static']) < 1e-5
 
 
+def test_full_size_values_vs_fp32_oracle():
+    """Values at the full training batch (B = 1024, O = 32, V = 40) against the op-for-op oracle in fp32 on the host,
+    chunked to bound its memory (about 5 MB of intermediates per image)."""
+    B, O, V = 1024, 32, 40
+    which = ('ll_per_example', 'posterior_mixing_prob', 'caps_presence', 'reg_per_example')
+    d = make_capsule_inputs(B, O, V, seed=13, dtype=torch.float32)
+    got = capsule_cuda(d, DEFAULT, which, part_grads=False)
+    keys = ('ll_per_example', 'posterior_mixing_prob', 'caps_presence', 'vote', 'soft_winner', 'mixing_log_prob',
+            'g_all_param')
+    ref = {k: [] for k in keys}
+    shared = {k: 0.0 for k in ('g_cpr_static', 'g_b0', 'g_b1', 'g_b2', 'g_b3')}
+    for b0 in range(0, B, 128):
+        part = dict(d)
+        for k in ('all_param', 'x', 'presence', 'noise_caps', 'noise_vote'):
+            part[k] = d[k][b0:b0 + 128]
+        part['up'] = {k: v[b0:b0 + 128] for k, v in d['up'].items()}
+        r = capsule_oracle(part, DEFAULT, which, dtype=torch.float32)
+        for k in keys:
+            ref[k].append(r[k])
+        for k in shared:
+            shared[k] = shared[k] + r[k]
+    for k in keys:
+        tol = TOL_GRAD if k.startswith('g_') else TOL_OUT
+        assert rel_err(got[k], torch.cat(ref[k]).reshape(got[k].shape)) < tol, k
+    for k, v in shared.items():
+        assert rel_err(got[k], v.reshape(got[k].shape)) < TOL_GRAD, k
+    from torch_scae_b200 import ops
+    assert ops.caps_fast_path_count() > 0          # ... and it was the persistent kernels that produced them
+
+
 # ---- fast path (csrc/caps_ll2.cu): pair-parallel kernels, taken when x / presence are data (SCAE training) -------------
 
 FAST_UP = ('ll_per_example', 'reg_per_example', 'posterior_mixing_prob', 'caps_presence', 'vote_presence', 'scale',

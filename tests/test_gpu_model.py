@@ -124,6 +124,60 @@ def test_mid_size_model_vs_cpu_oracle():
         assert l2_rel_err(got, sd[k].grad) < 2e-3, k
 
 
+BASELINE_MODELS = {
+    # BASELINE.json configs[3]: likelihood-stress (GEMM-form convolutions fall back to cuDNN at the 31x31 map, templates
+    # are processed in chunks by path 1, the capsule backward runs single-stage)
+    'stress': (dict(image_shape=(1, 64, 64), n_classes=10, n_part_caps=64, n_obj_caps=32,
+                    pcae_template_generator_params=dict(template_size=(21, 21)),
+                    scae_params=dict(reconstruct_alternatives=False)), 4),
+    # BASELINE.json configs[4]: colour images / templates
+    'color': (dict(image_shape=(3, 32, 32), n_classes=10, n_part_caps=24, n_obj_caps=32,
+                   scae_params=dict(reconstruct_alternatives=False)), 8),
+}
+
+
+@pytest.mark.parametrize('name', sorted(BASELINE_MODELS))
+def test_baseline_config_models_vs_cpu_oracle(name):
+    """Whole-model loss and gradients at the likelihood-stress and colour shapes of BASELINE.json against the CPU
+    oracle model (the GPU counterpart of tests/test_emulated_library.py's emulated runs of the same shapes)."""
+    from oracle import scae_model
+    from torch_scae_b200 import factory
+    import numpy as np
+    strict_fp32()
+    torch.manual_seed(1)
+    np.random.seed(1)
+    params, B = BASELINE_MODELS[name]
+    model = factory.make_scae(params)
+    with torch.no_grad():
+        for pname, p in model.named_parameters():
+            if 'templates_alpha' in pname or 'cpr_static' in pname or 'caps_bias_list' in pname:
+                p.copy_(0.1 * torch.randn_like(p))
+    cfg = factory.prepare_model_params(**params)
+    M, O = params['n_part_caps'], params['n_obj_caps']
+    image = torch.rand(B, *params['image_shape'])
+    label = torch.randint(0, 10, (B,))
+    noise = dict(part_presence=(torch.rand(B, M) - .5) * 4, caps=(torch.rand(B, O, 1) - .5) * 4,
+                 vote=(torch.rand(B, O, M) - .5) * 4)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    ref_res = scae_model.scae_forward(sd, cfg, image, noise, training=True)
+    ref_loss, ref_log = scae_model.scae_loss(ref_res, cfg, image, label)
+    ref_loss.backward()
+
+    model.to(DEV).train()
+    res = model(image.to(DEV), noise={k: v.to(DEV) for k, v in noise.items()})
+    loss, log = model.loss(res, image.to(DEV), label.to(DEV))
+    loss.backward()
+    assert rel_err(loss, ref_loss) < TOL_LL
+    for k in ref_log:
+        assert rel_err(log[k], ref_log[k]) < TOL_LL, k
+    named = dict(model.named_parameters())
+    for k in ('part_decoder.templates_alpha', 'part_decoder.bg_value', 'part_decoder.bg_mixing_logit',
+              'template_generator.template_logits', 'obj_decoder.capsule_layer.cpr_static', 'obj_encoder.fc1.weight'):
+        assert rel_err(named[k].grad, sd[k].grad) < TOL_GRAD, k
+    for k in ('part_encoder.att_conv.weight', 'part_encoder.encoder.network.0.weight'):
+        assert l2_rel_err(named[k].grad, sd[k].grad) < 2e-3, k
+
+
 def test_train_step_uses_the_capsule_fast_path_with_flat_parameters():
     """With parameters re-homed into one flat buffer (ddp.FlatGradBucket(flat_params=True)) every parameter must still be
     16-byte aligned, otherwise hot path 2 silently falls back from the bulk-copy kernels to the general ones."""

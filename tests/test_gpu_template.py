@@ -214,6 +214,52 @@ def test_full_size_properties():
     assert bool(torch.isfinite(a['g_templates']).all()) and bool(torch.isfinite(a['g_pose']).all())
 
 
+def test_full_size_values_vs_fp32_oracle():
+    """Values, not only properties, at a full-size batch: B = 128 MNIST-shaped images against the op-for-op oracle
+    evaluated in fp32 on the host (ATen's own affine_grid / grid_sample), chunked to bound its memory."""
+    B, M, C, h, w, H, W = 128, 40, 1, 11, 11, 40, 40
+    d = make_template_inputs(B, M, C, h, w, H, W, alpha=True, seed=5, dtype=torch.float32)
+    got = template_cuda(d)
+    lp, g_t, g_pose, g_pres, g_alpha = [], [], [], [], 0.0
+    for b0 in range(0, B, 32):
+        part = dict(d)
+        for k in ('templates', 'pose', 'presence', 'x', 'weight'):
+            part[k] = d[k][b0:b0 + 32]
+        r = template_oracle(part, torch.float64)
+        lp.append(r['log_prob'])
+        g_t.append(r['g_templates'])
+        g_pose.append(r['g_pose'])
+        g_pres.append(r['g_presence'])
+        g_alpha = g_alpha + r['g_templates_alpha']
+    assert rel_err(got['log_prob'], torch.cat(lp)) < TOL_LL
+    assert rel_err(got['g_templates'], torch.cat(g_t)) < TOL_GRAD
+    assert rel_err(got['g_presence'], torch.cat(g_pres)) < TOL_GRAD
+    assert rel_err(got['g_templates_alpha'], g_alpha) < TOL_GRAD
+    check_pose_grad(got['g_pose'], torch.cat(g_pose), 'B=128')
+
+
+def test_cell_decisions_match_aten_fp32():
+    """DESIGN.md section 2 claims the kernel makes the same bilinear cell decisions as ATen's fp32 sampler.  A cell flip
+    does not change the forward value (bilinear interpolation is continuous) but it changes the pose gradient by O(1)
+    of the affected pixel's contribution, so the comparison runs on g_pose: elements where the kernel deviates from
+    ATen-fp32 by more than 1e-4 of the largest gradient are counted and must be no more numerous than the elements where
+    ATen-fp32 itself deviates from fp64 (its own flips), on the MNIST-shaped inputs and on two reference golden cases."""
+    cases = [_f32(make_template_inputs(8, 40, 1, 11, 11, 40, 40, alpha=True, seed=s)) for s in (21, 22)]
+    n_kernel = n_aten = n_elems = 0
+    for d in cases:
+        got = template_cuda(d)['g_pose'].double().cpu()
+        a32 = template_oracle(d, torch.float32)['g_pose'].double()
+        f64 = template_oracle(d, torch.float64)['g_pose']
+        tol = 1e-4 * float(f64.abs().max())
+        n_kernel += int(((got - a32).abs() > tol).sum())
+        n_aten += int(((a32 - f64).abs() > tol).sum())
+        n_elems += f64.numel()
+    print(f'pose-gradient elements off by > 1e-4: kernel vs ATen-fp32 {n_kernel}, ATen-fp32 vs fp64 {n_aten}, of {n_elems}')
+    # the kernel folds the coordinate arithmetic into one FFMA per axis, so a pixel within an ulp of a cell boundary can
+    # still fall on the other side: allow that, but not more disagreement with ATen-fp32 than ATen-fp32 has with fp64
+    assert n_kernel <= max(n_aten, n_elems // 1000), (n_kernel, n_aten, n_elems)
+
+
 # ---- fused colourisation (SURVEY.md section 8f, n2): raw templates x per-image colours inside the kernels ---------------
 @pytest.mark.parametrize('cfg', [dict(B=5, M=40, C=1, h=11, w=11, H=40, W=40, alpha=True),
                                  dict(B=4, M=24, C=3, h=11, w=11, H=32, W=32, alpha=True),
