@@ -359,7 +359,7 @@ class StepHarness:
         from torch_scae_b200 import graph
         try:
             self.graphed = graph.GraphedTrainStep(self.model, self.opt, self.bucket, self.image, self.label)
-            self.graph_note = 'whole step captured' if world == 1 else 'fwd+bwd graph, eager NCCL all-reduce, optimizer graph'
+            self.graph_note = 'whole step captured' if world == 1 else f'whole step captured, {self.graphed.collective_note}'
         except Exception as exc:                            # noqa: BLE001 - report and fall back to eager launches
             self.graphed, self.graph_note = None, f'capture failed, eager launches: {type(exc).__name__}: {exc}'[:300]
             torch.cuda.synchronize()

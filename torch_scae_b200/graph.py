@@ -11,9 +11,10 @@ stream, and allocate nothing themselves (their outputs and workspaces come from 
 they are captured like any other node.  Random draws (the presence noises) use torch's graph-safe Philox offsets and
 differ on every replay, as in eager mode.
 
-With more than one rank the gradient all-reduce stays OUTSIDE the graphs (graph A: zero/forward/backward, eager NCCL
-all-reduce of the flat bucket, graph B: optimizer step) -- the collective is one call either way and keeping it eager
-avoids tying the NCCL communicator's lifetime to a captured graph.
+With more than one rank the gradient all-reduce of the flat bucket is captured INSIDE the one graph (NCCL collectives
+are capturable; the host then launches a single graph per step and the collective starts the moment the backward's last
+kernel ends instead of after a host round trip).  If the capture of the collective fails on this software stack the
+step falls back to graph A (zero/forward/backward), an eager all-reduce, graph B (optimizer step).
 """
 import torch
 
@@ -31,7 +32,8 @@ class GraphedTrainStep:
         self.model, self.optimizer, self.bucket = model, optimizer, bucket
         self.static_image = image.clone()
         self.static_label = label.clone() if label is not None else None
-        self.split = bucket.world > 1
+        self.split = False                      # True: two graphs around an eager all-reduce (the fall-back)
+        self.collective_note = 'single process' if bucket.world == 1 else ''
         self.graphs = []
         self.loss = None
         self._capture(warmup)
@@ -86,6 +88,21 @@ class GraphedTrainStep:
         self._restore(snap)
 
         pool = torch.cuda.graph_pool_handle()
+        if self.bucket.world > 1:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, capture_error_mode='thread_local'):
+                    self.loss = self._fwd_bwd()
+                    self.bucket.all_reduce_mean()
+                    self.optimizer.step()
+                self.graphs.append(g)
+                self.collective_note = 'NCCL all-reduce captured inside the graph'
+                return
+            except Exception as exc:                      # noqa: BLE001 - this stack cannot capture the collective
+                torch.cuda.synchronize()
+                self.split = True
+                self.collective_note = f'eager NCCL all-reduce between two graphs ({type(exc).__name__})'
+                self._restore(snap)
         g_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_a, pool=pool, capture_error_mode='thread_local'):
             self.loss = self._fwd_bwd()
