@@ -292,7 +292,7 @@ int scae_pose_transform(const float* t, const float* g, float* out, long rows, i
  *   - the classifier heads softmax(linear(x)) on the DETACHED caps_presence and posterior mass, both through
  *     prior_classifier (sic, :203-213), and F.cross_entropy applied to their softmax OUTPUTS (sic, :279-285).
  * O <= 64, K <= 16.  Deterministic (fixed-order batch sums).  Batch statistics are those of the B rows passed in (the
- * reference's semantics under Lightning DDP; the sync_batch_stats extension stays in PyTorch).
+ * reference's semantics under Lightning DDP); global-batch statistics: scae_loss_head_fwd_rows / _finish below.
  * ------------------------------------------------------------------------------------------------------------ */
 #define SCAE_LOSS_L2 0      /* capsule_l2_loss                                   */
 #define SCAE_LOSS_ENTROPY 1 /* capsule_entropy_loss, k = 1                       */
@@ -318,6 +318,14 @@ size_t scae_loss_head_workspace_bytes(const scae_loss_head_args* a); /* 0 when t
  * cls_prob[2,B,K] nullable = prior_cls_prob | posterior_cls_prob; stats[128] is what the backward needs. */
 int scae_loss_head_fwd(const scae_loss_head_args* a, float* terms, float* cls_prob, float* stats, void* workspace,
                        size_t workspace_bytes, scae_stream_t stream);
+/* The forward in two halves for data-parallel callers that want the between-example statistics of the GLOBAL batch
+ * (SURVEY.md section 8e): rows -> colsums[132] = [sum_b caps_presence (64) | sum_b mass / V (64) | 4 row sums]; the caller
+ * all-reduces colsums[0..127] over its ranks (one collective for the two O-float sums), sets between_constant to the
+ * global batch / n_classes, and finishes.  scae_loss_head_fwd == rows + finish on one rank. */
+int scae_loss_head_fwd_rows(const scae_loss_head_args* a, float* cls_prob, float* colsums, void* workspace,
+                            size_t workspace_bytes, scae_stream_t stream);
+int scae_loss_head_fwd_finish(const scae_loss_head_args* a, const float* colsums, float* terms, float* stats,
+                              scae_stream_t stream);
 /* g_total: DEVICE scalar, the gradient w.r.t. TOTAL.  g_caps_presence[B,O] and g_posterior[B,O,V] (nullable; written
  * only when sparsity != 0); g_cls[K*O + K] = gradient of cls_weight | cls_bias (required with label). */
 int scae_loss_head_bwd(const scae_loss_head_args* a, const float* stats, const float* g_total, float* g_caps_presence,

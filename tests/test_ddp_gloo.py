@@ -169,3 +169,66 @@ def test_flat_bucket_parameter_unused_in_a_later_step():
         opt.step()
         for (k, a), b in zip(ref.state_dict().items(), model.state_dict().values()):
             assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), (k, use_last)
+
+
+# ---- the same through the loss-head KERNELS on two GPUs: NCCL, skipped with fewer devices ---------
+def _loss_head_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    from torch_scae_b200 import ops
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    torch.manual_seed(7)
+    B, O, V, K = 16, 10, 8, 5
+    cp_full, post_full = torch.rand(B, O), torch.rand(B, O, V)
+    label_full = torch.randint(0, K, (B,))
+    head = nn.Linear(O, K)
+    weights = (0.7, 0.9, 1.3, 0.4)
+    results = {}
+    for pt, qt in (('l2', 'entropy'), ('entropy', 'kl'), ('kl', 'l2')):
+        sl = slice(rank * B // world, (rank + 1) * B // world)
+        cp = cp_full[sl].to(dev).requires_grad_(True)
+        post = post_full[sl].to(dev).requires_grad_(True)
+        h = nn.Linear(O, K).to(dev)
+        h.load_state_dict(head.state_dict())
+        total, terms, _ = ops.loss_head(cp, post, label_full[sl].to(dev), h, K, pt, qt, weights, None, True,
+                                        sync_batch_stats=True)
+        total.backward()
+        grads = torch.cat([cp.grad.flatten(), post.grad.flatten()]) / world      # FlatGradBucket.all_reduce_mean
+        parts = [torch.zeros_like(grads) for _ in range(world)]
+        dist.all_gather(parts, grads)
+        tsum = total.detach().clone()
+        dist.all_reduce(tsum)
+        if rank == 0:
+            cpr = cp_full.to(dev).requires_grad_(True)
+            postr = post_full.to(dev).requires_grad_(True)
+            tot_ref, terms_ref, _ = ops.loss_head(cpr, postr, label_full.to(dev), h, K, pt, qt, weights, None, True)
+            tot_ref.backward()
+            n_cp = cp.numel()
+            g_cp = torch.cat([p[:n_cp].view(-1, O) for p in parts])
+            g_post = torch.cat([p[n_cp:].view(-1, O, V) for p in parts])
+            rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+            results[pt + '/' + qt] = dict(total=rel(tsum / world, tot_ref.detach()), g_cp=rel(g_cp, cpr.grad),
+                                          g_post=rel(g_post, postr.grad),
+                                          between=rel(terms[[1, 3]], terms_ref[[1, 3]]))
+    if rank == 0:
+        torch.save(results, out)
+    dist.destroy_process_group()
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two CUDA devices')
+def test_sync_batch_stats_loss_head_kernels_world2(tmp_path):
+    """sync_batch_stats=True through scae_loss_head_fwd_rows -> all-reduce -> _finish and the world-scaled backward: two
+    ranks on half the batch each reproduce the single-process loss head on the whole batch."""
+    out = str(tmp_path / 'loss_head.pt')
+    mp.spawn(_loss_head_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    for kind, r in res.items():
+        assert r['between'] < 1e-5 and r['g_cp'] < 1e-4 and r['g_post'] < 1e-4, (kind, r)
+        # the within terms and cross-entropies are means over the shard: their rank average is the global mean
+        assert r['total'] < 1e-5, (kind, r)

@@ -3,6 +3,7 @@ import pytest
 import torch
 
 from conftest import rel_err
+from gpu_util import DEV
 
 pytestmark = pytest.mark.gpu
 
@@ -468,3 +469,32 @@ def test_nchw_rows_transposes(B, C, H, W):
     up = torch.randn(B * H * W, C, device='cuda')
     (gx,) = torch.autograd.grad((rows * up).sum(), [x])
     assert torch.equal(gx, up.view(B, H, W, C).permute(0, 3, 1, 2))
+
+
+def test_loss_head_split_forward_equals_the_fused_one():
+    """scae_loss_head_fwd_rows + scae_loss_head_fwd_finish (the halves a data-parallel caller all-reduces between) give the
+    terms and statistics of scae_loss_head_fwd bit for bit on one rank."""
+    import ctypes
+    from torch_scae_b200 import _lib, ops
+    lib = _lib.load()
+    torch.manual_seed(3)
+    B, O, V, K = 37, 32, 40, 10
+    cp, post = torch.rand(B, O, device=DEV), torch.rand(B, O, V, device=DEV)
+    label = torch.randint(0, K, (B,), device=DEV)
+    w, b = torch.randn(K, O, device=DEV), torch.randn(K, device=DEV)
+    args = _lib.LossHeadArgs(_lib.ptr(cp), _lib.ptr(post), _lib.ptr(label), _lib.ptr(w), _lib.ptr(b), B, O, V, K,
+                             1, _lib.LOSS_TYPES['l2'], _lib.LOSS_TYPES['entropy'], 0.7, 0.9, 1.3, 0.4, 3.2, 3.2, B / K)
+    ws_bytes = lib.scae_loss_head_workspace_bytes(ctypes.byref(args))
+    ws = torch.empty(ws_bytes, device=DEV, dtype=torch.uint8)
+    terms = [torch.zeros(8, device=DEV) for _ in range(2)]
+    stats = [torch.zeros(128, device=DEV) for _ in range(2)]
+    probs = [torch.zeros(2, B, K, device=DEV) for _ in range(2)]
+    _lib.check(lib.scae_loss_head_fwd(ctypes.byref(args), _lib.ptr(terms[0]), _lib.ptr(probs[0]), _lib.ptr(stats[0]),
+                                      _lib.ptr(ws), ws_bytes, ops._stream()), 'fwd')
+    colsums = torch.zeros(132, device=DEV)
+    _lib.check(lib.scae_loss_head_fwd_rows(ctypes.byref(args), _lib.ptr(probs[1]), _lib.ptr(colsums), _lib.ptr(ws),
+                                           ws_bytes, ops._stream()), 'rows')
+    _lib.check(lib.scae_loss_head_fwd_finish(ctypes.byref(args), _lib.ptr(colsums), _lib.ptr(terms[1]),
+                                             _lib.ptr(stats[1]), ops._stream()), 'finish')
+    assert torch.equal(terms[0], terms[1]) and torch.equal(stats[0], stats[1]) and torch.equal(probs[0], probs[1])
+    assert rel_err(colsums[:O], cp.sum(0)) < 1e-6 and rel_err(colsums[64:64 + O], post.sum(-1).sum(0) / V) < 1e-6

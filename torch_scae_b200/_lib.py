@@ -107,6 +107,8 @@ SYMBOLS = {
     'scae_loss_head_workspace_bytes': (c_size_t, [POINTER(LossHeadArgs)]),
     'scae_loss_head_fwd': (c_int, [POINTER(LossHeadArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'scae_loss_head_bwd': (c_int, [POINTER(LossHeadArgs)] + [c_void_p] * 6 + [c_size_t, c_void_p]),
+    'scae_loss_head_fwd_rows': (c_int, [POINTER(LossHeadArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'scae_loss_head_fwd_finish': (c_int, [POINTER(LossHeadArgs), c_void_p, c_void_p, c_void_p, c_void_p]),
     'scae_rmsprop_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_float, c_float, c_float, c_float,
                                   c_void_p]),
     'scae_attnpool_fwd': (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p]),

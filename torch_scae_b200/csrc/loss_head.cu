@@ -471,6 +471,44 @@ SCAE_EXPORT int scae_loss_head_fwd(const scae_loss_head_args* a, float* terms, f
   return SCAE_OK;
 }
 
+// The forward in two halves, so that a data-parallel caller can sum the batch-global column statistics over its ranks in
+// between (the two O-float all-reduces of the between-example sparsity terms):
+//   rows   : per-row terms + this shard's column sums -> colsums[2 * 64 + 4] = [sum_b caps_presence | sum_b mass / V |
+//            sum of prior within, posterior within, prior xe, posterior xe over the rows]
+//   finish : terms / stats from (possibly all-reduced) colsums; a->between_constant is the GLOBAL batch / n_classes
+SCAE_EXPORT int scae_loss_head_fwd_rows(const scae_loss_head_args* a, float* cls_prob, float* colsums, void* workspace,
+                                        size_t workspace_bytes, scae_stream_t stream_) {
+  using namespace scae;
+  SCAE_REQUIRE(head_shape_ok(a), SCAE_ELIMIT, "loss_head: needs B, V > 0, 0 < O <= %d, K <= %d and known loss types",
+               kHeadMaxO, kHeadMaxK);
+  SCAE_REQUIRE(a->caps_presence && a->posterior && colsums, SCAE_EINVAL,
+               "loss_head: caps_presence, posterior and colsums are required");
+  SCAE_REQUIRE(a->label == nullptr || (a->cls_weight && a->cls_bias), SCAE_EINVAL,
+               "loss_head: labels need the classifier weight and bias");
+  SCAE_REQUIRE(workspace && workspace_bytes >= head_workspace_floats(a) * sizeof(float), SCAE_EINVAL,
+               "loss_head: workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int grid = head_grid(a->B);
+  const int vec = (a->V % 4 == 0) && aligned16(a->posterior);
+  float* partials = static_cast<float*>(workspace);
+  loss_head_fwd_kernel<<<grid, 32 * kHeadWarps, 0, stream>>>(*a, cls_prob, partials, vec);
+  note_launch();
+  SCAE_CUDA_TRY(cudaGetLastError());
+  return launch_reduce_rows(partials, colsums, grid, kHeadStat, stream);
+}
+
+SCAE_EXPORT int scae_loss_head_fwd_finish(const scae_loss_head_args* a, const float* colsums, float* terms, float* stats,
+                                          scae_stream_t stream_) {
+  using namespace scae;
+  SCAE_REQUIRE(head_shape_ok(a), SCAE_ELIMIT, "loss_head: needs B, V > 0, 0 < O <= %d, K <= %d and known loss types",
+               kHeadMaxO, kHeadMaxK);
+  SCAE_REQUIRE(colsums && terms && stats, SCAE_EINVAL, "loss_head: colsums, terms and stats are required");
+  loss_head_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(*a, colsums, 1, terms, stats);
+  note_launch();
+  SCAE_CUDA_TRY(cudaGetLastError());
+  return SCAE_OK;
+}
+
 SCAE_EXPORT int scae_loss_head_bwd(const scae_loss_head_args* a, const float* stats, const float* g_total,
                                    float* g_caps_presence, float* g_posterior, float* g_cls, void* workspace,
                                    size_t workspace_bytes, scae_stream_t stream_) {

@@ -445,7 +445,10 @@ class _LossHead(torch.autograd.Function):
     """Sparsity losses + classifier cross-entropies of SCAE.loss on the outputs of hot path 2 (csrc/loss_head.cu)."""
 
     @staticmethod
-    def forward(ctx, caps_presence, posterior, label, weight, bias, cfg):
+    def forward(ctx, caps_presence, posterior, label, weight, bias, cfg, world=1):
+        """``world`` > 1: the between-example statistics are those of the global batch -- the shard's column sums are
+        all-reduced between the two halves of the forward (cfg's between_constant is then the global batch / n_classes)
+        and the between terms' gradients are scaled by the world size (ddp.global_stat_loss)."""
         lib = _lib.load()
         caps_presence, posterior = caps_presence.contiguous(), posterior.contiguous()
         label = label.contiguous() if label is not None else None
@@ -461,8 +464,19 @@ class _LossHead(torch.autograd.Function):
         probs = torch.empty(2, B, K, device=dev, dtype=torch.float32) if label is not None else None
         ws_bytes = lib.scae_loss_head_workspace_bytes(ctypes.byref(args))
         ws = _workspace(ws_bytes, dev)
-        check(_timed('scae_loss_head_fwd', lib.scae_loss_head_fwd, ctypes.byref(args), ptr(terms), ptr(probs),
-                     ptr(stats), ptr(ws), ws_bytes, _stream()), 'scae_loss_head_fwd')
+        if world > 1:
+            import torch.distributed as dist
+            colsums = torch.empty(132, device=dev, dtype=torch.float32)
+            check(_timed('scae_loss_head_fwd', lib.scae_loss_head_fwd_rows, ctypes.byref(args), ptr(probs), ptr(colsums),
+                         ptr(ws), ws_bytes, _stream()), 'scae_loss_head_fwd_rows')
+            dist.all_reduce(colsums[:128], op=dist.ReduceOp.SUM)     # both O-float column sums in one collective
+            check(lib.scae_loss_head_fwd_finish(ctypes.byref(args), ptr(colsums), ptr(terms), ptr(stats), _stream()),
+                  'scae_loss_head_fwd_finish')
+            # averaged over ranks, a term every rank computes from global statistics would weigh 1 / world
+            cfg = cfg[:4] + (cfg[4] * world,) + cfg[5:6] + (cfg[6] * world,) + cfg[7:]
+        else:
+            check(_timed('scae_loss_head_fwd', lib.scae_loss_head_fwd, ctypes.byref(args), ptr(terms), ptr(probs),
+                         ptr(stats), ptr(ws), ws_bytes, _stream()), 'scae_loss_head_fwd')
         saved = [caps_presence, posterior, stats] + ([label, weight, bias] if label is not None else [])
         ctx.save_for_backward(*saved)
         ctx.cfg = cfg
@@ -494,7 +508,7 @@ class _LossHead(torch.autograd.Function):
                      ptr(g_cp), ptr(g_post), ptr(g_cls), ptr(ws), ws_bytes, _stream()), 'scae_loss_head_bwd')
         g_w = g_cls[:K * O].view(K, O) if g_cls is not None else None
         g_b = g_cls[K * O:] if g_cls is not None else None
-        return g_cp, g_post, None, g_w, g_b, None
+        return g_cp, g_post, None, g_w, g_b, None, None
 
 
 LOSS_HEAD_TERMS = ('prior_within_sparsity_loss', 'prior_between_sparsity_loss', 'posterior_within_sparsity_loss',
@@ -502,7 +516,7 @@ LOSS_HEAD_TERMS = ('prior_within_sparsity_loss', 'prior_between_sparsity_loss', 
 
 
 def loss_head(caps_presence, posterior, label, classifier, n_classes, prior_type, posterior_type, weights,
-              prior_within_constant=None, sparsity=True):
+              prior_within_constant=None, sparsity=True, sync_batch_stats=False):
     """The (B,O)-sized tail of SCAE.loss (stacked_capsule_auto_encoder.py:243-285) in one kernel pair per direction:
     the prior sparsity loss on ``caps_presence`` (B,O), the posterior one on ``posterior.sum(-1) / V`` and, with
     ``label``, the cross-entropies of both classifier heads (``classifier`` = nn.Linear shared by both, sic :211; its
@@ -528,11 +542,15 @@ def loss_head(caps_presence, posterior, label, classifier, n_classes, prior_type
                 and weight.shape[1] == O and label.dtype == torch.int64 and tuple(label.shape) == (B,)):
             return None
     default_c = float(O) / n_classes if n_classes else 0.0
+    world = 1
+    if sync_batch_stats:
+        from . import ddp
+        world = ddp.world_size()
     cfg = (int(bool(sparsity)), _lib.LOSS_TYPES.get(prior_type, 0), _lib.LOSS_TYPES.get(posterior_type, 0),
            float(weights[0]), float(weights[1]), float(weights[2]), float(weights[3]),
            float(default_c if prior_within_constant is None else prior_within_constant), float(default_c),
-           float(B) / n_classes if n_classes else 0.0)
-    total, terms, probs = _LossHead.apply(caps_presence, posterior, label, weight, bias, cfg)
+           float(B * world) / n_classes if n_classes else 0.0)
+    total, terms, probs = _LossHead.apply(caps_presence, posterior, label, weight, bias, cfg, world)
     return total, terms, probs if label is not None else None
 
 

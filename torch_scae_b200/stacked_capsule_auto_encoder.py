@@ -154,7 +154,7 @@ class SCAE(nn.Module):
             return None
         sparsity = self.prior_within_example_sparsity_weight > 0 or self.prior_between_example_sparsity_weight > 0
         cp, post = res.get('caps_presence'), res.get('posterior_mixing_prob')
-        if not (torch.is_tensor(cp) and cp.is_cuda and torch.is_tensor(post)) or self.sync_batch_stats:
+        if not (torch.is_tensor(cp) and cp.is_cuda and torch.is_tensor(post)):
             return None
         if label is not None:
             head = self.prior_classifier
@@ -169,7 +169,7 @@ class SCAE(nn.Module):
                              (self.prior_within_example_sparsity_weight, self.prior_between_example_sparsity_weight,
                               self.posterior_within_example_sparsity_weight,
                               self.posterior_between_example_sparsity_weight),
-                             self.prior_within_example_constant, sparsity)
+                             self.prior_within_example_constant, sparsity, self.sync_batch_stats)
 
     def loss(self, res, reconstruction_target, label=None):
         log = dict()
