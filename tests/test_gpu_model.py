@@ -194,3 +194,21 @@ def test_train_step_uses_the_capsule_fast_path_with_flat_parameters():
     loss.backward()
     bucket.collect()
     assert lib.scae_caps_fast_path_count() - before == 2      # forward and backward
+
+
+def test_class_default_soft_votes_stay_on_the_persistent_capsule_kernels():
+    """SCAE's class defaults -- vote_type='soft' (stacked_capsule_auto_encoder.py:31), here also with gradients into the
+    part poses (stop_grad_caps_target=False) -- send g_soft_winner and g_x through the capsule backward: both calls must
+    be served by the persistent kernels (csrc/caps_ll3*.cu), not by the general path."""
+    from torch_scae_b200 import factory, ops
+    model = factory.make_scae(dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=32,
+                                   scae_params=dict(reconstruct_alternatives=False, vote_type='soft',
+                                                    presence_type='soft', stop_grad_caps_target=False))).to(DEV).train()
+    image = torch.rand(16, 1, 40, 40, device=DEV)
+    label = torch.randint(0, 10, (16,), device=DEV)
+    before = ops.caps_fast_path_count()
+    loss, _ = model.loss(model(image), image, label)
+    loss.backward()
+    assert ops.caps_fast_path_count() - before == 2
+    assert all(p.grad is None or bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+    assert float(model.obj_decoder.dummy_vote.grad.abs().max()) > 0.0

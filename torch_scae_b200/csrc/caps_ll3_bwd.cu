@@ -42,13 +42,16 @@ struct Caps3BwdLayout {
   int S, G, NP, T, Tpad, Vp;
   int stage0, stage_stride;                      // floats; the in-place ring: S stages
   int prm, nz, xs, ps, lse, R, OS;               // offsets inside a stage
+  int gsw, gswp, gw, gwp, widx;                  // ... winner-gradient variant only: upstream gradients of the soft /
+                                                 // hard winner (V x 6, V each) and the saved winner index (int64)
   int pg0, pg_stride, gpost;                     // the posterior ring: kB3PG slots of {posterior, its upstream gradient}
-  int RED7, SPART, OBJ7, OSAVE, TIN, SC, BIAS, OBJSUM, CST, total;   // CTA-wide tiles
+  int RED7, SPART, OBJ7, OSAVE, TIN, SC, BIAS, OBJSUM, CST, GX, DSUM, total;   // CTA-wide tiles
   // byte strides / offsets the hot loop uses straight from the constant bank
   unsigned strideA4, V4, T4, strideR, strideO, nz4, gpost4, red_plane, red_step;
 };
 
-static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_upstream* up, int G, int NP, int S) {
+static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_upstream* up, int G, int NP, int S,
+                                       bool soft = false, bool want_gx = false) {
   const int O = a->O, V = a->V, A = 8 * V + 7, P = O * V;
   Caps3BwdLayout L;
   L.S = S, L.G = G, L.NP = NP, L.T = G * V, L.Tpad = (L.T + 31) & ~31;
@@ -66,6 +69,11 @@ static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_
   L.lse = take(V + 4) - L.stage0;
   L.R = take(O * 8) - L.stage0;
   L.OS = take(O * 4) - L.stage0;
+  L.gsw = take(soft && up->g_soft_winner ? V * 6 + 4 : 0) - L.stage0;
+  L.gswp = take(soft && up->g_soft_winner_presence ? V + 4 : 0) - L.stage0;
+  L.gw = take(soft && up->g_winner ? V * 6 + 4 : 0) - L.stage0;
+  L.gwp = take(soft && up->g_winner_presence ? V + 4 : 0) - L.stage0;
+  L.widx = take(soft && (up->g_winner || up->g_winner_presence) ? 2 * V + 4 : 0) - L.stage0;
   L.stage_stride = at - L.stage0;
   at = L.stage0 + S * L.stage_stride;
   L.pg0 = at;
@@ -82,7 +90,11 @@ static Caps3BwdLayout caps3_bwd_layout(const scae_caps_args* a, const scae_caps_
   L.SC = take(2 * 4);             // {g_ll, g_reg} of the image, by image parity
   L.BIAS = take(O * 8);
   L.OBJSUM = take(O * 8);
-  L.CST = take(8 * L.T * NP);   // [NP][8][T]: cpr_static (6), bias_vote, bias_scale + 0.5 of the thread's pairs
+  // [NP][8][T]: cpr_static (6), bias_vote, bias_scale + 0.5 of the thread's pairs (the winner-gradient variant needs the
+  // room for its extra tiles and reads them from global memory / L2 instead)
+  L.CST = take(soft ? 0 : 8 * L.T * NP);
+  L.GX = take(want_gx ? 6 * L.T : 0);          // the threads' shares of g_x
+  L.DSUM = take(soft ? V * 6 : 0);             // batch sum of the dummy vote's gradient
   L.total = at;
   L.strideA4 = 4u * (unsigned)(G * A), L.V4 = 4u * (unsigned)V, L.T4 = 4u * (unsigned)L.T;
   L.strideR = 32u * (unsigned)G, L.strideO = 16u * (unsigned)G;
@@ -100,6 +112,8 @@ struct Caps3BwdOut {
   float* g_all_param;   // [B,O,A] final: ReLU mask and regulariser applied
   float* g_presence;    // [B,V] nullable
   float* partials;      // [grid][O*A] per-CTA batch sums of the pre-activation gradient
+  float* g_x;           // [B,V,6] nullable (winner-gradient variant)
+  float* dummy_partials;   // [grid][V*6] nullable: per-CTA batch sums of the dummy vote's gradient
 };
 
 // ---- staging (one warp): each lane owns one contiguous per-image input ----------------------------------------------------
@@ -127,8 +141,8 @@ __device__ __forceinline__ void caps3_bwd_issue_runs(const B3Run& run, unsigned 
 
 // in-place stage s <- image b: all_param block (becomes the gradient block), noise rows, part poses / presences / lse
 __device__ __forceinline__ void caps3_bwd_issue(const scae_caps_args& a, const scae_caps_saved& sv,
-                                                const Caps3BwdLayout& L, float* smem, unsigned bar0, int s, int b,
-                                                int lane) {
+                                                const scae_caps_upstream& up, bool soft, const Caps3BwdLayout& L,
+                                                float* smem, unsigned bar0, int s, int b, int lane) {
   const int O = a.O, V = a.V, A = 8 * V + 7, P = O * V;
   float* st = smem + L.stage0 + s * L.stage_stride;
   B3Run run = {nullptr, nullptr, 0};
@@ -138,6 +152,14 @@ __device__ __forceinline__ void caps3_bwd_issue(const scae_caps_args& a, const s
     case 2: run = {a.x + (size_t)b * V * 6, st + L.xs, V * 6}; break;
     case 3: if (a.presence) run = {a.presence + (size_t)b * V, st + L.ps, V}; break;
     case 4: run = {sv.log_prob_per_point + (size_t)b * V, st + L.lse, V}; break;
+    case 5: if (soft && up.g_soft_winner) run = {up.g_soft_winner + (size_t)b * V * 6, st + L.gsw, V * 6}; break;
+    case 6: if (soft && up.g_soft_winner_presence) run = {up.g_soft_winner_presence + (size_t)b * V, st + L.gswp, V}; break;
+    case 7: if (soft && up.g_winner) run = {up.g_winner + (size_t)b * V * 6, st + L.gw, V * 6}; break;
+    case 8: if (soft && up.g_winner_presence) run = {up.g_winner_presence + (size_t)b * V, st + L.gwp, V}; break;
+    case 9:
+      if (soft && (up.g_winner || up.g_winner_presence))
+        run = {reinterpret_cast<const float*>(sv.winner_idx) + (size_t)b * V * 2, st + L.widx, V * 2};
+      break;
     default: break;
   }
   caps3_bwd_issue_runs(run, b3_full(bar0, s), lane);
@@ -222,9 +244,40 @@ __device__ __forceinline__ void caps3_bwd_object_tile(const scae_caps_args& a, c
   if (lane == 1) smem[L.SC + (img & 1) * 4 + 1] = up.g_reg_per_example ? smem[L.TIN + O * kB3Tin + 1] : 0.0f;
 }
 
+// the 8 batch-shared constants of a pair: from the thread's shared-memory slots, or (kGlobal) straight from global memory
+template <bool kGlobal>
+struct C3PairConst {
+  unsigned ca, T4;
+  const float *stc, *bv, *bs;   // cpr_static + 6 p, bias_vote + p, bias_scale + p
+  __device__ __forceinline__ float get(int c) const {
+    if (!kGlobal) return lds_f32(ca + (unsigned)c * T4);
+    return c < 6 ? __ldg(stc + c) : c == 6 ? __ldg(bv) : __ldg(bs) + 0.5f;
+  }
+};
+
+// forward of one pair from its staged parameters: the vote and its presence (what the winner-gradient pre-pass needs)
+template <bool kSim, class Const>
+__device__ __forceinline__ void caps3_pair_vote(unsigned da, unsigned la, const Const& cc, unsigned ra, unsigned nza,
+                                                bool deform, bool noise, float vt[6], float& vp) {
+  float t[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) t[c] = (deform ? lds_f32(da + 4 * c) : 0.0f) + cc.get(c);
+  PoseAffine pa;
+  pose_affine_mufu<kSim>(t, pa);
+  const float4 r0 = lds_f32x4(ra), r1 = lds_f32x4(ra + 16);
+  const float r[6] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+  compose_vote(r, pa.a, vt);
+  float lv = lds_f32(la) + cc.get(6);
+  if (noise) lv += lds_f32(nza);
+  vp = r1.z * sigmoid_fast(lv);
+}
+
 // kExtras: some per-pair upstream gradient beyond the training set (vote_presence, vote, scale, presence_logit_per_vote,
 // mixing_logit) is given; without it no pointer is tested in the pair loop
-template <bool kSim, int NP, int kMaxT, int kMinB, bool kExtras>
+// kSoft: the upstream gradients of the soft / hard winner and the part-side input gradient g_x are handled (the class
+// default vote_type = 'soft'): S[v] then needs every object's vote, so the pre-pass recomputes the forward of the
+// image it is about to process and the image takes two barriers
+template <bool kSim, int NP, int kMaxT, int kMinB, bool kExtras, bool kSoft>
 __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps_args a, const scae_caps_saved sv,
                                                                  const scae_caps_upstream up, const Caps3BwdOut out,
                                                                  const Caps3BwdLayout L) {
@@ -254,6 +307,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     smem[L.BIAS + i] = c < 6 ? __ldg(a.bias_cvr + oo * 6 + c) : c == 6 ? __ldg(a.bias_caps + oo) : 0.0f;
     smem[L.OBJSUM + i] = 0.0f;
   }
+  if (kSoft)
+    for (int i = tid; i < V * 6; i += Tpad) smem[L.DSUM + i] = 0.0f;
   __syncthreads();
   const bool stager = warp == (Tpad >> 5) - 1;
   const int chain_warp = Tpad > 32 ? 1 : 0;
@@ -261,7 +316,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     caps3_bwd_tile_inputs(a, sv, up, L, smem, blockIdx.x, lane);
     for (int i = 0; i < kB3PG && i < n_mine; ++i)
       caps3_bwd_issue_pg(sv, up, L, smem, bar0, i, blockIdx.x + i * gridDim.x, P, lane);
-    for (int i = 0; i < S && i < n_mine; ++i) caps3_bwd_issue(a, sv, L, smem, bar0, i, blockIdx.x + i * gridDim.x, lane);
+    for (int i = 0; i < S && i < n_mine; ++i) caps3_bwd_issue(a, sv, up, kSoft, L, smem, bar0, i, blockIdx.x + i * gridDim.x, lane);
     cp_async_wait<0>();
     caps3_bwd_object_tile<kSim>(a, up, L, smem, 0, 0, lane);
     __syncwarp();
@@ -285,11 +340,13 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       vmask |= 1u << j;
       // the pair's batch-shared parameters: thread-private shared-memory slots [j][c][tid] (conflict-free)
       const int p = oj * V + v;
-      float* cs = smem + L.CST + j * 8 * T + tid;
+      if (!kSoft) {
+        float* cs = smem + L.CST + j * 8 * T + tid;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) cs[c * T] = __ldg(a.cpr_static + (size_t)p * 6 + c);
-      cs[6 * T] = __ldg(a.bias_vote + p);
-      cs[7 * T] = __ldg(a.bias_scale + p) + 0.5f;
+        for (int c = 0; c < 6; ++c) cs[c * T] = __ldg(a.cpr_static + (size_t)p * 6 + c);
+        cs[6 * T] = __ldg(a.bias_vote + p);
+        cs[7 * T] = __ldg(a.bias_scale + p) + 0.5f;
+      }
     }
   }
   vmask = keep(vmask);
@@ -319,7 +376,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     }
     if (active) smem[L.SPART + (img & 1) * T + tid] = part;
   };
-  if (n_mine > 0) pre_pass(0);
+  if (!kSoft && n_mine > 0) pre_pass(0);
   __syncthreads();
 
   // the capsule-level gradients of image `img` (warp 0, one lane per object) from the sums phase B left in OBJ7
@@ -363,6 +420,42 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
     if (stager && i + 1 < n_mine) caps3_bwd_tile_inputs(a, sv, up, L, smem, blockIdx.x + (i + 1) * gridDim.x, lane);
     mbar_wait(b3_full(bar0, s), parity);   // the image's in-place stage has landed
 
+    // ---- winner-gradient variant: the pre-pass of THIS image (it needs every object's vote), then a barrier -------------
+    float gsw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gswp = 0.0f, gwp = 0.0f, post_dummy = 0.0f;
+    int widx = -1;
+    if (kSoft) {
+      const unsigned vmod6 = 4u * (((unsigned)b * V6mod) & 3u), vmod1 = 4u * (((unsigned)b * Vmod) & 3u);
+      if (up.g_soft_winner) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) gsw[c] = lds_f32(st + 4u * (unsigned)L.gsw + vmod6 + 24u * (unsigned)v + 4 * c);
+      }
+      if (up.g_soft_winner_presence) gswp = lds_f32(st + 4u * (unsigned)L.gswp + vmod1 + 4u * (unsigned)v);
+      if (up.g_winner_presence) gwp = lds_f32(st + 4u * (unsigned)L.gwp + vmod1 + 4u * (unsigned)v);
+      if (up.g_winner || up.g_winner_presence)   // int64 indices: the low words
+        widx = (int)lds_u32(st + 4u * (unsigned)L.widx + 4u * (((unsigned)b * ((unsigned)(2 * V) & 3u)) & 3u) + 8u * (unsigned)v);
+      post_dummy = ex2_approx((2.0f * kDummyLog - lds_f32(st + 4u * (unsigned)L.lse + vmod1 + 4u * (unsigned)v)) * kLog2eF);
+      mbar_wait(b3_ready(bar0, par), (unsigned)((i >> 1) & 1));
+      mbar_wait(b3_pgfull(bar0, i % kB3PG), (unsigned)((i / kB3PG) & 1));
+      float part = 0.0f;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        if (!(vmask >> j & 1u)) continue;
+        float vt[6], vp;
+        const int pj = tid + j * T;
+        const C3PairConst<kSoft> cc = {cst_addr + (unsigned)j * 8u * T4, T4, a.cpr_static + (size_t)pj * 6, a.bias_vote + pj,
+                                       a.bias_scale + pj};
+        caps3_pair_vote<kSim>(prm + d_off + (unsigned)j * strideA, prm + l_off + (unsigned)j * strideA, cc,
+                              st + r_off + (unsigned)j * strideR, st + L.nz4 + pbase + (unsigned)j * T4, deform,
+                              a.noise_vote != nullptr, vt, vp);
+        float h = have_gpost ? lds_f32(pgp + L.gpost4 + (unsigned)j * T4) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) h = fmaf(gsw[c], vt[c], h);
+        h = fmaf(gswp, vp, h);
+        part = fmaf(lds_f32(pgp + (unsigned)j * T4), h, part);
+      }
+      if (active) smem[L.SPART + par * T + tid] = part;
+      named_bar_sync(kB3Bar, (unsigned)Tpad);
+    }
     // ---- per-part values -------------------------------------------------------------------------------------------------
     float xv[6];
     {
@@ -377,6 +470,13 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       const float* sp = smem + L.SPART + par * T + v;
       for (int kk = 0; kk < G; ++kk) Sv += sp[kk * V];
     }
+    if (kSoft && up.g_soft_winner) {   // the dummy component's share: posterior(dummy) * <g_soft_winner, dummy_vote>
+      float hd = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) hd = fmaf(gsw[c], __ldg(a.dummy_vote + v * 6 + c), hd);
+      Sv = fmaf(post_dummy, hd, Sv);
+    }
+    float gx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     // the [7][P] tile is single-buffered: every thread must have finished the previous image's phase B
     if (i > 0) mbar_wait(b3_bdone(bar0, par ^ 1), (unsigned)(((i - 1) >> 1) & 1));
 
@@ -387,12 +487,14 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       const unsigned da = prm + d_off + (unsigned)j * strideA;   // row[6 v + c]
       const unsigned la = prm + l_off + (unsigned)j * strideA;   // row[6 V + 7 + v]; the scale slot 4 V bytes further
       const size_t e = (size_t)b * P + tid + (size_t)j * T;      // the pair in a (B,O,V) tensor
-      const unsigned ca = cst_addr + (unsigned)j * 8u * T4;
+      const int pj = tid + j * T;
+      const C3PairConst<kSoft> cc = {cst_addr + (unsigned)j * 8u * T4, T4, a.cpr_static + (size_t)pj * 6, a.bias_vote + pj,
+                                     a.bias_scale + pj};
       float raw[6], t[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         raw[c] = lds_f32(da + 4 * c);
-        t[c] = (deform ? raw[c] : 0.0f) + lds_f32(ca + (unsigned)c * T4);
+        t[c] = (deform ? raw[c] : 0.0f) + cc.get(c);
       }
       PoseAffine pa;
       pose_affine_mufu<kSim>(t, pa);
@@ -411,11 +513,11 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       float vt[6];
       compose_vote(r, pa.a, vt);
       const float raw_lv = lds_f32(la), raw_u = lds_f32(la + V4);
-      float lv = raw_lv + lds_f32(ca + 6u * T4);
+      float lv = raw_lv + cc.get(6);
       if (a.noise_vote) lv += lds_f32(st + L.nz4 + pbase + (unsigned)j * T4);
       const float pv = sigmoid_fast(lv);
       const float vp = pc * pv;
-      const float u05 = raw_u + lds_f32(ca + 7u * T4);
+      const float u05 = raw_u + cc.get(7);
       float sc = 1.0f, dsc = 0.0f;   // scale and d scale / d u
       if (learn) {
         const float z = ex2_approx(-fabsf(u05) * kLog2eF);   // softplus(x) = max(x, 0) + log1p(e^-|x|); its slope = sigmoid(x)
@@ -430,9 +532,15 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
         q = fmaf(diff[c], diff[c], q);
       }
       const float pst = lds_f32(pgp + (unsigned)j * T4);
-      const float h = have_gpost ? lds_f32(pgp + L.gpost4 + (unsigned)j * T4) : 0.0f;
+      float h = have_gpost ? lds_f32(pgp + L.gpost4 + (unsigned)j * T4) : 0.0f;
+      const bool is_win = kSoft && (k + G * j) == widx;
+      if (kSoft) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) h = fmaf(gsw[c], vt[c], h);
+        h = fmaf(gswp, vp, h);
+      }
       const float g_pl = pst * (h - Sv) + gllp * pst;
-      float g_vp = 0.0f;
+      float g_vp = kSoft ? gswp * pst + (is_win ? gwp : 0.0f) : 0.0f;
       if (kExtras && up.g_vote_presence) g_vp += __ldg(up.g_vote_presence + e);
       if (__float_as_int(os.y) == v) g_vp += os.x;
       float g_ml = g_pl;
@@ -445,6 +553,11 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
         gv[c] = coef * diff[c];
+        if (kSoft) {
+          gx[c] = fmaf(-coef, diff[c], gx[c]);
+          gv[c] = fmaf(gsw[c], pst, gv[c]);
+          if (is_win && up.g_winner) gv[c] += lds_f32(st + 4u * (unsigned)L.gw + 4u * (((unsigned)b * V6mod) & 3u) + 24u * (unsigned)v + 4 * c);
+        }
         if (kExtras && up.g_vote) gv[c] += __ldg(up.g_vote + e * 6 + c);
       }
       float g_sc = g_pl * inv_sc * fmaf(q, inv2, -6.0f);
@@ -484,10 +597,14 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       sts_f32(la, (relu && !(raw_lv > 0.0f)) ? 0.0f : g_lv);
       sts_f32(la + V4, (relu && !(raw_u > 0.0f)) ? 0.0f : g_u);
     }
+    if (kSoft && out.g_x && active) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) smem[L.GX + c * T + tid] = gx[c];
+    }
     fence_proxy_async();   // the gradient block is read by the bulk store issued after the barrier
 
     // ---- pre-pass of the next image ---------------------------------------------------------------------------------------
-    if (i + 1 < n_mine) pre_pass(i + 1);
+    if (!kSoft && i + 1 < n_mine) pre_pass(i + 1);
     if (tid == 0) bulk_wait_all();   // the previous image's bulk store (issued a whole pass ago) has completed
     named_bar_sync(kB3Bar, (unsigned)Tpad);   // the image's only barrier
 
@@ -527,11 +644,28 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       if (on && half == 0) smem[L.OBJ7 + par * O * 8 + oo * 8 + c] = sum;
     }
+    if (kSoft) {
+      // g_x[v][c] = the object groups' shares summed; the dummy vote's gradient accumulates over the CTA's images
+      const int skip = Tpad > 64 ? 64 : 0;   // warps 0 and 1 are busy with the store and the capsule-level chain
+      for (int idx = tid - skip; idx >= 0 && idx < 6 * V; idx += Tpad - skip) {
+        const int c = idx / V, vv = idx - c * V;
+        if (out.g_x) {
+          float sum = 0.0f;
+          for (int kk = 0; kk < G; ++kk) sum += smem[L.GX + c * T + kk * V + vv];
+          out.g_x[((size_t)b * V + vv) * 6 + c] = sum;
+        }
+        if (up.g_soft_winner) {
+          const float lse_v = smem[L.stage0 + s * L.stage_stride + L.lse + (int)(((unsigned)b * Vmod) & 3u) + vv];
+          const float g = smem[L.stage0 + s * L.stage_stride + L.gsw + (int)(((unsigned)b * V6mod) & 3u) + vv * 6 + c];
+          smem[L.DSUM + vv * 6 + c] += g * ex2_approx((2.0f * kDummyLog - lse_v) * kLog2eF);
+        }
+      }
+    }
     mbar_arrive(b3_bdone(bar0, par));   // this thread is done with the [7][O][Vp] tile
     if (warp == 0 && i + S < n_mine) {   // once the block has been read out of the stage, the stage takes image i + S
       if (lane == 0) bulk_wait_read_all();
       __syncwarp();
-      caps3_bwd_issue(a, sv, L, smem, bar0, s, blockIdx.x + (i + S) * gridDim.x, lane);
+      caps3_bwd_issue(a, sv, up, kSoft, L, smem, bar0, s, blockIdx.x + (i + S) * gridDim.x, lane);
     }
     if (stager && i + 1 < n_mine) {
       // the next image's object tile, from the inputs copied during this pass; the other warps pick it up through `ready`
@@ -574,6 +708,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) caps3_bwd_kernel(const scae_caps
       const int oo = idx / 7, c = idx - oo * 7;
       dst[(size_t)oo * A + 6 * V + c] = smem[L.OBJSUM + oo * 8 + c];
     }
+    if (kSoft && out.dummy_partials)
+      for (int idx = tid; idx < V * 6; idx += Tpad) out.dummy_partials[(size_t)blockIdx.x * V * 6 + idx] = smem[L.DSUM + idx];
   }
 }
 
@@ -592,7 +728,8 @@ struct Caps3BwdPlan {
 };
 
 // G object groups x V parts threads, NP = ceil(O / G) pairs each; 20 warps at most (96 registers per thread)
-static bool caps3_plan_bwd(const scae_caps_args* a, const scae_caps_upstream* up, Caps3BwdPlan* plan) {
+static bool caps3_plan_bwd(const scae_caps_args* a, const scae_caps_upstream* up, bool soft, bool want_gx,
+                           Caps3BwdPlan* plan) {
   const int O = a->O, V = a->V;
   const int budget = max_smem_optin();
   const int force_np = b3_env_int("SCAE_CAPS3_BWD_NP", 0), force_s = b3_env_int("SCAE_CAPS3_BWD_STAGES", 0);
@@ -606,8 +743,8 @@ static bool caps3_plan_bwd(const scae_caps_args* a, const scae_caps_upstream* up
     if (threads > 640) continue;
     const double eff = (double)O / ((double)G * NP);
     int S = force_s >= 2 && force_s <= kB3MaxStages ? force_s : 3;
-    Caps3BwdLayout L = caps3_bwd_layout(a, up, G, NP, S);
-    while (S > 2 && (size_t)L.total * sizeof(float) > (size_t)budget) L = caps3_bwd_layout(a, up, G, NP, --S);
+    Caps3BwdLayout L = caps3_bwd_layout(a, up, G, NP, S, soft, want_gx);
+    while (S > 2 && (size_t)L.total * sizeof(float) > (size_t)budget) L = caps3_bwd_layout(a, up, G, NP, --S, soft, want_gx);
     if ((size_t)L.total * sizeof(float) > (size_t)budget) continue;
     if (found && (eff < best_eff - 1e-9 || (eff < best_eff + 1e-9 && T <= best_T))) continue;
     plan->NP = NP, plan->threads = threads, plan->L = L, plan->smem = (size_t)L.total * sizeof(float);
@@ -622,8 +759,8 @@ static int caps3_bwd_grid(const scae_caps_args* a) {   // an upper bound: two CT
   return a->B < sms ? a->B : sms;
 }
 
-size_t caps3_bwd_workspace_bytes(const scae_caps_args* a) {
-  return (size_t)caps3_bwd_grid(a) * a->O * (8 * a->V + 7) * sizeof(float);
+size_t caps3_bwd_workspace_bytes(const scae_caps_args* a) {   // per-CTA partial rows: [O*A] and, behind them, [V*6]
+  return (size_t)caps3_bwd_grid(a) * ((size_t)a->O * (8 * a->V + 7) + (size_t)a->V * 6) * sizeof(float);
 }
 
 int caps3_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_caps_upstream* up, float* g_all_param,
@@ -631,35 +768,45 @@ int caps3_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_
               size_t workspace_bytes, cudaStream_t stream, bool* handled) {
   *handled = false;
   if ((long)a->O * a->V >= (1L << 22)) return SCAE_OK;
-  // upstream gradients that need the vote-weighted sums over objects, and part-side input gradients, stay on the
-  // general path (caps_ll.cu); a training step with vote_type = presence_type = 'enc' produces none of them
-  if (up->g_soft_winner || up->g_soft_winner_presence || up->g_winner || up->g_winner_presence ||
-      up->g_mixing_log_prob || g_x)
-    return SCAE_OK;
+  // the gradient of mixing_log_prob (never differentiated by SCAE) stays on the general path (caps_ll.cu)
+  if (up->g_mixing_log_prob) return SCAE_OK;
+  // upstream gradients of the soft / hard winner (vote_type / presence_type 'soft', 'hard') and the part-side input
+  // gradient (stop_grad_caps_target = False): the winner-gradient variant of the kernel
+  const bool soft = up->g_soft_winner || up->g_soft_winner_presence || up->g_winner || up->g_winner_presence || g_x;
+  if ((up->g_winner || up->g_winner_presence) && !saved->winner_idx) return SCAE_OK;
   const void* need16[] = {a->all_param, a->cpr_static, a->x, g_all_param, saved->posterior_mixing_prob,
                           saved->log_prob_per_point};
   for (const void* p : need16)
     if (!aligned16(p)) return SCAE_OK;
   const void* opt16[] = {a->noise_vote, a->noise_caps, a->presence, up->g_posterior_mixing_prob, up->g_caps_presence,
-                         up->g_presence_logit_per_caps, up->g_caps_presence ? saved->caps_presence_arg : nullptr};
+                         up->g_presence_logit_per_caps, up->g_caps_presence ? saved->caps_presence_arg : nullptr,
+                         up->g_soft_winner, up->g_soft_winner_presence, up->g_winner, up->g_winner_presence,
+                         (up->g_winner || up->g_winner_presence) ? saved->winner_idx : nullptr};
   for (const void* p : opt16)
     if (p && !aligned16(p)) return SCAE_OK;
   Caps3BwdPlan plan;
-  if (!caps3_plan_bwd(a, up, &plan)) return SCAE_OK;
+  if (!caps3_plan_bwd(a, up, soft, g_x != nullptr, &plan)) return SCAE_OK;
   const int O = a->O, V = a->V, A = 8 * V + 7, n = O * A;
   if (workspace_bytes < caps3_bwd_workspace_bytes(a)) return SCAE_OK;
   const bool sim = (a->flags & SCAE_CAPS_SIMILARITY) != 0;
   void (*kern)(const scae_caps_args, const scae_caps_saved, const scae_caps_upstream, const Caps3BwdOut,
                const Caps3BwdLayout) = nullptr;
   const bool extras = up->g_vote_presence || up->g_mixing_logit || up->g_vote || up->g_scale || up->g_presence_logit_per_vote;
-#define B3_PICK(NP_, MAXT_, MINB_)                                                                                      \
-  (sim ? (extras ? caps3_bwd_kernel<true, NP_, MAXT_, MINB_, true> : caps3_bwd_kernel<true, NP_, MAXT_, MINB_, false>)  \
-       : (extras ? caps3_bwd_kernel<false, NP_, MAXT_, MINB_, true> : caps3_bwd_kernel<false, NP_, MAXT_, MINB_, false>))
-  const bool two = !extras && plan.NP == 1 && plan.threads <= 416 && 2 * (plan.smem + 1024) <= 228u * 1024u;   // two CTAs per SM
-  if (two) kern = B3_PICK(1, 416, 2);
-  else if (plan.NP == 1) kern = B3_PICK(1, 640, 1);
-  else if (plan.NP == 2) kern = B3_PICK(2, 640, 1);
-  else kern = B3_PICK(4, 512, 1);
+  // compiled variants: the training set of upstream gradients (fast), and everything else (extras + winner gradients)
+#define B3_PICK(NP_, MAXT_, MINB_)                                                                        \
+  (sim ? (extras || soft ? caps3_bwd_kernel<true, NP_, MAXT_, MINB_, true, true>                          \
+                         : caps3_bwd_kernel<true, NP_, MAXT_, MINB_, false, false>)                       \
+       : (extras || soft ? caps3_bwd_kernel<false, NP_, MAXT_, MINB_, true, true>                         \
+                         : caps3_bwd_kernel<false, NP_, MAXT_, MINB_, false, false>))
+  const bool two = !extras && !soft && plan.NP == 1 && plan.threads <= 416 &&
+                   2 * (plan.smem + 1024) <= 228u * 1024u;   // two CTAs per SM
+  if (two) kern = caps3_bwd_kernel<false, 1, 416, 2, false, false>;
+  if (two && sim) kern = caps3_bwd_kernel<true, 1, 416, 2, false, false>;
+  if (!two) {
+    if (plan.NP == 1) kern = B3_PICK(1, 640, 1);
+    else if (plan.NP == 2) kern = B3_PICK(2, 640, 1);
+    else kern = B3_PICK(4, 512, 1);
+  }
 #undef B3_PICK
   if (plan.NP == 4 && plan.threads > 512) return SCAE_OK;
   SCAE_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -667,13 +814,19 @@ int caps3_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_
   int grid = sm_count() * (two ? 2 : 1);
   if (grid > a->B) grid = a->B;
   float* partials = static_cast<float*>(workspace);
-  Caps3BwdOut out{g_all_param, g_presence, partials};
+  float* dummy_partials = (soft && up->g_soft_winner && g_dummy_vote) ? partials + (size_t)grid * n : nullptr;
+  Caps3BwdOut out{g_all_param, g_presence, partials, g_x, dummy_partials};
   kern<<<grid, plan.threads, plan.smem, stream>>>(*a, *saved, *up, out, plan.L);
   note_launch();
   SCAE_CUDA_TRY(cudaGetLastError());
   int rc = launch_reduce_rows(partials, g_shared, grid, n, stream);
   if (rc != SCAE_OK) return rc;
-  if (g_dummy_vote) SCAE_CUDA_TRY(cudaMemsetAsync(g_dummy_vote, 0, (size_t)V * 6 * sizeof(float), stream));
+  if (dummy_partials) {
+    rc = launch_reduce_rows(dummy_partials, g_dummy_vote, grid, V * 6, stream);
+    if (rc != SCAE_OK) return rc;
+  } else if (g_dummy_vote) {
+    SCAE_CUDA_TRY(cudaMemsetAsync(g_dummy_vote, 0, (size_t)V * 6 * sizeof(float), stream));
+  }
   *handled = true;
   return SCAE_OK;
 }
