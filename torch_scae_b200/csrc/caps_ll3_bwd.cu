@@ -785,13 +785,14 @@ int caps3_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_
   for (const void* p : opt16)
     if (p && !aligned16(p)) return SCAE_OK;
   Caps3BwdPlan plan;
-  if (!caps3_plan_bwd(a, up, soft, g_x != nullptr, &plan)) return SCAE_OK;
+  const bool extras = up->g_vote_presence || up->g_mixing_logit || up->g_vote || up->g_scale || up->g_presence_logit_per_vote;
+  const bool general = soft || extras;   // the compiled variant with every upstream gradient: its tiles must exist
+  if (!caps3_plan_bwd(a, up, general, g_x != nullptr, &plan)) return SCAE_OK;
   const int O = a->O, V = a->V, A = 8 * V + 7, n = O * A;
   if (workspace_bytes < caps3_bwd_workspace_bytes(a)) return SCAE_OK;
   const bool sim = (a->flags & SCAE_CAPS_SIMILARITY) != 0;
   void (*kern)(const scae_caps_args, const scae_caps_saved, const scae_caps_upstream, const Caps3BwdOut,
                const Caps3BwdLayout) = nullptr;
-  const bool extras = up->g_vote_presence || up->g_mixing_logit || up->g_vote || up->g_scale || up->g_presence_logit_per_vote;
   // compiled variants: the training set of upstream gradients (fast), and everything else (extras + winner gradients)
 #define B3_PICK(NP_, MAXT_, MINB_)                                                                        \
   (sim ? (extras || soft ? caps3_bwd_kernel<true, NP_, MAXT_, MINB_, true, true>                          \
