@@ -101,9 +101,21 @@ int scae_tmpl_ll_bwd(const scae_tmpl_args* a, const float* x, const float* grad_
 /* Materialises what the reference's decoder returns eagerly (part_decoder.py:239-243) and the mixture's point
  * estimates (distributions.py:37-39, :50-77 with straight_through_gradient=False); every output nullable:
  *   transformed_templates[B,M+1,C,H,W], mixing_logits[B,M+1,(alpha?1:C),H,W] (presence already added),
- *   mode[B,C,H,W], mean[B,C,H,W].  No gradients (validation / logging path). */
+ *   mode[B,C,H,W], mean[B,C,H,W], mode_component[B,(alpha?1:C),H,W] = index (as a float) of the component the mode takes
+ *   each pixel from, M = background.  No gradients here; scae_tmpl_mode_bwd is the backward of `mode`. */
 int scae_tmpl_render(const scae_tmpl_args* a, float* transformed_templates, float* mixing_logits, float* mode,
-                     float* mean, scae_stream_t stream);
+                     float* mean, float* mode_component, scae_stream_t stream);
+
+/* Backward of pdf.mode() (distributions.py:50-77 with straight_through_gradient=False -- what SCAE.loss differentiates
+ * when recon_mse_weight > 0, stacked_capsule_auto_encoder.py:226-230): the gradient w.r.t. the mode image flows, pixel by
+ * pixel, into the warp of the component the arg-max picked.  component_cache[B,2,C,H,W]: planes [b,0,c] hold that
+ * component's index as a float (scae_tmpl_render's mode_component[B,(alpha?1:C),H,W], M = background; repeated over the
+ * channels in alpha mode), planes [b,1,c] are ignored.  Outputs and workspace as scae_tmpl_ll_bwd (same scatter kernel);
+ * the mixing logits get no gradient (g_presence = g_alpha = 0, not produced); of g_scalars[4] only d/d bg_value can be
+ * non-zero. */
+int scae_tmpl_mode_bwd(const scae_tmpl_args* a, const float* grad_mode, const float* component_cache, float* g_templates,
+                       float* g_color, float* g_pose, float* g_bg_image, float* g_scalars, void* workspace,
+                       size_t workspace_bytes, scae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Hot path 2: object->part vote composition + part-pose mixture likelihood

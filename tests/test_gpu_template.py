@@ -322,3 +322,51 @@ def test_fused_colourisation_render_and_module_api():
         assert torch.equal(fused.pdf.log_prob(x), plain.pdf.log_prob(x))
         assert torch.equal(fused.transformed_templates, plain.transformed_templates)
         assert torch.equal(fused.pdf.mode(), plain.pdf.mode())
+
+
+# ---- backward of pdf.mode() through the render / mode-backward kernels -------------------------
+@pytest.mark.parametrize('cfg', [dict(B=4, M=40, C=1, h=11, w=11, H=40, W=40, alpha=True, bg_image=False),
+                                 dict(B=3, M=24, C=3, h=11, w=11, H=32, W=32, alpha=True, bg_image=True),
+                                 dict(B=3, M=6, C=2, h=7, w=9, H=12, W=10, alpha=False, bg_image=False)])
+def test_mode_backward_matches_the_pytorch_ops(cfg):
+    """d/d(templates, pose, bg) of sum(w * pdf.mode()) -- what recon_mse_weight > 0 differentiates
+    (stacked_capsule_auto_encoder.py:226-230) -- from scae_tmpl_render + scae_tmpl_mode_bwd equals autograd through the
+    materialised GaussianMixture (affine_grid / grid_sample / one_hot(argmax)), in fp64 on the host."""
+    from torch_scae_b200.distributions import GaussianMixture
+    from torch_scae_b200.part_decoder import TemplateBasedImageDecoder
+    from torch.distributions import Normal
+    B, M, C, h, w, H, W = (cfg[k] for k in ('B', 'M', 'C', 'h', 'w', 'H', 'W'))
+    d = _f32(make_template_inputs(B, M, C, h, w, H, W, alpha=cfg['alpha'], bg_image=cfg['bg_image'], seed=31))
+    dec = TemplateBasedImageDecoder(n_templates=M, template_size=(h, w), output_size=(H, W),
+                                    use_alpha_channel=cfg['alpha'], background_value=not cfg['bg_image'])
+    with torch.no_grad():
+        for k, v in d['params'].items():
+            getattr(dec, k).copy_(v.reshape(getattr(dec, k).shape))
+
+    def run(dev, dtype, fused):
+        m = TemplateBasedImageDecoder(n_templates=M, template_size=(h, w), output_size=(H, W),
+                                      use_alpha_channel=cfg['alpha'], background_value=not cfg['bg_image'])
+        m.load_state_dict(dec.state_dict())
+        m = m.to(dev, dtype)
+        leaf = {k: (d[k].to(dev, dtype).clone().requires_grad_(True) if d[k] is not None else None)
+                for k in ('templates', 'pose', 'bg_image')}
+        presence = d['presence'].to(dev, dtype)
+        if fused:
+            mode = m(templates=leaf['templates'], pose=leaf['pose'], presence=presence, bg_image=leaf['bg_image']).pdf.mode()
+        else:
+            loc, logits = m.differentiable_materialize(leaf['templates'], leaf['pose'], presence, leaf['bg_image'])
+            mode = GaussianMixture(Normal(loc, m.output_scale()), logits).mode()
+        (mode * d['weight'].to(dev, dtype)).sum().backward()
+        grads = {k: v.grad for k, v in leaf.items() if v is not None}
+        if not cfg['bg_image']:
+            grads['bg_value'] = m.bg_value.grad
+        return mode.detach(), grads
+
+    got_mode, got = run(DEV, torch.float32, True)
+    ref_mode, ref = run('cpu', torch.float64, False)
+    assert rel_err(got_mode, ref_mode) < 1e-5
+    for k in ref:
+        if k == 'pose':
+            check_pose_grad(got[k], ref[k], (cfg, k))
+        else:
+            assert rel_err(got[k], ref[k]) < TOL_GRAD, (cfg, k)

@@ -84,7 +84,8 @@ SYMBOLS = {
     'scae_tmpl_ll_fwd': (c_int, [POINTER(TmplArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'scae_tmpl_ll_bwd_workspace_bytes': (c_size_t, [POINTER(TmplArgs)]),
     'scae_tmpl_ll_bwd': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 11 + [c_size_t, c_void_p]),
-    'scae_tmpl_render': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 5),
+    'scae_tmpl_render': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 6),
+    'scae_tmpl_mode_bwd': (c_int, [POINTER(TmplArgs)] + [c_void_p] * 8 + [c_size_t, c_void_p]),
     'scae_caps_ll_fwd': (c_int, [POINTER(CapsArgs), POINTER(CapsOutputs), c_void_p]),
     'scae_caps_ll_bwd_workspace_bytes': (c_size_t, [POINTER(CapsArgs)]),
     'scae_caps_ll_bwd': (c_int, [POINTER(CapsArgs), POINTER(CapsSaved), POINTER(CapsUpstream)] + [c_void_p] * 6 +

@@ -44,7 +44,7 @@ struct ScalarAcc {
 };
 
 // background component of one pixel (evaluated once per pixel, with the first template group)
-template <int C, bool kAlpha>
+template <int C, bool kAlpha, bool kMode>
 __device__ __forceinline__ void bwd_background(const scae_tmpl_args& a, const TmplScalars& sc, const float* xv,
                                                const float* G, const float* Nc, const float* Dc, size_t px0, int HW,
                                                float* g_bg_image, ScalarAcc& acc) {
@@ -52,6 +52,15 @@ __device__ __forceinline__ void bwd_background(const scae_tmpl_args& a, const Tm
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     const size_t px = px0 + (size_t)c * HW;
+    if (kMode) {   // backward of pdf.mode(): the pixel's gradient goes to the component it was taken from (Nc = its index)
+      const float gl = Nc[c] == (float)a.M ? G[c] : 0.0f;
+      if (a.bg_image) {
+        if (g_bg_image) g_bg_image[px] = gl;
+      } else {
+        acc.bgval += gl;
+      }
+      continue;
+    }
     const float bg = a.bg_image ? __ldg(a.bg_image + px) : sc.bg_loc;
     const float bl = kAlpha ? sc.bg_logit : bg * sc.inv_tau;
     const float d = xv[c] - bg;
@@ -76,16 +85,30 @@ __device__ __forceinline__ void bwd_background(const scae_tmpl_args& a, const Tm
 }
 
 // per-(pixel, template) gradients.  Returns g_loc[c] (c < C) and, in v[C], the summed logit gradient (alpha mode).
-template <int C, bool kAlpha, int kPad>
+template <int C, bool kAlpha, int kPad, bool kMode>
 __device__ __forceinline__ Texel<kPad> bwd_pixel(const TmplScalars& sc, const Texel<kPad>& t00, const Texel<kPad>& t10,
                                                  const Texel<kPad>& t01, const Texel<kPad>& t11, const Tap& t,
                                                  float lpres, const float* xv, const float* G, const float* Nc,
-                                                 const float* Dc, ScalarAcc& acc, float& glp, float& gtx, float& gty) {
+                                                 const float* Dc, ScalarAcc& acc, float& glp, float& gtx, float& gty,
+                                                 float m_index) {
   const float two_i2s = 2.0f * sc.i2s;
   const float gx1 = 1.0f - t.fx, gy1 = 1.0f - t.fy;
   Texel<kPad> out;
 #pragma unroll
   for (int c = 0; c < kPad; ++c) out.v[c] = 0.0f;
+  if (kMode) {
+    // backward of pdf.mode() (distributions.py:50-77 without the straight-through estimator): d mode / d loc = 1 for the
+    // component the arg-max picked (its index sits in Nc), nothing flows to the mixing logits
+    glp = gtx = gty = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float gl = Nc[c] == m_index ? G[c] : 0.0f;
+      out.v[c] = gl;
+      gtx = fmaf(gl, fmaf(t11.v[c] - t01.v[c], t.fy, (t10.v[c] - t00.v[c]) * gy1), gtx);
+      gty = fmaf(gl, fmaf(t11.v[c] - t10.v[c], t.fx, (t01.v[c] - t00.v[c]) * gx1), gty);
+    }
+    return out;
+  }
   float al = 0.0f, pD_shared = 0.0f;
   if (kAlpha) {
     al = bilerp<kPad>(t00, t10, t01, t11, t, C) + lpres;
@@ -161,7 +184,9 @@ __device__ __forceinline__ void texel_add(float* dst, const float* v) {
 //
 // Occupancy beats instruction count here (profiles/r01l): 4 CTAs/SM at 64 registers is 5-7 % faster than 3 CTAs/SM at
 // 80 registers, also with the base-grid coordinates in a shared-memory table.
-template <int C, bool kAlpha>
+// kMode: the same scatter for the backward of pdf.mode() -- `gout` is the gradient w.r.t. the mode image and `cache`'s
+// first C planes hold the index of the component each pixel took its value from (scae_tmpl_mode_bwd)
+template <int C, bool kAlpha, bool kMode>
 __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan_kernel(const scae_tmpl_args a,
                                                                                     const float* __restrict__ x,
                                                                                     const float* __restrict__ gout,
@@ -238,7 +263,7 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
           Dc[c] = __ldg(cache + cx + (size_t)C * HW);
           if (staged) PIX[c * HWp + p] = make_float4(xv[c], G[c], Nc[c], Dc[c]);
         }
-        if (first) bwd_background<C, kAlpha>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
+        if (first) bwd_background<C, kAlpha, kMode>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
       }
     }
     if (staged) __syncthreads();
@@ -309,7 +334,8 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
         const Texel<kPad> t00 = ld_texel<kPad>(q), t10 = ld_texel<kPad>(q + kPad);
         const Texel<kPad> t01 = ld_texel<kPad>(q + row), t11 = ld_texel<kPad>(q + row + kPad);
         float glp, gtx, gty;
-        const Texel<kPad> gv = bwd_pixel<C, kAlpha, kPad>(sc, t00, t10, t01, t11, t, lpres, xv, G, Nc, Dc, acc, glp, gtx, gty);
+        const Texel<kPad> gv =
+            bwd_pixel<C, kAlpha, kPad, kMode>(sc, t00, t10, t01, t11, t, lpres, xv, G, Nc, Dc, acc, glp, gtx, gty, (float)m);
         sgx += gtx;
         sgxX = fmaf(gtx, X, sgxX);
         sgxY = fmaf(gtx, Y, sgxY);
@@ -537,7 +563,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_bwd(
   TmplBwdOut out{g_templates, g_color, a->template_color ? raw_partials : nullptr, g_pose, g_presence, g_bg_image,
                  (alpha && g_alpha) ? alpha_partials : nullptr, scalar_partials};
   SCAE_TMPL_DISPATCH(a->C, alpha, {
-    auto kern = tmpl_ll_bwd_scan_kernel<kC, kA>;
+    auto kern = tmpl_ll_bwd_scan_kernel<kC, kA, false>;
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
     if (rc != SCAE_OK) return rc;
     kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, x, grad_log_prob, cache, out, g);
@@ -548,6 +574,49 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_bwd(
     rc = launch_reduce_rows(alpha_partials, g_alpha, g.grid, a->M * a->h * a->w, stream);
     if (rc != SCAE_OK) return rc;
   }
+  if (a->template_color) {
+    rc = launch_reduce_rows(raw_partials, g_templates, g.grid, a->M * a->C * a->h * a->w, stream);
+    if (rc != SCAE_OK) return rc;
+  }
+  return launch_reduce_rows(scalar_partials, g_scalars, g.grid, 4, stream);
+}
+
+// Backward of pdf.mode() (distributions.py:50-77, straight_through_gradient=False; what SCAE.loss differentiates when
+// recon_mse_weight > 0, stacked_capsule_auto_encoder.py:226-230): the gradient w.r.t. the mode image flows, pixel by pixel,
+// into the warp of the component the arg-max picked.  `component_cache[B,2,C,H,W]`: planes [b,0,c] hold that component's
+// index as a float (M = background; scae_tmpl_render's mode_component, repeated over the channels in alpha mode), planes
+// [b,1,c] are ignored.  Same scatter, workspace and outputs as scae_tmpl_ll_bwd; nothing flows to the mixing logits, so
+// g_presence / g_alpha are zero and not produced.  g_scalars[4]: only d / d bg_value can be non-zero.
+extern "C" __attribute__((visibility("default"))) int scae_tmpl_mode_bwd(
+    const scae_tmpl_args* a, const float* grad_mode, const float* component_cache, float* g_templates, float* g_color,
+    float* g_pose, float* g_bg_image, float* g_scalars, void* workspace, size_t workspace_bytes, scae_stream_t stream_) {
+  int rc = tmpl_validate(a);
+  if (rc != SCAE_OK) return rc;
+  SCAE_REQUIRE(grad_mode && component_cache && g_templates && g_pose && g_scalars, SCAE_EINVAL,
+               "tmpl mode bwd: a required pointer is NULL");
+  SCAE_REQUIRE(!a->template_color || g_color, SCAE_EINVAL, "tmpl mode bwd: g_color is required with template_color");
+  TmplGeom g;
+  rc = tmpl_bwd_plan(a, &g);
+  if (rc != SCAE_OK) return rc;
+  const size_t need =
+      (tmpl_ws_alpha_floats(a, g.grid) + tmpl_ws_raw_floats(a, g.grid) + (size_t)g.grid * 4) * sizeof(float);
+  SCAE_REQUIRE(workspace && workspace_bytes >= need, SCAE_EINVAL, "tmpl mode bwd: workspace too small (%zu < %zu)",
+               workspace_bytes, need);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool alpha = a->mode == SCAE_TMPL_MODE_ALPHA;
+  float* alpha_partials = static_cast<float*>(workspace);
+  float* raw_partials = alpha_partials + tmpl_ws_alpha_floats(a, g.grid);
+  float* scalar_partials = raw_partials + tmpl_ws_raw_floats(a, g.grid);
+  TmplBwdOut out{g_templates, g_color, a->template_color ? raw_partials : nullptr, g_pose, nullptr, g_bg_image, nullptr,
+                 scalar_partials};
+  SCAE_TMPL_DISPATCH(a->C, alpha, {
+    auto kern = tmpl_ll_bwd_scan_kernel<kC, kA, true>;
+    rc = tmpl_prepare_kernel(kern, g.smem_bytes);
+    if (rc != SCAE_OK) return rc;
+    kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, grad_mode, grad_mode, component_cache, out, g);
+    note_launch();
+  });
+  SCAE_CUDA_TRY(cudaGetLastError());
   if (a->template_color) {
     rc = launch_reduce_rows(raw_partials, g_templates, g.grid, a->M * a->C * a->h * a->w, stream);
     if (rc != SCAE_OK) return rc;

@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_ll_fwd_kernel(const scae
 template <int C, bool kAlpha>
 __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_render_kernel(const scae_tmpl_args a, float* __restrict__ tt,
                                                                       float* __restrict__ ml, float* __restrict__ mode,
-                                                                      float* __restrict__ mean, const TmplGeom g) {
+                                                                      float* __restrict__ mean, float* __restrict__ comp,
+                                                                      const TmplGeom g) {
   using TT = TexTraits<C, kAlpha>;
   constexpr int kPad = TT::kPad, ND = kAlpha ? 1 : C;
   extern __shared__ __align__(16) float smem[];
@@ -274,8 +275,12 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_render_kernel(const scae
           }
           // argmax ties go to the lowest component index (torch.argmax); bg has the highest index, so templates win ties
           bool bg_best[ND];
+          int best_m[ND];   // the component the mode takes its value from (M = background)
 #pragma unroll
-          for (int d = 0; d < ND; ++d) bg_best[d] = true;
+          for (int d = 0; d < ND; ++d) {
+            bg_best[d] = true;
+            best_m[d] = a.M;
+          }
           for (int m0 = 0; m0 < a.M; m0 += g.mc) {
             const int mc = min(g.mc, a.M - m0);
             __syncthreads();
@@ -326,6 +331,7 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_render_kernel(const scae
                 if (better) {
                   best_logit[d] = logit[d];
                   bg_best[d] = false;
+                  best_m[d] = m;
                 }
               }
             }
@@ -338,8 +344,10 @@ __global__ void __launch_bounds__(kTmplThreads, 2) tmpl_render_kernel(const scae
               if (mean) mean[((size_t)b * C + c) * HW + pix] = acc[c] * __frcp_rn(L[kAlpha ? 0 : c].s);
             }
 #pragma unroll
-            for (int d = 0; d < ND; ++d)
+            for (int d = 0; d < ND; ++d) {
               if (ml) ml[(((size_t)b * K + a.M) * CL + d) * HW + pix] = kAlpha ? sc.bg_logit : bgv[d] * sc.inv_tau;
+              if (comp) comp[((size_t)b * CL + d) * HW + pix] = (float)best_m[d];
+            }
           }
         }
   }
@@ -376,7 +384,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_fwd(const sca
 extern "C" __attribute__((visibility("default"))) int scae_tmpl_render(const scae_tmpl_args* a,
                                                                        float* transformed_templates,
                                                                        float* mixing_logits, float* mode, float* mean,
-                                                                       scae_stream_t stream_) {
+                                                                       float* mode_component, scae_stream_t stream_) {
   int rc = tmpl_validate(a);
   if (rc != SCAE_OK) return rc;
   TmplGeom g;
@@ -388,7 +396,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_render(const sca
     auto kern = tmpl_render_kernel<kC, kA>;
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
     if (rc != SCAE_OK) return rc;
-    kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, transformed_templates, mixing_logits, mode, mean, g);
+    kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, transformed_templates, mixing_logits, mode, mean, mode_component, g);
     note_launch();
   });
   SCAE_CUDA_TRY(cudaGetLastError());

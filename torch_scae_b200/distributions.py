@@ -154,4 +154,14 @@ class TemplateMixture:
             fast = self._fast_point_estimate('mode')
             if fast is not None:
                 return fast
+            if self._materialized is None:
+                # gradients wanted (recon_mse_weight > 0, stacked_capsule_auto_encoder.py:226-230): render + mode-backward
+                # kernels; the B x (M+1) x C x H x W tensors are not formed in either direction
+                templates, pose, presence, bg_image = self._inputs
+                d = self._decoder
+                return ops.TemplateMixtureMode.apply(
+                    templates, pose, presence, bg_image, d.templates_alpha if d.use_alpha_channel else None,
+                    d.bg_value if d.background_value else None, d.bg_mixing_logit if d.use_alpha_channel else None,
+                    None if d.use_alpha_channel else d.temperature_logit, d.scale if d.learn_output_scale else None,
+                    tuple(d.output_size), self._color)
         return self._eager().mode(straight_through_gradient, maximum)

@@ -726,12 +726,62 @@ def template_render(templates, pose, presence, bg_image, templates_alpha, bg_val
     dev = templates.device
     shapes = dict(transformed_templates=(B, M + 1, C, H, W),
                   mixing_logits=(B, M + 1, 1 if templates_alpha is not None else C, H, W),
-                  mode=(B, C, H, W), mean=(B, C, H, W))
+                  mode=(B, C, H, W), mean=(B, C, H, W),
+                  mode_component=(B, 1 if templates_alpha is not None else C, H, W))
     out = {k: torch.empty(shapes[k], device=dev, dtype=torch.float32) for k in want}
     check(lib.scae_tmpl_render(ctypes.byref(args), ptr(out.get('transformed_templates')),
-                               ptr(out.get('mixing_logits')), ptr(out.get('mode')), ptr(out.get('mean')), _stream()),
-          'scae_tmpl_render')
+                               ptr(out.get('mixing_logits')), ptr(out.get('mode')), ptr(out.get('mean')),
+                               ptr(out.get('mode_component')), _stream()), 'scae_tmpl_render')
     return out
+
+
+class TemplateMixtureMode(torch.autograd.Function):
+    """``pdf.mode()`` (distributions.py:50-77 without the straight-through estimator) with its backward: the render kernel
+    also records which component every pixel took its value from, and scae_tmpl_mode_bwd scatters the upstream gradient
+    into that component's warp (the same segmented-scan scatter as the likelihood backward).  Differentiable w.r.t.
+    templates | (raw templates, colours), pose, bg_image, bg_value; the arg-max passes nothing to the mixing logits."""
+
+    @staticmethod
+    def forward(ctx, templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit, temperature_logit,
+                scale, output_size, color=None):
+        tensors = [_f32c(t) for t in (templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit,
+                                      temperature_logit, scale, color)]
+        r = template_render(*tensors[:9], output_size, ('mode', 'mode_component'), tensors[9])
+        ctx.save_for_backward(*[t for t in tensors if t is not None], r['mode_component'])
+        ctx.present = [t is not None for t in tensors]
+        ctx.output_size = tuple(output_size)
+        return r['mode']
+
+    @staticmethod
+    def backward(ctx, g_mode):
+        lib = _lib.load()
+        saved = list(ctx.saved_tensors)
+        comp = saved.pop()
+        it = iter(saved)
+        templates, pose, presence, bg_image, templates_alpha, bg_value, bg_mixing_logit, temperature_logit, scale, \
+            color = [next(it) if p else None for p in ctx.present]
+        M, C, h, w = templates.shape[-4:]
+        B = pose.shape[0]
+        H, W = ctx.output_size
+        g = _f32c(g_mode)
+        args = _tmpl_args(templates, templates_alpha, pose, presence, bg_image, bg_value, bg_mixing_logit,
+                          temperature_logit, scale, (H, W), color)
+        dev = templates.device
+        # [B,2,C,H,W] in the layout of the likelihood cache: plane 0 = component index per channel, plane 1 unused
+        cache = torch.zeros(B, 2, C, H, W, device=dev, dtype=torch.float32)
+        cache[:, 0] = comp.expand(B, C, H, W)
+        g_templates = torch.empty_like(templates)
+        g_color = torch.empty_like(color) if color is not None else None
+        g_pose = torch.empty_like(pose)
+        g_bg_image = torch.empty_like(bg_image) if bg_image is not None else None
+        g_scalars = torch.empty(4, device=dev, dtype=torch.float32)
+        ws_bytes = lib.scae_tmpl_ll_bwd_workspace_bytes(ctypes.byref(args))
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        check(_timed('scae_tmpl_mode_bwd', lib.scae_tmpl_mode_bwd, ctypes.byref(args), ptr(g), ptr(cache),
+                     ptr(g_templates), ptr(g_color), ptr(g_pose), ptr(g_bg_image), ptr(g_scalars), ptr(ws), ws_bytes,
+                     _stream()), 'scae_tmpl_mode_bwd')
+        g_bg_value = g_scalars[0:1].reshape(bg_value.shape) if bg_value is not None and bg_image is None else None
+        return (g_templates, g_pose, None, g_bg_image, None, g_bg_value, None, None, None, None, g_color)
 
 
 # =================================================================================================================
