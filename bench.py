@@ -97,6 +97,22 @@ def issue_roof_ms(name, batch, sm_mhz, M=40, H=40, W=40, C=1, sms=148, **_):
     return units * ISSUE_LANE_INSTR[name] / (sms * 128 * sm_mhz * 1e6) * 1e3
 
 
+def measured_issue_ms(name, batch, sm_mhz, sms=148):
+    """Time the kernel's ACTUAL instruction stream would take at a perfect issue rate: lane-instructions per launch as
+    ncu counted them for this build (profiles/issue_counts.json, written by tools/summarize_ncu.py from the committed
+    --set full capture; MNIST config), scaled to the batch.  t_measured / this = the issue-pipe utilisation."""
+    path = os.path.join(ROOT, 'profiles', 'issue_counts.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        rec = json.load(f)
+    k = rec.get('kernels', {}).get(name)
+    if not k:
+        return None
+    lane_instr = k['lane_instr_per_launch'] * batch / rec['batch']
+    return lane_instr / (sms * 128 * sm_mhz * 1e6) * 1e3
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -531,7 +547,14 @@ def run_gpu(args):
         if name in ISSUE_LANE_INSTR:
             t_issue = issue_roof_ms(name, B, (clocks or {}).get('sm_mhz') or 1965, **shape)
             kernels[name].update(binding_roof='sm issue rate', issue_roof_ms=round(t_issue, 4),
-                                 frac_of_issue_roof=round(t_issue / avg_ms, 3))
+                                 frac_of_issue_roof=round(t_issue / avg_ms, 3),
+                                 issue_roof_basis=f'{ISSUE_LANE_INSTR[name]} algorithmic lane-instructions per (pixel, '
+                                                  'component)')
+            if config in ('mnist32', 'mnist10'):
+                t_meas = measured_issue_ms(name, B, (clocks or {}).get('sm_mhz') or 1965)
+                if t_meas is not None:      # ncu-counted instruction stream of this build: issue-pipe utilisation
+                    kernels[name].update(measured_issue_ms=round(t_meas, 4),
+                                         issue_pipe_utilisation=round(t_meas / avg_ms, 3))
         else:
             kernels[name].update(binding_roof='hbm')
     dominant = max(kernels, key=lambda k: kernels[k]['ms'])
@@ -540,6 +563,7 @@ def run_gpu(args):
                     frac=kernels[dominant]['frac_of_hbm_peak'], traffic=traffic, peak_source=peak_src,
                     binding_roof=kernels[dominant]['binding_roof'],
                     frac_of_binding_roof=kernels[dominant].get('frac_of_issue_roof', kernels[dominant]['frac_of_hbm_peak']),
+                    issue_pipe_utilisation=kernels[dominant].get('issue_pipe_utilisation'),
                     hbm_bound_kernels={k: v['frac_of_hbm_peak'] for k, v in kernels.items() if v['binding_roof'] == 'hbm'},
                     note='path-1 kernels are fp32-issue / shared-memory bound by construction (the B x K x H x W tensor '
                          'is never written); the HBM-shaped kernels are the two capsule ones (hbm_bound_kernels: in-step '

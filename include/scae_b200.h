@@ -42,6 +42,9 @@ int scae_abi_version(void);
 const char* scae_last_error(void);
 /* Compiled-for architecture string, e.g. "sm_100a". */
 const char* scae_build_arch(void);
+/* Hash of the sources this library was compiled from (torch_scae_b200/build.py::source_id); the Python binding refuses a
+ * library whose id differs from the checked-out sources. */
+const char* scae_build_id(void);
 /* Number of CUDA kernels this library has launched from the calling thread so far (monotonic; bench.py's launch
  * accounting reads it before and after each entry point). */
 unsigned long long scae_launch_count(void);

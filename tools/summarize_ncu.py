@@ -28,7 +28,8 @@ METRICS = [
     'lts__t_sectors_op_read.sum', 'lts__t_sectors_op_write.sum',
 ]
 ENTRY = {'tmpl_ll_fwd': 'scae_tmpl_ll_fwd', 'tmpl_ll_bwd': 'scae_tmpl_ll_bwd', 'caps_ll_fwd': 'scae_caps_ll_fwd',
-         'caps_ll_bwd': 'scae_caps_ll_bwd'}
+         'caps_ll_bwd': 'scae_caps_ll_bwd', 'caps2_fwd': 'scae_caps_ll_fwd', 'caps2_bwd': 'scae_caps_ll_bwd',
+         'caps3_fwd': 'scae_caps_ll_fwd', 'caps3_bwd': 'scae_caps_ll_bwd'}
 
 
 def to_bytes(value, unit):
@@ -62,17 +63,17 @@ def launches(path, tag, title):
     print('wrote', out)
 
 
-def kernels(rep, tag, title):
+def kernels(rep, tag, title, batch=1024):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     out = os.path.join(ROOT, 'profiles', f'{tag}_kernels.md')
-    traffic = {}
+    traffic, issue = {}, {}
     with open(out, 'w') as f:
         f.write(f'# ncu --set full, hot-path kernels -- {title}\n\n')
         f.write('Command (B200, under gpurun): `ncu --set full --clock-control none --import-source on --profile-from-start '
-                "off -k regex:'tmpl_ll|caps_ll|caps_bwd|reduce_rows' -o gpurun_out/prof python tools/profile_step.py`; read "
+                "off -k regex:'tmpl_ll|caps' -o gpurun_out/prof python tools/profile_step.py`; read "
                 'here with `ncu -i ... --page raw --csv`.\n\n')
         for d in data:
             name = d[idx['Kernel Name']]
@@ -90,8 +91,16 @@ def kernels(rep, tag, title):
                     b = to_bytes(d[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) + \
                         to_bytes(d[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
                     traffic[entry] = traffic.get(entry, 0) + int(b)
+                    # lane-instructions the kernel actually executes per launch (ncu): bench.py divides by the work units
+                    # of its batch for the issue-roof figures of the path-1 kernels
+                    warp_inst = float(d[idx['smsp__inst_executed.sum']].replace(',', ''))
+                    lanes = float(d[idx['smsp__thread_inst_executed_per_inst_executed.ratio']].replace(',', ''))
+                    issue[entry] = dict(lane_instr_per_launch=warp_inst * lanes, warp_instr_per_launch=warp_inst,
+                                        kernel=name[:80])
     with open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w') as f:
         json.dump(traffic, f, indent=1, sort_keys=True)
+    with open(os.path.join(ROOT, 'profiles', 'issue_counts.json'), 'w') as f:
+        json.dump(dict(batch=batch, source=f'ncu --set full, {tag}', kernels=issue), f, indent=1, sort_keys=True)
     print('wrote', out, 'and profiles/traffic.json', traffic)
 
 
@@ -101,8 +110,9 @@ if __name__ == '__main__':
     ap.add_argument('--title', default='one SCAE train step, B=1024, MNIST config (O=32)')
     ap.add_argument('--launches')
     ap.add_argument('--rep')
+    ap.add_argument('--batch', type=int, default=1024, help='images per launch in the --rep capture')
     a = ap.parse_args()
     if a.launches:
         launches(a.launches, a.tag, a.title)
     if a.rep:
-        kernels(a.rep, a.tag, a.title)
+        kernels(a.rep, a.tag, a.title, a.batch)

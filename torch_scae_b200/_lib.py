@@ -76,6 +76,7 @@ class CapsSaved(Structure):
 # every symbol include/scae_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'scae_abi_version': (c_int, []),
+    'scae_build_id': (c_char_p, []),
     'scae_last_error': (c_char_p, []),
     'scae_build_arch': (c_char_p, []),
     'scae_launch_count': (c_ulonglong, []),
@@ -147,6 +148,11 @@ def load():
         fn.argtypes = argtypes
     if lib.scae_abi_version() != ABI_VERSION:
         raise ScaeError(f'ABI mismatch: library {lib.scae_abi_version()} != binding {ABI_VERSION}; rebuild')
+    from . import build as _build
+    have, want = lib.scae_build_id().decode(), _build.source_id()
+    if have != want:
+        raise ScaeError(f'{LIB_PATH} was built from other sources (build id {have}, sources {want}); rebuild it with '
+                        '`python -m torch_scae_b200.build`')
     _lib = lib
     return lib
 

@@ -57,3 +57,39 @@ class LazyAttrDict(AttrDict):
 
     def is_materialized(self, key):
         return not isinstance(dict.__getitem__(self, key), _Thunk)
+
+    # every way of reading the mapping resolves the deferred entries it touches, so that dict(res), {**res}, res.copy(),
+    # res.pop(k), pickling or a collate function never see the internal thunks
+    def keys(self):
+        return list(dict.keys(self))
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def pop(self, key, *default):
+        if key in self:
+            value = self[key]
+            dict.__delitem__(self, key)
+            return value
+        if default:
+            return default[0]
+        raise KeyError(key)
+
+    def popitem(self):
+        key = next(reversed(dict.keys(self)))
+        return key, self.pop(key)
+
+    def setdefault(self, key, default=None):
+        if key not in self:
+            dict.__setitem__(self, key, default)
+        return self[key]
+
+    def copy(self):
+        return AttrDict(self.items())
+
+    def to_dict(self):
+        """plain dict with every deferred entry computed"""
+        return dict(self.items())
+
+    def __reduce__(self):
+        return (AttrDict, (self.to_dict(),))

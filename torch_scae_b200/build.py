@@ -24,12 +24,34 @@ def _nvcc():
     raise RuntimeError('nvcc not found; cannot build libscae_b200.so')
 
 
-def is_stale():
+def source_id():
+    """sha256 over every source and header the library is built from (and the flags): compiled into the library
+    (``scae_build_id()``) and compared by ``_lib.load()``, so a stale .so -- e.g. one that travelled to another machine
+    with newer sources -- is noticed whatever the file times say."""
+    import hashlib
+    hsh = hashlib.sha256(' '.join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), 'rb') as fh:
+            hsh.update(f.encode() + b'\0' + fh.read())
+    return hsh.hexdigest()[:16]
+
+
+def built_id():
+    """build id recorded in the existing library, or None"""
     if not os.path.exists(LIB_PATH):
-        return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > built for d in deps)
+        return None
+    import ctypes
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+        fn = lib.scae_build_id
+        fn.restype = ctypes.c_char_p
+        return fn().decode()
+    except (OSError, AttributeError):
+        return None
+
+
+def is_stale():
+    return built_id() != source_id()
 
 
 def build(force=False, verbose=False):
@@ -38,9 +60,10 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = _nvcc()
     objs = []
+    build_id = source_id()
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace('.cu', '.o'))
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc, *NVCC_FLAGS, f'-DSCAE_BUILD_ID="{build_id}"', '-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
             print(' '.join(cmd), flush=True)

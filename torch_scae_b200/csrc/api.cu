@@ -147,6 +147,11 @@ SCAE_EXPORT const char* scae_last_error(void) { return scae::g_error; }
 
 SCAE_EXPORT const char* scae_build_arch(void) { return "sm_100a"; }
 
+#ifndef SCAE_BUILD_ID
+#define SCAE_BUILD_ID "unknown"
+#endif
+SCAE_EXPORT const char* scae_build_id(void) { return SCAE_BUILD_ID; }
+
 SCAE_EXPORT unsigned long long scae_launch_count(void) { return scae::g_launches; }
 
 SCAE_EXPORT unsigned long long scae_caps_fast_path_count(void) { return scae::g_fast_path.load(); }

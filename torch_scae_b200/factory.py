@@ -63,11 +63,13 @@ def prepare_model_params(image_shape, n_classes, n_part_caps, n_obj_caps, pcae_c
 def make_scae(model_params: dict):
     """Builds the five sub-modules and the SCAE wrapper (factory.py:152-178)."""
     cfg = prepare_model_params(**model_params)
+    # sub-modules are constructed in the reference's order (cnn, part encoder, template generator, part decoder, object
+    # encoder, object decoder) so that the same torch seed consumes the RNG stream in the same order; the stacked
+    # per-capsule MLP weights (PerCapsuleMLP) are the one place whose initial draws are not stream-identical
     part_encoder = CapsuleImageEncoder(encoder=CNNEncoder(**cfg['pcae_cnn_encoder']), **cfg['pcae_encoder'])
+    template_generator = TemplateGenerator(**cfg['pcae_template_generator'])
+    part_decoder = TemplateBasedImageDecoder(**cfg['pcae_decoder'])
+    obj_encoder = SetTransformer(**cfg['ocae_encoder_set_transformer'])
     obj_decoder = CapsuleObjectDecoder(CapsuleLayer(**cfg['ocae_decoder_capsule']))
-    return SCAE(part_encoder=part_encoder,
-                template_generator=TemplateGenerator(**cfg['pcae_template_generator']),
-                part_decoder=TemplateBasedImageDecoder(**cfg['pcae_decoder']),
-                obj_encoder=SetTransformer(**cfg['ocae_encoder_set_transformer']),
-                obj_decoder=obj_decoder,
-                **cfg['scae'])
+    return SCAE(part_encoder=part_encoder, template_generator=template_generator, part_decoder=part_decoder,
+                obj_encoder=obj_encoder, obj_decoder=obj_decoder, **cfg['scae'])

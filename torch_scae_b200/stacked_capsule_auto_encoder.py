@@ -132,7 +132,12 @@ class SCAE(nn.Module):
                 td_presence = pres.repeat_interleave(O, dim=0) * res.vote_presence_binary.view(-1, pres.shape[1])
                 res.top_down_per_caps_rec = decode(res.vote.detach().view(-1, *res.vote.shape[2:]), td_presence, O,
                                                    detach=True)
-        res.templates = templates
+        if color is not None:
+            # the differentiable product exists only if somebody reads it (a user loss / regulariser on res.templates gets
+            # its gradient; the training step itself never forms the (B,M,C,h,w) tensor with a graph)
+            res.set_lazy('templates', lambda: raw * color[:, :, :, None, None])
+        else:
+            res.templates = templates
         res.template_presence = enc.presence
         rec = res.rec
         res.set_lazy('transformed_templates', lambda: rec.transformed_templates)
