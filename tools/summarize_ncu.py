@@ -63,7 +63,7 @@ def launches(path, tag, title):
     print('wrote', out)
 
 
-def kernels(rep, tag, title, batch=1024):
+def kernels(rep, tag, title, batch=1024, write_json=True):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -97,6 +97,9 @@ def kernels(rep, tag, title, batch=1024):
                     lanes = float(d[idx['smsp__thread_inst_executed_per_inst_executed.ratio']].replace(',', ''))
                     issue[entry] = dict(lane_instr_per_launch=warp_inst * lanes, warp_instr_per_launch=warp_inst,
                                         kernel=name[:80])
+    if not write_json:
+        print('wrote', out)
+        return
     with open(os.path.join(ROOT, 'profiles', 'traffic.json'), 'w') as f:
         json.dump(traffic, f, indent=1, sort_keys=True)
     with open(os.path.join(ROOT, 'profiles', 'issue_counts.json'), 'w') as f:
@@ -110,9 +113,10 @@ if __name__ == '__main__':
     ap.add_argument('--title', default='one SCAE train step, B=1024, MNIST config (O=32)')
     ap.add_argument('--launches')
     ap.add_argument('--rep')
+    ap.add_argument('--no-json', action='store_true', help='only the markdown summary (keep traffic.json / issue_counts.json)')
     ap.add_argument('--batch', type=int, default=1024, help='images per launch in the --rep capture')
     a = ap.parse_args()
     if a.launches:
         launches(a.launches, a.tag, a.title)
     if a.rep:
-        kernels(a.rep, a.tag, a.title, a.batch)
+        kernels(a.rep, a.tag, a.title, a.batch, not a.no_json)
