@@ -84,6 +84,18 @@ inline unsigned lds_u32(unsigned addr) { return *reinterpret_cast<const unsigned
 inline float4 lds_f32x4(unsigned addr) { return *reinterpret_cast<const float4*>((const char*)emu_dynamic_smem + addr); }
 inline void sts_f32(unsigned addr, float v) { *reinterpret_cast<float*>((char*)emu_dynamic_smem + addr) = v; }
 inline void sts_u32(unsigned addr, unsigned v) { *reinterpret_cast<unsigned*>((char*)emu_dynamic_smem + addr) = v; }
+inline float2 lds_f32x2(unsigned addr) { return *reinterpret_cast<const float2*>((const char*)emu_dynamic_smem + addr); }
+inline void smem_add_pred_f32(unsigned addr, float a, bool pred) {
+  if (pred) *reinterpret_cast<float*>((char*)emu_dynamic_smem + addr) += a;
+}
+inline void smem_add_pred_f32x2(unsigned addr, float a, float b, bool pred) {
+  float* p = reinterpret_cast<float*>((char*)emu_dynamic_smem + addr);
+  if (pred) p[0] += a, p[1] += b;
+}
+inline void smem_add_pred_f32x4(unsigned addr, float a, float b, float c, float d, bool pred) {
+  float* p = reinterpret_cast<float*>((char*)emu_dynamic_smem + addr);
+  if (pred) p[0] += a, p[1] += b, p[2] += c, p[3] += d;
+}
 inline void mbar_init(unsigned bar, unsigned count) {
   std::lock_guard<std::mutex> lock(emu_async_mutex);
   emu_mbarrier& b = emu_mbarriers[bar];

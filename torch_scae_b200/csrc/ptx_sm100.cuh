@@ -77,6 +77,37 @@ __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
 __device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ float2 lds_f32x2(unsigned addr) {   // 8-byte aligned
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+// Predicated read-modify-write of 1 / 2 / 4 consecutive floats: [addr] += v where `pred` holds, as predicated
+// instructions (no branch, no reconvergence bookkeeping).  Callers guarantee that the lanes with `pred` set use distinct
+// addresses.
+__device__ __forceinline__ void smem_add_pred_f32(unsigned addr, float a, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tsetp.ne.u32 p, %2, 0;\n\t"
+      "@p ld.shared.f32 t, [%0];\n\t@p add.f32 t, t, %1;\n\t@p st.shared.f32 [%0], t;\n\t}" ::"r"(addr),
+      "f"(a), "r"((unsigned)pred)
+      : "memory");
+}
+__device__ __forceinline__ void smem_add_pred_f32x2(unsigned addr, float a, float b, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 t, u;\n\tsetp.ne.u32 p, %3, 0;\n\t"
+      "@p ld.shared.v2.f32 {t, u}, [%0];\n\t@p add.f32 t, t, %1;\n\t@p add.f32 u, u, %2;\n\t"
+      "@p st.shared.v2.f32 [%0], {t, u};\n\t}" ::"r"(addr),
+      "f"(a), "f"(b), "r"((unsigned)pred)
+      : "memory");
+}
+__device__ __forceinline__ void smem_add_pred_f32x4(unsigned addr, float a, float b, float c, float d, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 t, u, v, w;\n\tsetp.ne.u32 p, %5, 0;\n\t"
+      "@p ld.shared.v4.f32 {t, u, v, w}, [%0];\n\t@p add.f32 t, t, %1;\n\t@p add.f32 u, u, %2;\n\t"
+      "@p add.f32 v, v, %3;\n\t@p add.f32 w, w, %4;\n\t@p st.shared.v4.f32 [%0], {t, u, v, w};\n\t}" ::"r"(addr),
+      "f"(a), "f"(b), "f"(c), "f"(d), "r"((unsigned)pred)
+      : "memory");
+}
 
 // ---- mbarrier + bulk (TMA) copies, 1-D --------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -163,35 +163,81 @@ __device__ __forceinline__ void write_scalar_partials(const scae_tmpl_args& a, c
 }
 
 // ================================================================================================================
-// scan kernel: warp per (image, template), segmented-scan scatter
+// run kernel: warp per (image, template); a lane walks a run of consecutive pixels and keeps the four corner sums of
+// its current bilinear cell in registers
 // ================================================================================================================
-constexpr int kScanThreads = 256;
+//
+// The template / alpha gradient is a transposed bilinear interpolation.  Along an image row the sampling coordinates move
+// on a straight line, so the pixels that fall into one bilinear cell are CONSECUTIVE.  Every lane therefore walks its own
+// run of `L` consecutive pixels of one row, one pixel per step, and accumulates the four corner contributions of the
+// cell it is in (4 x NCH registers).  Only when the cell changes -- every `magnification` pixels, 7 at the MNIST
+// configuration -- does the lane add its sums to the warp's private gradient atlas in shared memory with plain vector
+// read-modify-writes.  Lanes that leave the SAME cell in the same step (neighbouring rows of an unrotated template) are
+// found with one MATCH.ANY and take turns in lane order; within a turn all cells are distinct, and the corners are
+// updated one after the other, so no two lanes touch an address in the same instruction and the summation order is
+// fixed by the program: bit-reproducible, no atomics, no cross-lane scan.  (The predecessor did a segmented warp scan of
+// all eight values on every 32-pixel pass: 313 warp instructions per pass against ~150 here; profiles/r02_*.)
+//
+// Mapping.  A row is cut into k runs (k a power of two, L = ceil(W / k)); a "walk" is 32 runs in lock-step: lane ->
+// (row slot q = lane / k, segment lane % k).  Walk w takes the rows q * walks + w, so the rows a warp works on at the same
+// time are `walks` pixels apart and rarely share a cell.  Pixel records {x, upstream gradient, the two cached lse
+// terms} are staged per band of `band_walks` walks in the order the lanes read them ([walk][lane][step], one LDS.128 per
+// step); ragged ends and dead runs hold pad records {0, 0, 1e30, 1e30} that turn every contribution into an exact
+// zero without a select in the loop.  Images whose records do not fit next to the atlases are processed band by band
+// (two CTA barriers per band), the cell sums and pose sums carried in registers across bands.
+constexpr int kRunThreads = 256;
 
-// texel += v over the NCH live channels, as one vector read-modify-write of the padded texel
+// [addr] += the NCH live channels of one corner where `pred` holds: one predicated vector read-modify-write of the padded
+// texel (values, not a pointer: the sums must stay in registers across the asm statements)
+template <int kPad>
+__device__ __forceinline__ void texel_add_pred(unsigned addr, float v0, float v1, float v2, float v3, bool pred) {
+  if (kPad == 1) smem_add_pred_f32(addr, v0, pred);
+  else if (kPad == 2) smem_add_pred_f32x2(addr, v0, v1, pred);
+  else smem_add_pred_f32x4(addr, v0, v1, v2, v3, pred);
+}
+#define SCAE_CORNER(k) acc[k][0], acc[k][NCH > 1 ? 1 : 0], NCH > 2 ? acc[k][NCH > 2 ? 2 : 0] : 0.0f, NCH > 3 ? acc[k][NCH > 3 ? 3 : 0] : 0.0f
+
+// Lanes with `fl` set add their corner sums to the cell at shared address `cur_off` (+ gat: the warp's gradient atlas)
+// and start the cell `new_off`.  Lanes that flush the same cell take turns in lane order.
 template <int kPad, int NCH>
-__device__ __forceinline__ void texel_add(float* dst, const float* v) {
-  Texel<kPad> t = ld_texel<kPad>(dst);
+__device__ __forceinline__ void flush_cells(unsigned gat, unsigned row, int lane, bool fl, unsigned& cur_off,
+                                            unsigned new_off, float (&acc)[4][NCH]) {
+  const unsigned peers = __match_any_sync(0xffffffffu, fl ? cur_off : (0xFFFFFF00u | (unsigned)lane));
+  const unsigned rank = (unsigned)__popc(peers & ((1u << lane) - 1u));
+  const unsigned turns = redux_max_u32(0xffffffffu, fl ? rank + 1u : 0u);
+  const unsigned ga = cur_off + gat, gb = ga + row;
+#pragma unroll 1
+  for (unsigned r = 0; r < turns; ++r) {
+    const bool mine = fl && rank == r;
+    texel_add_pred<kPad>(ga, SCAE_CORNER(0), mine);
+    __syncwarp();
+    texel_add_pred<kPad>(ga + kPad * 4, SCAE_CORNER(1), mine);
+    __syncwarp();
+    texel_add_pred<kPad>(gb, SCAE_CORNER(2), mine);
+    __syncwarp();
+    texel_add_pred<kPad>(gb + kPad * 4, SCAE_CORNER(3), mine);
+    __syncwarp();
+  }
+  if (fl) {
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) t.v[c] += v[c];
-  st_texel<kPad>(dst, t);
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) acc[k][c] = 0.0f;
+    cur_off = new_off;
+  }
 }
 
 // Work unit = (image b, template group grp): the CTA's warps take the templates grp * nwarps + warp.  Units are dealt
 // round-robin to the persistent CTAs, so a batch of 1024 images is 5120 units over 592 CTAs (8.6 each) instead of
 // 1.7 whole images each -- the tail of the last wave shrinks from 14 % to 4 % of the kernel.
-// (Image too large for the shared-memory pixel records: one unit = one whole image, so that the pixel data the warps
-// re-read from global memory stays in the CTA's L1.)
-//
-// Occupancy beats instruction count here (profiles/r01l): 4 CTAs/SM at 64 registers is 5-7 % faster than 3 CTAs/SM at
-// 80 registers, also with the base-grid coordinates in a shared-memory table.
 // kMode: the same scatter for the backward of pdf.mode() -- `gout` is the gradient w.r.t. the mode image and `cache`'s
 // first C planes hold the index of the component each pixel took its value from (scae_tmpl_mode_bwd)
 template <int C, bool kAlpha, bool kMode>
-__global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan_kernel(const scae_tmpl_args a,
-                                                                                    const float* __restrict__ x,
-                                                                                    const float* __restrict__ gout,
-                                                                                    const float* __restrict__ cache,
-                                                                                    const TmplBwdOut out, const TmplGeom g) {
+__global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_kernel(const scae_tmpl_args a,
+                                                                                   const float* __restrict__ x,
+                                                                                   const float* __restrict__ gout,
+                                                                                   const float* __restrict__ cache,
+                                                                                   const TmplBwdOut out, const TmplGeom g) {
   using TT = TexTraits<C, kAlpha>;
   constexpr int kPad = TT::kPad, NCH = TT::kCh;
   extern __shared__ __align__(16) float smem[];
@@ -200,273 +246,220 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
   float* atlas = smem + (size_t)warp * 2 * atlas_floats;  // this warp's value atlas
   float* gatlas = atlas + atlas_floats;                   // ... and gradient atlas
   float* red = smem + (size_t)nwarps * 2 * atlas_floats;  // [64] block-reduction scratch
-  float* xs = red + 64;                                   // [W] affine_grid base coordinates
-  float* ys = xs + a.W;                                   // [H]
-  const int HW = a.H * a.W, hw = a.h * a.w, pw = g.pw, ph = g.ph, W = a.W;
-  // [C][H*W] records {x, upstream gradient, cached numerator lse, cached denominator lse} of the current image: every
-  // warp of the CTA works on the same image, so the four global loads (and their 64-bit address arithmetic) that each
-  // (template, pass) would repeat are paid once per unit
-  const bool staged = g.pix_floats > 0;
-  float4* PIX = reinterpret_cast<float4*>(smem + (((size_t)nwarps * 2 * atlas_floats + 64 + a.W + a.H + 3) & ~(size_t)3));
-  // When H*W is not a multiple of 32 the last pass has dead lanes; every plane is followed by 32 pad records
-  // {0, 0, 1e30, 1e30}: upstream gradient 0 and both responsibilities exp(-huge) = 0, so a dead lane computes
-  // exact zeros without any select in the hot loop.
-  const bool all_valid = (HW & 31) == 0;
-  const int HWp = all_valid ? HW : HW + 32;
-  if (staged && !all_valid) {
-    for (int e = threadIdx.x; e < C * 32; e += blockDim.x)
-      PIX[(e >> 5) * HWp + HW + (e & 31)] = make_float4(0.f, 0.f, 1e30f, 1e30f);
-  }
+  // run geometry (tmpl_bwd_plan): k runs of L pixels per row, `walks` walks per image, `bw` walks per staged band
+  const int L = g.tw, Lp = g.ppt, kshift = g.k, kruns = 1 << kshift, walks = g.tiles_y, bw = g.tiles_x;
+  float* xs = red + 64;                                   // [kruns * L] affine_grid base coordinates (0 past W)
+  float* ys = xs + kruns * L;                             // [H]
+  const int HW = a.H * a.W, hw = a.h * a.w, pw = g.pw, ph = g.ph, W = a.W, H = a.H;
+  // records {x, upstream gradient, cached numerator lse, cached denominator lse} of the current band, [C][bw][32][Lp]
+  float4* PIX =
+      reinterpret_cast<float4*>(smem + (((size_t)nwarps * 2 * atlas_floats + 64 + kruns * L + H + 3) & ~(size_t)3));
+  const int plane = bw * 32 * Lp;
+  #pragma unroll 1
   for (int e = lane; e < 2 * atlas_floats; e += 32) atlas[e] = 0.0f;
-  for (int e = threadIdx.x; e < a.W; e += blockDim.x) xs[e] = base_coord(e, a.W);
-  for (int e = threadIdx.x; e < a.H; e += blockDim.x) ys[e] = base_coord(e, a.H);
+  #pragma unroll 1
+  for (int e = threadIdx.x; e < kruns * L; e += blockDim.x) xs[e] = e < W ? base_coord(e, W) : 0.0f;
+  #pragma unroll 1
+  for (int e = threadIdx.x; e < H; e += blockDim.x) ys[e] = base_coord(e, H);
   const TmplScalars sc = tmpl_scalars(a);
   const float lim_x = keep((float)a.w + 2.5f), lim_y = keep((float)a.h + 2.5f);
-  const unsigned row = keep((unsigned)(pw * kPad));
-  // tap offsets are relative to the start of shared memory: the warp's atlas offset is folded into the constant
-  const unsigned atlas_off = (unsigned)(warp * 2 * atlas_floats);
-  const unsigned base0 = keep(atlas_off - kMagicBits * (row + (unsigned)kPad));
-  const unsigned gat = keep((unsigned)atlas_floats);
+  // the hot loop addresses shared memory by 32-bit byte address: tap offsets carry the warp's atlas address, so a tap is
+  // one LDS [reg + imm] and a cell's identity (the flush key) is the address of its north-west texel
+  const unsigned sbase = smem_u32(smem);
+  const unsigned row = keep((unsigned)(pw * kPad * 4));
+  const unsigned atlas_off = sbase + (unsigned)(warp * 2 * atlas_floats) * 4u;
+  const unsigned base0 = keep(atlas_off - kMagicBits * (row + (unsigned)(kPad * 4)));
+  const unsigned gat = keep((unsigned)atlas_floats * 4u);
+  const unsigned pix_addr = smem_u32(PIX), xs_addr = smem_u32(xs);
   const float hw_x = 0.5f * (float)a.w, hw_y = 0.5f * (float)a.h;
-  const float inv_pw = 1.0f / (float)pw;
+  const float inv_pw = 1.0f / (float)pw, inv_L = 1.0f / (float)L;
   float* my_alpha_partial = (kAlpha && out.alpha_partials) ? out.alpha_partials + (size_t)blockIdx.x * a.M * hw : nullptr;
   if (my_alpha_partial)
+    #pragma unroll 1
     for (int e = threadIdx.x; e < a.M * hw; e += blockDim.x) my_alpha_partial[e] = 0.0f;
   // fused colourisation: the batch-shared raw templates get a per-CTA partial row like the alpha logits
   const bool colored = a.template_color != nullptr;
   float* my_raw_partial = colored ? out.raw_partials + (size_t)blockIdx.x * a.M * C * hw : nullptr;
   if (my_raw_partial)
+    #pragma unroll 1
     for (int e = threadIdx.x; e < a.M * C * hw; e += blockDim.x) my_raw_partial[e] = 0.0f;
   ScalarAcc acc;
   __syncthreads();   // partial row zeroed before any warp accumulates into it; xs / ys complete
-  // row / column of this lane's pixel in the first pass, and its advance per pass
-  const int i0 = lane / W, j0 = lane - i0 * W;
-  const int di = 32 / W, dj = 32 - di * W;
+  const int q_lane = lane >> kshift, col0 = (lane & (kruns - 1)) * L;
+  const int nbands = (walks + bw - 1) / bw;
 
   const int groups = g.groups, n_units = a.B * groups;
+  #pragma unroll 1
   for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
     const int b = u / groups, grp = u - b * groups;
     const bool first = grp == 0;   // the background component and g_bg_image belong to the image, not to a template
-    // ---- pixel records of the image (whole CTA) and, once per image, the background component ----------------------
-    if (staged) __syncthreads();                       // the previous unit's records are no longer read
-    if (staged || (first && warp == 0)) {
-      const int p_first = staged ? (int)threadIdx.x : lane, p_step = staged ? (int)blockDim.x : 32;
-      for (int p = p_first; p < HW; p += p_step) {
+    const int m = grp * nwarps + warp;
+    const bool has_m = m < a.M;    // (no early exit: every warp takes part in the band barriers)
+    // ---- per-template setup (all lanes compute the same coefficients) -------------------------------------------
+    const int mm = has_m ? m : 0;
+    const float* pp = a.pose + ((size_t)b * a.M + mm) * 6;
+    const float Ax = __ldg(pp + 0) * hw_x, Bx = __ldg(pp + 1) * hw_x, Cx = (__ldg(pp + 2) + 1.0f) * hw_x + 1.5f;
+    const float Ay = __ldg(pp + 3) * hw_y, By = __ldg(pp + 4) * hw_y, Cy = (__ldg(pp + 5) + 1.0f) * hw_y + 1.5f;
+    const float pres = a.presence ? __ldg(a.presence + (size_t)b * a.M + mm) : 1.0f;
+    const float lpres = a.presence ? log_safe_f(pres) : 0.0f;
+    const float* src = a.templates + ((colored ? (size_t)0 : (size_t)b * a.M) + mm) * C * hw;
+    float colv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) colv[c] = colored ? __ldg(a.template_color + ((size_t)b * a.M + mm) * C + c) : 1.0f;
+    if (has_m) {
+      const float inv_w = 1.0f / (float)a.w;
+      #pragma unroll 1
+      for (int e = lane; e < hw; e += 32) {
+        const int y = (int)(((float)e + 0.5f) * inv_w), xx = e - y * a.w;
+        float* q = atlas + ((size_t)(y + 2) * pw + (xx + 2)) * kPad;
+#pragma unroll
+        for (int c = 0; c < C; ++c) q[c] = __ldg(src + (size_t)c * hw + e) * colv[c];
+        if (kAlpha) q[C] = __ldg(a.templates_alpha + (size_t)mm * hw + e);
+      }
+    }
+    float sgx = 0.f, sgxX = 0.f, sgxY = 0.f, sgy = 0.f, sgyX = 0.f, sgyY = 0.f, spres = 0.f;
+    // the lane's current cell (starts in the border corner, whose gradient is discarded) and its four corner sums
+    unsigned cur_off = atlas_off;
+    float cs[4][NCH];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) cs[k][c] = 0.0f;
+
+    #pragma unroll 1
+    for (int band = 0; band < nbands; ++band) {
+      // ---- pixel records of the band (whole CTA) and, once per image, the background component -------------------
+      __syncthreads();                       // the previous band's records are no longer read
+      const int w0 = band * bw;
+      #pragma unroll 1
+      for (int e = threadIdx.x; e < bw * 32 * L; e += blockDim.x) {
+        const int slot = (int)(((float)e + 0.5f) * inv_L), s = e - slot * L;
+        const int ln = slot & 31, wk = slot >> 5;
+        const int r_img = (ln >> kshift) * walks + w0 + wk, c_img = (ln & (kruns - 1)) * L + s;
+        const bool ok = r_img < H && c_img < W && w0 + wk < walks;
+        const int p = r_img * W + c_img;
         float xv[C], G[C], Nc[C], Dc[C];
         const size_t px0 = (size_t)b * C * HW + p;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           const size_t cx = (size_t)b * 2 * C * HW + (size_t)c * HW + p;
-          xv[c] = __ldg(x + px0 + (size_t)c * HW);
-          G[c] = __ldg(gout + px0 + (size_t)c * HW);
-          Nc[c] = __ldg(cache + cx);
-          Dc[c] = __ldg(cache + cx + (size_t)C * HW);
-          if (staged) PIX[c * HWp + p] = make_float4(xv[c], G[c], Nc[c], Dc[c]);
+          xv[c] = ok ? __ldg(x + px0 + (size_t)c * HW) : 0.0f;
+          G[c] = ok ? __ldg(gout + px0 + (size_t)c * HW) : 0.0f;
+          Nc[c] = ok ? __ldg(cache + cx) : 1e30f;
+          Dc[c] = ok ? __ldg(cache + cx + (size_t)C * HW) : 1e30f;
+          PIX[c * plane + slot * Lp + s] = make_float4(xv[c], G[c], Nc[c], Dc[c]);
         }
-        if (first) bwd_background<C, kAlpha, kMode>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
+        if (first && ok) bwd_background<C, kAlpha, kMode>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
       }
-    }
-    if (staged) __syncthreads();
-    for (int tt = 0; tt < g.mc; ++tt) {
-      const int m = (grp * g.mc + tt) * nwarps + warp;
-      if (m >= a.M) break;
-      // ---- per-template setup (all lanes compute the same coefficients) -----------------------------------------
-      const float* pp = a.pose + ((size_t)b * a.M + m) * 6;
-      const float Ax = __ldg(pp + 0) * hw_x, Bx = __ldg(pp + 1) * hw_x, Cx = (__ldg(pp + 2) + 1.0f) * hw_x + 1.5f;
-      const float Ay = __ldg(pp + 3) * hw_y, By = __ldg(pp + 4) * hw_y, Cy = (__ldg(pp + 5) + 1.0f) * hw_y + 1.5f;
-      const float pres = a.presence ? __ldg(a.presence + (size_t)b * a.M + m) : 1.0f;
-      const float lpres = a.presence ? log_safe_f(pres) : 0.0f;
-      const float* src = a.templates + ((colored ? (size_t)0 : (size_t)b * a.M) + m) * C * hw;
-      float colv[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) colv[c] = colored ? __ldg(a.template_color + ((size_t)b * a.M + m) * C + c) : 1.0f;
-      {
-        const float inv_w = 1.0f / (float)a.w;
-        for (int e = lane; e < hw; e += 32) {
-          const int y = (int)(((float)e + 0.5f) * inv_w), xx = e - y * a.w;
-          float* q = atlas + ((size_t)(y + 2) * pw + (xx + 2)) * kPad;
-#pragma unroll
-          for (int c = 0; c < C; ++c) q[c] = __ldg(src + (size_t)c * hw + e) * colv[c];
-          if (kAlpha) q[C] = __ldg(a.templates_alpha + (size_t)m * hw + e);
-        }
-      }
-      __syncwarp();
-      float sgx = 0.f, sgxX = 0.f, sgxY = 0.f, sgy = 0.f, sgyX = 0.f, sgyY = 0.f, spres = 0.f;
-
-      // ---- passes of 32 consecutive pixels (row-major) -----------------------------------------------------------
-      int i = i0, j = j0;
-      const float4* pix_ptr = PIX + lane;     // loop-carried pointer: one IADD per pass instead of a re-derived address
-      for (int p0 = 0; p0 < HW; p0 += 32, pix_ptr += 32) {
-        const int p = p0 + lane;
-        const bool valid = p < HW;
-        float xv[C], G[C], Nc[C], Dc[C];
-        if (staged) {
+      __syncthreads();
+      if (!has_m) continue;
+      // ---- walks of the band: 32 runs in lock-step, one pixel per lane per step -----------------------------------
+      #pragma unroll 1
+      for (int wk = 0; wk < bw && w0 + wk < walks; ++wk) {
+        const int r_img = q_lane * walks + w0 + wk;
+        const float Y = ys[r_img < H ? r_img : H - 1];       // (a dead run reads pad records: every contribution is 0)
+        const float yx = fmaf(Y, Bx, Cx), yy = fmaf(Y, By, Cy);
+        unsigned xa = keep(xs_addr + (unsigned)col0 * 4u);                        // loop-carried addresses: X of the
+        unsigned ra = keep(pix_addr + (unsigned)((wk * 32 + lane) * Lp) * 16u);   // lane's column, its pixel record
+        float wgx = 0.f, wgy = 0.f;
+        #pragma unroll 1
+        for (int s = 0; s < L; ++s, xa += 4u, ra += 16u) {
+          float xv[C], G[C], Nc[C], Dc[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const float4 r4 = pix_ptr[c * HWp];     // a dead lane reads a pad record
+            const float4 r4 = lds_f32x4(ra + (unsigned)(c * plane) * 16u);
             xv[c] = r4.x;
             G[c] = r4.y;
             Nc[c] = r4.z;
             Dc[c] = r4.w;
           }
-        } else {
-          const int pc = valid ? p : 0;
+          const float X = lds_f32(xa);
+          Tap t;
+          tap_setup<kPad, 4>(fmaf(X, Ax, yx), fmaf(X, Ay, yy), lim_x, lim_y, row, base0, t);
+          const Texel<kPad> t00 = lds_texel<kPad>(t.off), t10 = lds_texel<kPad>(t.off + kPad * 4);
+          const Texel<kPad> t01 = lds_texel<kPad>(t.off + row), t11 = lds_texel<kPad>(t.off + row + kPad * 4);
+          float glp, gtx, gty;
+          const Texel<kPad> gv =
+              bwd_pixel<C, kAlpha, kPad, kMode>(sc, t00, t10, t01, t11, t, lpres, xv, G, Nc, Dc, acc, glp, gtx, gty, (float)m);
+          wgx += gtx;
+          sgxX = fmaf(gtx, X, sgxX);
+          wgy += gty;
+          sgyX = fmaf(gty, X, sgyX);
+          spres += glp;
+          // ---- the cell changed: hand the finished sums to the gradient atlas ---------------------------------------
+          const bool changed = t.off != cur_off;
+          if (__any_sync(0xffffffffu, changed)) flush_cells<kPad, NCH>(gat, row, lane, changed, cur_off, t.off, cs);
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const size_t px = (size_t)b * C * HW + (size_t)c * HW + pc;
-            const size_t cx = (size_t)b * 2 * C * HW + (size_t)c * HW + pc;
-            xv[c] = __ldg(x + px);
-            G[c] = valid ? __ldg(gout + px) : 0.0f;
-            Nc[c] = __ldg(cache + cx);
-            Dc[c] = __ldg(cache + cx + (size_t)C * HW);
+          for (int c = 0; c < NCH; ++c) {
+            cs[0][c] = fmaf(gv.v[c], t.w00, cs[0][c]);
+            cs[1][c] = fmaf(gv.v[c], t.w10, cs[1][c]);
+            cs[2][c] = fmaf(gv.v[c], t.w01, cs[2][c]);
+            cs[3][c] = fmaf(gv.v[c], t.w11, cs[3][c]);
           }
         }
-        const float X = xs[valid ? j : 0], Y = ys[valid ? i : 0];
-        i += di;                         // advance to the next pass
-        j += dj;
-        if (j >= W) {
-          j -= W;
-          ++i;
-        }
-        Tap t;
-        tap_setup<kPad>(fmaf(Y, Bx, fmaf(X, Ax, Cx)), fmaf(Y, By, fmaf(X, Ay, Cy)), lim_x, lim_y, row, base0, t);
-        const float* q = smem + t.off;
-        const Texel<kPad> t00 = ld_texel<kPad>(q), t10 = ld_texel<kPad>(q + kPad);
-        const Texel<kPad> t01 = ld_texel<kPad>(q + row), t11 = ld_texel<kPad>(q + row + kPad);
-        float glp, gtx, gty;
-        const Texel<kPad> gv =
-            bwd_pixel<C, kAlpha, kPad, kMode>(sc, t00, t10, t01, t11, t, lpres, xv, G, Nc, Dc, acc, glp, gtx, gty, (float)m);
-        sgx += gtx;
-        sgxX = fmaf(gtx, X, sgxX);
-        sgxY = fmaf(gtx, Y, sgxY);
-        sgy += gty;
-        sgyX = fmaf(gty, X, sgyX);
-        sgyY = fmaf(gty, Y, sgyY);
-        spres += glp;
-
-        // Cells that touch no interior texel land in the zero border, whose gradient is discarded.  Parts cover a
-        // fraction of the image, so whole passes miss the template: they keep their logit / presence gradient (above) and
-        // skip the scatter.
-        if (!__any_sync(0xffffffffu, valid && t.interior)) continue;
-        // ---- segmented scan over lanes that share (row, cell) -------------------------------------------------------
-        // the base-grid Y is strictly increasing with the row, so "same row" is "same Y"
-        float v[4][NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          v[0][c] = gv.v[c] * t.w00;
-          v[1][c] = gv.v[c] * t.w10;
-          v[2][c] = gv.v[c] * t.w01;
-          v[3][c] = gv.v[c] * t.w11;
-        }
-        const unsigned key = valid ? t.off : 0xFFFFFFFFu;
-        const unsigned key_prev = __shfl_up_sync(0xffffffffu, key, 1);
-        const float y_prev = __shfl_up_sync(0xffffffffu, Y, 1);
-        const bool head = lane == 0 || key != key_prev || Y != y_prev;
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        const int seg_start = 31 - __clz(heads & (0xFFFFFFFFu >> (31 - lane)));
-        const int dist = lane - seg_start;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          if (__ballot_sync(0xffffffffu, dist >= d) == 0u) break;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-              const float up = __shfl_up_sync(0xffffffffu, v[k][c], d);
-              if (dist >= d) v[k][c] += up;
-            }
-        }
-        const bool tail = valid && (lane == 31 || ((heads >> (lane + 1)) & 1u));
-        // ---- segment tails update the warp's gradient atlas: corner by corner, row by row => no address collisions ---
-        const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
-        const float y_first = __shfl_sync(0xffffffffu, Y, 0);
-        const float y_last = __shfl_sync(0xffffffffu, Y, 31 - __clz(valid_mask));
-        float* gq = smem + (t.off + gat);
-        // A pass of 32 consecutive pixels can straddle image rows.  Within one row the cells of different segments are
-        // distinct; across rows they could coincide (extreme magnification), so check once with MATCH and only then
-        // fall back to updating row by row.
-        bool by_row = false;
-        if (y_first != y_last) {
-          const unsigned tails = __ballot_sync(0xffffffffu, tail);
-          const unsigned peers = __match_any_sync(0xffffffffu, tail ? key : (0xFFFFFF00u | (unsigned)lane));
-          by_row = __any_sync(0xffffffffu, tail && (peers & tails & ~(1u << lane)) != 0u);
-        }
-        if (!by_row) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (tail) texel_add<kPad, NCH>(gq + (k & 1 ? kPad : 0) + (k & 2 ? row : 0), v[k]);
-            __syncwarp();
-          }
-        } else {
-          float y_cur = y_first;
-          for (;;) {
-            const bool mine = tail && Y == y_cur;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (mine) texel_add<kPad, NCH>(gq + (k & 1 ? kPad : 0) + (k & 2 ? row : 0), v[k]);
-              __syncwarp();
-            }
-            const unsigned later = __ballot_sync(0xffffffffu, valid && Y > y_cur);
-            if (later == 0u) break;
-            y_cur = __shfl_sync(0xffffffffu, Y, __ffs(later) - 1);
-          }
-        }
+        sgx += wgx;                  // Y is constant along a run
+        sgxY = fmaf(wgx, Y, sgxY);
+        sgy += wgy;
+        sgyY = fmaf(wgy, Y, sgyY);
       }
-
-      // ---- pose / presence gradients of (b, m) -------------------------------------------------------------------
-      {
-        float v7[7] = {sgxX, sgxY, sgx, sgyX, sgyY, sgy, spres};
-#pragma unroll
-        for (int q7 = 0; q7 < 7; ++q7) v7[q7] = warp_sum(v7[q7]);
-        if (lane == 0) {
-          float* gp = out.g_pose + ((size_t)b * a.M + m) * 6;
-          gp[0] = v7[0] * hw_x;
-          gp[1] = v7[1] * hw_x;
-          gp[2] = v7[2] * hw_x;
-          gp[3] = v7[3] * hw_y;
-          gp[4] = v7[4] * hw_y;
-          gp[5] = v7[5] * hw_y;
-          if (out.g_presence) out.g_presence[(size_t)b * a.M + m] = pres < kLogSafeEps ? 0.0f : v7[6] / pres;
-        }
-      }
-      __syncwarp();
-      // ---- flush + clear the gradient atlas ----------------------------------------------------------------------
-      {
-        float* dst = colored ? my_raw_partial + (size_t)m * C * hw : out.g_templates + ((size_t)b * a.M + m) * C * hw;
-        float gcol[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) gcol[c] = 0.0f;
-        for (int e = lane; e < pw * ph; e += 32) {
-          const int yy = (int)(((float)e + 0.5f) * inv_pw), xx = e - yy * pw;
-          float* q = gatlas + (size_t)e * kPad;
-          if (yy >= 2 && yy < ph - 2 && xx >= 2 && xx < pw - 2) {
-            const int te = (yy - 2) * a.w + (xx - 2);
-            if (colored) {
-              // template = raw * colour: d/d raw = colour * g (summed over the batch), d/d colour = sum_texels raw * g
-#pragma unroll
-              for (int c = 0; c < C; ++c) {
-                dst[(size_t)c * hw + te] += colv[c] * q[c];
-                gcol[c] = fmaf(__ldg(src + (size_t)c * hw + te), q[c], gcol[c]);
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < C; ++c) dst[(size_t)c * hw + te] = q[c];
-            }
-            if (kAlpha && my_alpha_partial) my_alpha_partial[(size_t)m * hw + te] += q[C];
-          }
-#pragma unroll
-          for (int c = 0; c < kPad; ++c) q[c] = 0.0f;
-        }
-        if (colored) {
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float t = warp_sum(gcol[c]);
-            if (lane == 0) out.g_color[((size_t)b * a.M + m) * C + c] = t;
-          }
-        }
-      }
-      __syncwarp();
     }
+    if (!has_m) continue;
+    flush_cells<kPad, NCH>(gat, row, lane, true, cur_off, atlas_off, cs);
+
+    // ---- pose / presence gradients of (b, m) -------------------------------------------------------------------
+    {
+      float v7[7] = {sgxX, sgxY, sgx, sgyX, sgyY, sgy, spres};
+#pragma unroll
+      for (int q7 = 0; q7 < 7; ++q7) v7[q7] = warp_sum(v7[q7]);
+      if (lane == 0) {
+        float* gp = out.g_pose + ((size_t)b * a.M + m) * 6;
+        gp[0] = v7[0] * hw_x;
+        gp[1] = v7[1] * hw_x;
+        gp[2] = v7[2] * hw_x;
+        gp[3] = v7[3] * hw_y;
+        gp[4] = v7[4] * hw_y;
+        gp[5] = v7[5] * hw_y;
+        if (out.g_presence) out.g_presence[(size_t)b * a.M + m] = pres < kLogSafeEps ? 0.0f : v7[6] / pres;
+      }
+    }
+    __syncwarp();
+    // ---- flush + clear the gradient atlas ----------------------------------------------------------------------
+    {
+      float* dst = colored ? my_raw_partial + (size_t)m * C * hw : out.g_templates + ((size_t)b * a.M + m) * C * hw;
+      float gcol[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) gcol[c] = 0.0f;
+      #pragma unroll 1
+      for (int e = lane; e < pw * ph; e += 32) {
+        const int yy = (int)(((float)e + 0.5f) * inv_pw), xx = e - yy * pw;
+        float* q = gatlas + (size_t)e * kPad;
+        if (yy >= 2 && yy < ph - 2 && xx >= 2 && xx < pw - 2) {
+          const int te = (yy - 2) * a.w + (xx - 2);
+          if (colored) {
+            // template = raw * colour: d/d raw = colour * g (summed over the batch), d/d colour = sum_texels raw * g
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              dst[(size_t)c * hw + te] += colv[c] * q[c];
+              gcol[c] = fmaf(__ldg(src + (size_t)c * hw + te), q[c], gcol[c]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) dst[(size_t)c * hw + te] = q[c];
+          }
+          if (kAlpha && my_alpha_partial) my_alpha_partial[(size_t)m * hw + te] += q[C];
+        }
+#pragma unroll
+        for (int c = 0; c < kPad; ++c) q[c] = 0.0f;
+      }
+      if (colored) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float t = warp_sum(gcol[c]);
+          if (lane == 0) out.g_color[((size_t)b * a.M + m) * C + c] = t;
+        }
+      }
+    }
+    __syncwarp();
   }
   write_scalar_partials(a, sc, kAlpha, acc, red, out.scalar_partials + (size_t)blockIdx.x * 4);
 }
@@ -477,45 +470,71 @@ __global__ void __launch_bounds__(kScanThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_scan
 static int tmpl_bwd_plan(const scae_tmpl_args* a, TmplGeom* gp) {
   const int kpad = tmpl_texel_floats(a);
   const size_t limit = (size_t)max_smem_optin();
-  // one padded value atlas + one gradient atlas per warp, nothing that scales with the image
+  const size_t per_sm = limit + 1024;               // shared memory of one SM; every resident CTA also pays 1 KB
   TmplGeom& g = *gp;
   memset(&g, 0, sizeof(g));
   g.pw = a->w + 4;
   g.ph = a->h + 4;
   g.atlas_floats = (int)(((size_t)g.pw * g.ph * kpad + 3) / 4 * 4);
-  int threads = kScanThreads;
-  size_t smem;
-  for (;;) {
-    smem = ((size_t)(threads / 32) * 2 * g.atlas_floats + 64 + a->W + a->H + 8) * sizeof(float);
-    if (smem <= limit || threads == 32) break;
-    threads /= 2;                                   // very large templates: fewer warps per CTA
-  }
-  SCAE_REQUIRE(smem <= limit, SCAE_ELIMIT, "tmpl bwd: a %dx%d template does not fit in shared memory", a->h, a->w);
-  const int warps = threads / 32;
-  // per-image pixel records in shared memory when at least two CTAs per SM still fit (each CTA also pays 1 KB reserved)
-  {
-    const size_t hw = (size_t)a->H * a->W, hwp = (hw & 31) == 0 ? hw : hw + 32;   // + pad records for dead lanes
-    const size_t pix_bytes = 4 * a->C * hwp * sizeof(float) + 16;
-    const char* e = getenv("SCAE_TMPL_BWD_STAGE");
-    const bool allow = e == nullptr || strcmp(e, "0") != 0;
-    if (allow && 2 * (smem + pix_bytes + 1024) <= limit + 1024) {
-      g.pix_floats = (int)(4 * a->C * hwp);
-      smem += pix_bytes;
+  // ---- runs: k = 2^kshift runs of L pixels per row, 32 / k rows per walk.  Lane efficiency first, then long runs
+  //      (every run ends with a flush) ---------------------------------------------------------------------------------
+  int best_shift = 0;
+  double best_score = -1.0;
+  for (int sh = 0; sh <= 5; ++sh) {
+    const int k = 1 << sh, L = (a->W + k - 1) / k, rows = 32 / k, walks = (a->H + rows - 1) / rows;
+    if (sh > 0 && L < 2) break;
+    const double eff = (double)a->H * a->W / ((double)walks * 32 * L);
+    const double score = eff * L / (L + 1.0);
+    if (score > best_score * 1.0001) {
+      best_score = score;
+      best_shift = sh;
     }
   }
-  // work units: (image, group of warps x mc templates).  With staged pixel records a unit is one template per warp;
-  // without them a unit is the whole image, so that the pixel data re-read from global memory stays in the CTA's L1.
-  g.mc = g.pix_floats > 0 ? 1 : (a->M + warps - 1) / warps;
-  g.groups = (a->M + warps * g.mc - 1) / (warps * g.mc);
-  g.threads = threads;
-  g.smem_bytes = smem;
-  int per_sm = (int)((limit + 1024) / (smem + 1024));
-  const int by_threads = 2048 / threads;
-  if (per_sm > by_threads) per_sm = by_threads;
-  const int cap = a->C == 1 ? 4 : 3;               // compiled with __launch_bounds__(256, C == 1 ? 4 : 3)
-  if (per_sm > cap) per_sm = cap;
-  if (per_sm < 1) per_sm = 1;
-  const long slots = (long)sm_count() * per_sm;
+  const int k = 1 << best_shift, L = (a->W + k - 1) / k, walks = (a->H + 32 / k - 1) / (32 / k);
+  g.k = best_shift;
+  g.tw = L;
+  g.tiles_y = walks;
+  const int cap = a->C == 1 ? 4 : 3;                // compiled with __launch_bounds__(256, C == 1 ? 4 : 3)
+  int threads = kRunThreads;
+  for (;;) {
+    // one padded value atlas + one gradient atlas per warp, block scratch, coordinate tables
+    const size_t fixed = ((size_t)(threads / 32) * 2 * g.atlas_floats + 64 + (size_t)k * L + a->H + 8) * sizeof(float);
+    // band of `bw` walks of pixel records at run pitch Lp; the whole image at the highest occupancy if it fits, else
+    // the largest band two CTAs per SM leave room for, else one CTA per SM.  An odd pitch keeps the record loads free
+    // of bank conflicts and is taken when it costs no occupancy.
+    for (int occ = cap; occ >= 1 && g.threads == 0; --occ) {
+      size_t budget = per_sm / occ - 1024;
+      if (budget > limit) budget = limit;
+      if (budget < fixed + 16) continue;
+      for (int odd = 1; odd >= 0 && g.threads == 0; --odd) {
+        const int Lp = odd ? (L | 1) : L;
+        const size_t walk_bytes = (size_t)16 * a->C * 32 * Lp;
+        int bw = (int)((budget - fixed - 16) / walk_bytes);
+        if (bw > walks) bw = walks;
+        if (bw < 1) continue;
+        if (bw < walks && occ > 2) continue;          // bands instead of the whole image only at <= 2 CTAs per SM
+        g.ppt = Lp;
+        g.tiles_x = bw;
+        g.pix_floats = (int)(walk_bytes / 4 * bw);
+        g.threads = threads;
+        g.smem_bytes = fixed + 16 + walk_bytes * bw;
+      }
+    }
+    if (g.threads != 0 || threads == 32) break;
+    threads /= 2;                                   // very large templates: fewer warps per CTA
+  }
+  SCAE_REQUIRE(g.threads != 0, SCAE_ELIMIT, "tmpl bwd: a %dx%d template with a %dx%d image does not fit in shared memory",
+               a->h, a->w, a->H, a->W);
+  const int warps = g.threads / 32;
+  // work units: (image, group of `warps` templates), one template per warp
+  g.mc = 1;
+  g.groups = (a->M + warps - 1) / warps;
+  int per = (int)(per_sm / (g.smem_bytes + 1024));
+  const int by_threads = 2048 / g.threads;
+  if (per > by_threads) per = by_threads;
+  if (per > cap) per = cap;
+  if (per < 1) per = 1;
+  const long slots = (long)sm_count() * per;
   const long units = (long)a->B * g.groups;
   g.grid = units < slots ? (int)units : (int)slots;
   return SCAE_OK;
@@ -563,7 +582,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_bwd(
   TmplBwdOut out{g_templates, g_color, a->template_color ? raw_partials : nullptr, g_pose, g_presence, g_bg_image,
                  (alpha && g_alpha) ? alpha_partials : nullptr, scalar_partials};
   SCAE_TMPL_DISPATCH(a->C, alpha, {
-    auto kern = tmpl_ll_bwd_scan_kernel<kC, kA, false>;
+    auto kern = tmpl_ll_bwd_run_kernel<kC, kA, false>;
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
     if (rc != SCAE_OK) return rc;
     kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, x, grad_log_prob, cache, out, g);
@@ -610,7 +629,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_mode_bwd(
   TmplBwdOut out{g_templates, g_color, a->template_color ? raw_partials : nullptr, g_pose, nullptr, g_bg_image, nullptr,
                  scalar_partials};
   SCAE_TMPL_DISPATCH(a->C, alpha, {
-    auto kern = tmpl_ll_bwd_scan_kernel<kC, kA, true>;
+    auto kern = tmpl_ll_bwd_run_kernel<kC, kA, true>;
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
     if (rc != SCAE_OK) return rc;
     kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, grad_mode, grad_mode, component_cache, out, g);

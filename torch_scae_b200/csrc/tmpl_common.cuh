@@ -29,12 +29,12 @@ struct TexTraits {
 // How one image is mapped on a CTA: threads form `k` row-groups of `tw` columns; a thread owns column j and rows
 // r, r+k, r+2k, ... (`ppt` of them) of the current pixel tile.
 struct TmplGeom {
-  int tw, k, ppt, threads;
-  int tiles_x, tiles_y;
+  int tw, k, ppt, threads;   // backward (tmpl_bwd_plan): tw = run length L, k = log2(runs per row), ppt = record pitch of a run
+  int tiles_x, tiles_y;      // backward: tiles_x = walks per staged band, tiles_y = walks per image
   int mc;             // forward: templates per shared-memory chunk; backward: templates per warp per work unit
   int pw, ph;         // padded atlas width / height
   int atlas_floats;   // floats of one atlas (mc templates), rounded up to a multiple of 4 to keep 16-byte alignment
-  int pix_floats;     // backward: floats of the per-image pixel record tile (0 = read x / grad / cache from global)
+  int pix_floats;     // backward: floats of the pixel-record tile of one band
   int groups;         // backward: template groups per image (work unit = image x group of `warps per CTA` templates)
   int grid;
   size_t smem_bytes;
@@ -86,6 +86,34 @@ __device__ __forceinline__ void st_texel<4>(float* p, const Texel<4>& t) {
   *reinterpret_cast<float4*>(p) = make_float4(t.v[0], t.v[1], t.v[2], t.v[3]);
 }
 
+// texel at a 32-bit shared-memory address
+template <int N>
+__device__ __forceinline__ Texel<N> lds_texel(unsigned addr);
+template <>
+__device__ __forceinline__ Texel<1> lds_texel<1>(unsigned addr) {
+  Texel<1> t;
+  t.v[0] = lds_f32(addr);
+  return t;
+}
+template <>
+__device__ __forceinline__ Texel<2> lds_texel<2>(unsigned addr) {
+  const float2 q = lds_f32x2(addr);
+  Texel<2> t;
+  t.v[0] = q.x;
+  t.v[1] = q.y;
+  return t;
+}
+template <>
+__device__ __forceinline__ Texel<4> lds_texel<4>(unsigned addr) {
+  const float4 q = lds_f32x4(addr);
+  Texel<4> t;
+  t.v[0] = q.x;
+  t.v[1] = q.y;
+  t.v[2] = q.z;
+  t.v[3] = q.w;
+  return t;
+}
+
 // ATen affine_grid base coordinates, align_corners=False: linspace(-1, 1, n) * (n - 1) / n, mirroring ATen's
 // symmetric linspace (RangeFactories) and the two-step scaling of AffineGridGenerator.cpp::linspace_from_neg_one.
 __device__ __forceinline__ float base_coord(int i, int n) {
@@ -130,7 +158,8 @@ struct Tap {
 
 // tx, ty: atlas coordinates (texel coordinate + 2).  lim_x = w + 2.5, lim_y = h + 2.5.  row = pw * kPad,
 // base = template offset - kMagicBits * (row + kPad) (unsigned wrap-around arithmetic).
-template <int kPad>
+// kUnit = 4: `row` and `base` in bytes, t.off a shared-memory byte address (the backward kernel's explicit LDS / STS).
+template <int kPad, int kUnit = 1>
 __device__ __forceinline__ void tap_setup(float tx, float ty, float lim_x, float lim_y, unsigned row, unsigned base,
                                           Tap& t) {
   tx = fminf(fmaxf(tx, 0.5f), lim_x);
@@ -140,7 +169,7 @@ __device__ __forceinline__ void tap_setup(float tx, float ty, float lim_x, float
   t.interior = tx >= 1.0f && tx < lim_x - 0.5f && ty >= 1.0f && ty < lim_y - 0.5f;
   t.fx = tx - (ux - kMagic);
   t.fy = ty - (uy - kMagic);
-  t.off = __float_as_uint(uy) * row + __float_as_uint(ux) * (unsigned)kPad + base;
+  t.off = __float_as_uint(uy) * row + __float_as_uint(ux) * (unsigned)(kPad * kUnit) + base;
   const float gx1 = 1.0f - t.fx, gy1 = 1.0f - t.fy;
   t.w00 = gx1 * gy1;
   t.w10 = t.fx * gy1;
