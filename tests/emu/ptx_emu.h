@@ -85,6 +85,24 @@ inline float4 lds_f32x4(unsigned addr) { return *reinterpret_cast<const float4*>
 inline void sts_f32(unsigned addr, float v) { *reinterpret_cast<float*>((char*)emu_dynamic_smem + addr) = v; }
 inline void sts_u32(unsigned addr, unsigned v) { *reinterpret_cast<unsigned*>((char*)emu_dynamic_smem + addr) = v; }
 inline float2 lds_f32x2(unsigned addr) { return *reinterpret_cast<const float2*>((const char*)emu_dynamic_smem + addr); }
+inline void lds_pred_f32(unsigned addr, float& a, bool pred) {
+  if (pred) a = lds_f32(addr);
+}
+inline void lds_pred_f32x2(unsigned addr, float& a, float& b, bool pred) {
+  const float* p = reinterpret_cast<const float*>((const char*)emu_dynamic_smem + addr);
+  if (pred) a = p[0], b = p[1];
+}
+inline void lds_pred_f32x4(unsigned addr, float& a, float& b, float& c, float& d, bool pred) {
+  const float* p = reinterpret_cast<const float*>((const char*)emu_dynamic_smem + addr);
+  if (pred) a = p[0], b = p[1], c = p[2], d = p[3];
+}
+inline void sts_pred_u32(unsigned addr, unsigned v, bool pred) {
+  if (pred) sts_u32(addr, v);
+}
+inline void sts_pred_f32x4(unsigned addr, float a, float b, float c, float d, bool pred) {
+  float* p = reinterpret_cast<float*>((char*)emu_dynamic_smem + addr);
+  if (pred) p[0] = a, p[1] = b, p[2] = c, p[3] = d;
+}
 inline void smem_add_pred_f32(unsigned addr, float a, bool pred) {
   if (pred) *reinterpret_cast<float*>((char*)emu_dynamic_smem + addr) += a;
 }

@@ -14,6 +14,11 @@ log "pytest_tmpl rc=$? $(tail -1 gpurun_out/pytest_tmpl.txt)"
 timeout 300 python tools/kernel_bench.py --configs mnist32,stress,color --batches 1024,8192 --iters 10 --only tmpl \
     > gpurun_out/kernel_bench_tmpl.jsonl 2> gpurun_out/kernel_bench_tmpl.err
 log "kernel_bench rc=$?"
+for v in $TMPL_VARIANTS; do
+    env $v timeout 300 python tools/kernel_bench.py --configs mnist32,stress --batches 1024 --iters 10 --only tmpl \
+        > gpurun_out/kernel_bench_tmpl_$v.jsonl 2> gpurun_out/kernel_bench_tmpl_$v.err
+    log "kernel_bench $v rc=$?"
+done
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'tmpl_ll_bwd' -s 3 -c 1 -o gpurun_out/prof_tmpl_bwd \
     python tools/kernel_bench.py --configs mnist32 --batches 1024 --iters 2 --only tmpl > gpurun_out/ncu_tmpl.log 2>&1
 log "ncu tmpl rc=$?"

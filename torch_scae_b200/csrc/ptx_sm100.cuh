@@ -82,6 +82,36 @@ __device__ __forceinline__ float2 lds_f32x2(unsigned addr) {   // 8-byte aligned
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
   return v;
 }
+// Predicated loads: the destination keeps its value where `pred` does not hold.
+__device__ __forceinline__ void lds_pred_f32(unsigned addr, float& a, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.f32 %0, [%1];\n\t}"
+               : "+f"(a)
+               : "r"(addr), "r"((unsigned)pred)
+               : "memory");
+}
+__device__ __forceinline__ void lds_pred_f32x2(unsigned addr, float& a, float& b, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.shared.v2.f32 {%0, %1}, [%2];\n\t}"
+               : "+f"(a), "+f"(b)
+               : "r"(addr), "r"((unsigned)pred)
+               : "memory");
+}
+__device__ __forceinline__ void lds_pred_f32x4(unsigned addr, float& a, float& b, float& c, float& d, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+f"(a), "+f"(b), "+f"(c), "+f"(d)
+               : "r"(addr), "r"((unsigned)pred)
+               : "memory");
+}
+// Predicated stores.
+__device__ __forceinline__ void sts_pred_u32(unsigned addr, unsigned v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v),
+               "r"((unsigned)pred)
+               : "memory");
+}
+__device__ __forceinline__ void sts_pred_f32x4(unsigned addr, float a, float b, float c, float d, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(addr),
+               "f"(a), "f"(b), "f"(c), "f"(d), "r"((unsigned)pred)
+               : "memory");
+}
 // Predicated read-modify-write of 1 / 2 / 4 consecutive floats: [addr] += v where `pred` holds, as predicated
 // instructions (no branch, no reconvergence bookkeeping).  Callers guarantee that the lanes with `pred` set use distinct
 // addresses.

@@ -197,34 +197,76 @@ __device__ __forceinline__ void texel_add_pred(unsigned addr, float v0, float v1
 }
 #define SCAE_CORNER(k) acc[k][0], acc[k][NCH > 1 ? 1 : 0], NCH > 2 ? acc[k][NCH > 2 ? 2 : 0] : 0.0f, NCH > 3 ? acc[k][NCH > 3 ? 3 : 0] : 0.0f
 
-// Lanes with `fl` set add their corner sums to the cell at shared address `cur_off` (+ gat: the warp's gradient atlas)
-// and start the cell `new_off`.  Lanes that flush the same cell take turns in lane order.
+// ---- per-warp queue of finished cells ----------------------------------------------------------------------------------
+// A lane that leaves a cell appends {cell address, four corner sums} to its warp's queue in shared memory (a ring of
+// kQueueCap entries: keys [cap] u32, sums [cap][kPad] float4).  Cells change for a few lanes in nearly every step, so
+// handing them to the gradient atlas right away would run the read-modify-write sequence at 10-20 % lane utilisation;
+// the queue is drained 32 entries at a time instead, one entry per lane.
+constexpr int kQueueCap = 64;          // >= 2 x 32: an append of up to 32 entries always fits after a drain
+constexpr int kQueueDrainAt = kQueueCap - 32;
+
+struct CellQueue {
+  unsigned keys, sums;    // shared-memory byte addresses of the two arrays
+  unsigned head, tail;    // monotonic entry counters (warp-uniform); slot = counter & (kQueueCap - 1)
+};
+
+// lanes with `on` set append (cell, sums); `lane_lt` = mask of the lower lanes
 template <int kPad, int NCH>
-__device__ __forceinline__ void flush_cells(unsigned gat, unsigned row, int lane, bool fl, unsigned& cur_off,
-                                            unsigned new_off, float (&acc)[4][NCH]) {
-  const unsigned peers = __match_any_sync(0xffffffffu, fl ? cur_off : (0xFFFFFF00u | (unsigned)lane));
-  const unsigned rank = (unsigned)__popc(peers & ((1u << lane) - 1u));
-  const unsigned turns = redux_max_u32(0xffffffffu, fl ? rank + 1u : 0u);
-  const unsigned ga = cur_off + gat, gb = ga + row;
-#pragma unroll 1
-  for (unsigned r = 0; r < turns; ++r) {
-    const bool mine = fl && rank == r;
-    texel_add_pred<kPad>(ga, SCAE_CORNER(0), mine);
-    __syncwarp();
-    texel_add_pred<kPad>(ga + kPad * 4, SCAE_CORNER(1), mine);
-    __syncwarp();
-    texel_add_pred<kPad>(gb, SCAE_CORNER(2), mine);
-    __syncwarp();
-    texel_add_pred<kPad>(gb + kPad * 4, SCAE_CORNER(3), mine);
-    __syncwarp();
-  }
-  if (fl) {
+__device__ __forceinline__ void queue_append(CellQueue& q, unsigned on_mask, bool on, unsigned lane_lt, unsigned cell,
+                                             const float (&acc)[4][NCH]) {
+  const unsigned slot = (q.tail + (unsigned)__popc(on_mask & lane_lt)) & (unsigned)(kQueueCap - 1);
+  sts_pred_u32(q.keys + slot * 4u, cell, on);
+  const unsigned va = q.sums + slot * (unsigned)(16 * kPad);
+  if (kPad == 1) {
+    sts_pred_f32x4(va, acc[0][0], acc[1][0], acc[2][0], acc[3][0], on);
+  } else if (kPad == 2) {
+    sts_pred_f32x4(va, acc[0][0], acc[0][NCH > 1 ? 1 : 0], acc[1][0], acc[1][NCH > 1 ? 1 : 0], on);
+    sts_pred_f32x4(va + 16u, acc[2][0], acc[2][NCH > 1 ? 1 : 0], acc[3][0], acc[3][NCH > 1 ? 1 : 0], on);
+  } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) acc[k][c] = 0.0f;
-    cur_off = new_off;
+      sts_pred_f32x4(va + 16u * k, acc[k][0], acc[k][NCH > 1 ? 1 : 0], acc[k][NCH > 2 ? 2 : 0],
+                     NCH > 3 ? acc[k][NCH > 3 ? 3 : 0] : 0.0f, on);
   }
+  q.tail += (unsigned)__popc(on_mask);
+}
+
+// The (up to) 32 oldest entries, one per lane, go to the warp's gradient atlas (shared address cell + gat).  Entries of
+// the same cell take turns in queue order; within a turn all cells are distinct and the corners are updated one after
+// the other, so no two lanes touch an address in the same instruction and the summation order is fixed.
+template <int kPad>
+__device__ __forceinline__ void queue_drain(CellQueue& q, unsigned gat, unsigned row, int lane, unsigned lane_lt) {
+  __syncwarp();                                   // the appended entries are visible to the whole warp
+  const unsigned cnt = q.tail - q.head, n = cnt < 32u ? cnt : 32u;
+  const bool have = (unsigned)lane < n;
+  const unsigned slot = (q.head + (unsigned)lane) & (unsigned)(kQueueCap - 1);
+  const unsigned cell = have ? lds_u32(q.keys + slot * 4u) : (0xFFFFFF00u | (unsigned)lane);
+  float e[4 * kPad];
+#pragma unroll
+  for (int p4 = 0; p4 < kPad; ++p4) {
+    const float4 v = lds_f32x4(q.sums + slot * (unsigned)(16 * kPad) + 16u * p4);
+    e[4 * p4 + 0] = v.x, e[4 * p4 + 1] = v.y, e[4 * p4 + 2] = v.z, e[4 * p4 + 3] = v.w;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, cell);
+  const unsigned rank = (unsigned)__popc(peers & lane_lt);
+  const unsigned turns = redux_max_u32(0xffffffffu, have ? rank + 1u : 0u);
+  const unsigned ga = cell + gat, gb = ga + row;
+#pragma unroll 1
+  for (unsigned r = 0; r < turns; ++r) {
+    const bool mine = have && rank == r;
+    texel_add_pred<kPad>(ga, e[0], e[kPad > 1 ? 1 : 0], e[kPad > 2 ? 2 : 0], e[kPad > 2 ? 3 : 0], mine);
+    __syncwarp();
+    texel_add_pred<kPad>(ga + kPad * 4, e[kPad], e[kPad + (kPad > 1 ? 1 : 0)], e[kPad + (kPad > 2 ? 2 : 0)],
+                         e[kPad + (kPad > 2 ? 3 : 0)], mine);
+    __syncwarp();
+    texel_add_pred<kPad>(gb, e[2 * kPad], e[2 * kPad + (kPad > 1 ? 1 : 0)], e[2 * kPad + (kPad > 2 ? 2 : 0)],
+                         e[2 * kPad + (kPad > 2 ? 3 : 0)], mine);
+    __syncwarp();
+    texel_add_pred<kPad>(gb + kPad * 4, e[3 * kPad], e[3 * kPad + (kPad > 1 ? 1 : 0)], e[3 * kPad + (kPad > 2 ? 2 : 0)],
+                         e[3 * kPad + (kPad > 2 ? 3 : 0)], mine);
+    __syncwarp();
+  }
+  q.head += n;
 }
 
 // Work unit = (image b, template group grp): the CTA's warps take the templates grp * nwarps + warp.  Units are dealt
@@ -232,8 +274,8 @@ __device__ __forceinline__ void flush_cells(unsigned gat, unsigned row, int lane
 // 1.7 whole images each -- the tail of the last wave shrinks from 14 % to 4 % of the kernel.
 // kMode: the same scatter for the backward of pdf.mode() -- `gout` is the gradient w.r.t. the mode image and `cache`'s
 // first C planes hold the index of the component each pixel took its value from (scae_tmpl_mode_bwd)
-template <int C, bool kAlpha, bool kMode>
-__global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_kernel(const scae_tmpl_args a,
+template <int C, bool kAlpha, bool kMode, int kOcc>
+__global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(const scae_tmpl_args a,
                                                                                    const float* __restrict__ x,
                                                                                    const float* __restrict__ gout,
                                                                                    const float* __restrict__ cache,
@@ -243,18 +285,22 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int atlas_floats = g.atlas_floats;               // one padded template, multiple of 4 floats
-  float* atlas = smem + (size_t)warp * 2 * atlas_floats;  // this warp's value atlas
-  float* gatlas = atlas + atlas_floats;                   // ... and gradient atlas
-  float* red = smem + (size_t)nwarps * 2 * atlas_floats;  // [64] block-reduction scratch
+  constexpr int kQueueFloats = kQueueCap * (1 + 4 * kPad);   // keys + sums of one warp's queue
+  const int warp_floats = 2 * atlas_floats + kQueueFloats;
+  float* atlas = smem + (size_t)warp * warp_floats;       // this warp's value atlas
+  float* gatlas = atlas + atlas_floats;                   // ... its gradient atlas
+  float* red = smem + (size_t)nwarps * warp_floats;       // [64] block-reduction scratch
   // run geometry (tmpl_bwd_plan): k runs of L pixels per row, `walks` walks per image, `bw` walks per staged band
-  const int L = g.tw, Lp = g.ppt, kshift = g.k, kruns = 1 << kshift, walks = g.tiles_y, bw = g.tiles_x;
+  const int L = g.tw, skew_shift = g.ppt, kshift = g.k, kruns = 1 << kshift, walks = g.tiles_y, bw = g.tiles_x;
   float* xs = red + 64;                                   // [kruns * L] affine_grid base coordinates (0 past W)
   float* ys = xs + kruns * L;                             // [H]
   const int HW = a.H * a.W, hw = a.h * a.w, pw = g.pw, ph = g.ph, W = a.W, H = a.H;
-  // records {x, upstream gradient, cached numerator lse, cached denominator lse} of the current band, [C][bw][32][Lp]
+  // records {x, upstream gradient, cached numerator lse, cached denominator lse} of the current band, [C][bw][32 L + 8]:
+  // run `ln` of a walk starts at ln * L + (ln >> skew_shift); the skew spreads the eight lanes of a quarter-warp over the
+  // eight 16-byte bank groups whatever the parity of L (one LDS.128 per step, conflict-free)
   float4* PIX =
-      reinterpret_cast<float4*>(smem + (((size_t)nwarps * 2 * atlas_floats + 64 + kruns * L + H + 3) & ~(size_t)3));
-  const int plane = bw * 32 * Lp;
+      reinterpret_cast<float4*>(smem + (((size_t)nwarps * warp_floats + 64 + kruns * L + H + 3) & ~(size_t)3));
+  const int walk_recs = 32 * L + (31 >> skew_shift) + 1, plane = bw * walk_recs;
   #pragma unroll 1
   for (int e = lane; e < 2 * atlas_floats; e += 32) atlas[e] = 0.0f;
   #pragma unroll 1
@@ -267,7 +313,12 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
   // one LDS [reg + imm] and a cell's identity (the flush key) is the address of its north-west texel
   const unsigned sbase = smem_u32(smem);
   const unsigned row = keep((unsigned)(pw * kPad * 4));
-  const unsigned atlas_off = sbase + (unsigned)(warp * 2 * atlas_floats) * 4u;
+  const unsigned atlas_off = sbase + (unsigned)(warp * warp_floats) * 4u;
+  CellQueue queue;                                       // ... and its cell queue: sums (16-byte aligned), then keys
+  queue.sums = keep(atlas_off + (unsigned)(2 * atlas_floats) * 4u);
+  queue.keys = queue.sums + (unsigned)(kQueueCap * 16 * kPad);
+  queue.head = queue.tail = 0u;
+  const unsigned lane_lt = keep((1u << lane) - 1u);
   const unsigned base0 = keep(atlas_off - kMagicBits * (row + (unsigned)(kPad * 4)));
   const unsigned gat = keep((unsigned)atlas_floats * 4u);
   const unsigned pix_addr = smem_u32(PIX), xs_addr = smem_u32(xs);
@@ -318,15 +369,19 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
       }
     }
     float sgx = 0.f, sgxX = 0.f, sgxY = 0.f, sgy = 0.f, sgyX = 0.f, sgyY = 0.f, spres = 0.f;
-    // the lane's current cell (starts in the border corner, whose gradient is discarded) and its four corner sums
+    // the lane's current cell (starts in the border corner: zero texels, gradient discarded): its four texels and its
+    // four corner sums
     unsigned cur_off = atlas_off;
+    Texel<kPad> t00, t10, t01, t11;
+#pragma unroll
+    for (int c = 0; c < kPad; ++c) t00.v[c] = t10.v[c] = t01.v[c] = t11.v[c] = 0.0f;
     float cs[4][NCH];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int c = 0; c < NCH; ++c) cs[k][c] = 0.0f;
+    queue.head = queue.tail = 0u;
 
-    #pragma unroll 1
     for (int band = 0; band < nbands; ++band) {
       // ---- pixel records of the band (whole CTA) and, once per image, the background component -------------------
       __syncthreads();                       // the previous band's records are no longer read
@@ -347,7 +402,7 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
           G[c] = ok ? __ldg(gout + px0 + (size_t)c * HW) : 0.0f;
           Nc[c] = ok ? __ldg(cache + cx) : 1e30f;
           Dc[c] = ok ? __ldg(cache + cx + (size_t)C * HW) : 1e30f;
-          PIX[c * plane + slot * Lp + s] = make_float4(xv[c], G[c], Nc[c], Dc[c]);
+          PIX[c * plane + wk * walk_recs + ln * L + (ln >> skew_shift) + s] = make_float4(xv[c], G[c], Nc[c], Dc[c]);
         }
         if (first && ok) bwd_background<C, kAlpha, kMode>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
       }
@@ -360,7 +415,7 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
         const float Y = ys[r_img < H ? r_img : H - 1];       // (a dead run reads pad records: every contribution is 0)
         const float yx = fmaf(Y, Bx, Cx), yy = fmaf(Y, By, Cy);
         unsigned xa = keep(xs_addr + (unsigned)col0 * 4u);                        // loop-carried addresses: X of the
-        unsigned ra = keep(pix_addr + (unsigned)((wk * 32 + lane) * Lp) * 16u);   // lane's column, its pixel record
+        unsigned ra = keep(pix_addr + (unsigned)(wk * walk_recs + lane * L + (lane >> skew_shift)) * 16u);   // its records
         float wgx = 0.f, wgy = 0.f;
         #pragma unroll 1
         for (int s = 0; s < L; ++s, xa += 4u, ra += 16u) {
@@ -376,8 +431,25 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
           const float X = lds_f32(xa);
           Tap t;
           tap_setup<kPad, 4>(fmaf(X, Ax, yx), fmaf(X, Ay, yy), lim_x, lim_y, row, base0, t);
-          const Texel<kPad> t00 = lds_texel<kPad>(t.off), t10 = lds_texel<kPad>(t.off + kPad * 4);
-          const Texel<kPad> t01 = lds_texel<kPad>(t.off + row), t11 = lds_texel<kPad>(t.off + row + kPad * 4);
+          // ---- the cell changed: queue the finished sums, fetch the new cell's texels; drain the queue when 32 entries
+          //      have gathered -----------------------------------------------------------------------------------------
+          const bool changed = t.off != cur_off;
+          const unsigned chm = __ballot_sync(0xffffffffu, changed);
+          if (chm != 0u) {
+            queue_append<kPad, NCH>(queue, chm, changed, lane_lt, cur_off, cs);
+            if (changed) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) cs[k][c] = 0.0f;
+              cur_off = t.off;
+            }
+            lds_texel_pred<kPad>(t.off, t00, changed);
+            lds_texel_pred<kPad>(t.off + kPad * 4, t10, changed);
+            lds_texel_pred<kPad>(t.off + row, t01, changed);
+            lds_texel_pred<kPad>(t.off + row + kPad * 4, t11, changed);
+            if (queue.tail - queue.head >= (unsigned)kQueueDrainAt) queue_drain<kPad>(queue, gat, row, lane, lane_lt);
+          }
           float glp, gtx, gty;
           const Texel<kPad> gv =
               bwd_pixel<C, kAlpha, kPad, kMode>(sc, t00, t10, t01, t11, t, lpres, xv, G, Nc, Dc, acc, glp, gtx, gty, (float)m);
@@ -386,9 +458,6 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
           wgy += gty;
           sgyX = fmaf(gty, X, sgyX);
           spres += glp;
-          // ---- the cell changed: hand the finished sums to the gradient atlas ---------------------------------------
-          const bool changed = t.off != cur_off;
-          if (__any_sync(0xffffffffu, changed)) flush_cells<kPad, NCH>(gat, row, lane, changed, cur_off, t.off, cs);
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
             cs[0][c] = fmaf(gv.v[c], t.w00, cs[0][c]);
@@ -404,7 +473,9 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
       }
     }
     if (!has_m) continue;
-    flush_cells<kPad, NCH>(gat, row, lane, true, cur_off, atlas_off, cs);
+    queue_append<kPad, NCH>(queue, 0xffffffffu, true, lane_lt, cur_off, cs);
+    while (queue.tail != queue.head) queue_drain<kPad>(queue, gat, row, lane, lane_lt);
+    __syncwarp();
 
     // ---- pose / presence gradients of (b, m) -------------------------------------------------------------------
     {
@@ -467,6 +538,16 @@ __global__ void __launch_bounds__(kRunThreads, C == 1 ? 4 : 3) tmpl_ll_bwd_run_k
 // ================================================================================================================
 // host
 // ================================================================================================================
+// CTAs per SM the kernel is compiled for (register budget 64 / 80 per thread)
+// CTAs of 256 threads per SM the kernel is compiled for: __launch_bounds__(256, 3) = 80 registers for one-channel
+// images, (256, 2) = 128 registers for colour (12-16 corner sums + 16 cached texel values per lane)
+static int tmpl_bwd_occ(int C) { return C == 1 ? 3 : 2; }
+
+// Picks the run geometry (k = 2^kshift runs of L pixels per row, 32 / k rows per walk), the warps per CTA and the band of
+// walks whose pixel records are staged at a time.  Every candidate is scored by
+//   occupancy (warps per SM, saturating at 24)  x  lane efficiency of the walks  x  L / (L + 1) (every run ends with a
+//   cell change)  x  a mild penalty per extra band (two CTA barriers each) and per halving of the warps (the records
+//   are staged once per group of `warps` templates)
 static int tmpl_bwd_plan(const scae_tmpl_args* a, TmplGeom* gp) {
   const int kpad = tmpl_texel_floats(a);
   const size_t limit = (size_t)max_smem_optin();
@@ -476,52 +557,54 @@ static int tmpl_bwd_plan(const scae_tmpl_args* a, TmplGeom* gp) {
   g.pw = a->w + 4;
   g.ph = a->h + 4;
   g.atlas_floats = (int)(((size_t)g.pw * g.ph * kpad + 3) / 4 * 4);
-  // ---- runs: k = 2^kshift runs of L pixels per row, 32 / k rows per walk.  Lane efficiency first, then long runs
-  //      (every run ends with a flush) ---------------------------------------------------------------------------------
-  int best_shift = 0;
-  double best_score = -1.0;
-  for (int sh = 0; sh <= 5; ++sh) {
-    const int k = 1 << sh, L = (a->W + k - 1) / k, rows = 32 / k, walks = (a->H + rows - 1) / rows;
-    if (sh > 0 && L < 2) break;
-    const double eff = (double)a->H * a->W / ((double)walks * 32 * L);
-    const double score = eff * L / (L + 1.0);
-    if (score > best_score * 1.0001) {
-      best_score = score;
-      best_shift = sh;
-    }
-  }
-  const int k = 1 << best_shift, L = (a->W + k - 1) / k, walks = (a->H + 32 / k - 1) / (32 / k);
-  g.k = best_shift;
-  g.tw = L;
-  g.tiles_y = walks;
-  const int cap = a->C == 1 ? 4 : 3;                // compiled with __launch_bounds__(256, C == 1 ? 4 : 3)
-  int threads = kRunThreads;
-  for (;;) {
-    // one padded value atlas + one gradient atlas per warp, block scratch, coordinate tables
-    const size_t fixed = ((size_t)(threads / 32) * 2 * g.atlas_floats + 64 + (size_t)k * L + a->H + 8) * sizeof(float);
-    // band of `bw` walks of pixel records at run pitch Lp; the whole image at the highest occupancy if it fits, else
-    // the largest band two CTAs per SM leave room for, else one CTA per SM.  An odd pitch keeps the record loads free
-    // of bank conflicts and is taken when it costs no occupancy.
-    for (int occ = cap; occ >= 1 && g.threads == 0; --occ) {
-      size_t budget = per_sm / occ - 1024;
-      if (budget > limit) budget = limit;
-      if (budget < fixed + 16) continue;
-      for (int odd = 1; odd >= 0 && g.threads == 0; --odd) {
-        const int Lp = odd ? (L | 1) : L;
-        const size_t walk_bytes = (size_t)16 * a->C * 32 * Lp;
+  const int cap = tmpl_bwd_occ(a->C);
+  const int regs = cap == 3 ? 80 : 128;
+  double best = -1.0;
+  int best_per = 1;
+  for (int threads = kRunThreads; threads >= 32; threads /= 2) {
+    const int warps = threads / 32;
+    int by_regs = 65536 / (regs * threads), by_threads = 2048 / threads;
+    const int occ_max = by_regs < by_threads ? by_regs : by_threads;
+    for (int ks = 0; ks <= 5; ++ks) {
+      const int k = 1 << ks, L = (a->W + k - 1) / k, rows = 32 / k, walks = (a->H + rows - 1) / rows;
+      if (ks > 0 && L < 2) break;
+      // one padded value atlas + one gradient atlas + one cell queue per warp, block scratch, coordinate tables
+      const size_t fixed =
+          ((size_t)warps * (2 * g.atlas_floats + kQueueCap * (1 + 4 * kpad)) + 64 + (size_t)k * L + a->H + 8) * sizeof(float);
+      // run ln of a walk starts at record ln * L + (ln >> sh): with 2^tz | L, sh = 3 - tz makes the eight lanes of a
+      // quarter-warp hit eight different 16-byte bank groups (odd L: no skew needed)
+      int tz = 0;
+      while (tz < 3 && ((L >> tz) & 1) == 0) ++tz;
+      const int sh = tz == 0 ? 5 : 3 - tz;
+      const size_t walk_bytes = (size_t)16 * a->C * (32 * L + (31 >> sh) + 1);
+      for (int occ = occ_max; occ >= 1; --occ) {
+        size_t budget = per_sm / occ - 1024;
+        if (budget > limit) budget = limit;
+        if (budget < fixed + 16 + walk_bytes) continue;
         int bw = (int)((budget - fixed - 16) / walk_bytes);
         if (bw > walks) bw = walks;
-        if (bw < 1) continue;
-        if (bw < walks && occ > 2) continue;          // bands instead of the whole image only at <= 2 CTAs per SM
-        g.ppt = Lp;
-        g.tiles_x = bw;
-        g.pix_floats = (int)(walk_bytes / 4 * bw);
-        g.threads = threads;
-        g.smem_bytes = fixed + 16 + walk_bytes * bw;
+        const int nbands = (walks + bw - 1) / bw;
+        bw = (walks + nbands - 1) / nbands;          // even bands
+        const double w = (double)occ * warps;
+        const double f_occ = w >= 24.0 ? 1.0 : sqrt(w / 24.0);
+        const double eff = (double)a->H * a->W / ((double)walks * 32 * L);
+        const double score =
+            f_occ * eff * (L / (L + 1.0)) / (1.0 + 0.02 * (nbands - 1)) / (1.0 + 0.5 / warps);
+        if (score > best * 1.0001) {
+          best = score;
+          best_per = occ;
+          g.k = ks;
+          g.tw = L;
+          g.tiles_y = walks;
+          g.ppt = sh;
+          g.tiles_x = bw;
+          g.pix_floats = (int)(walk_bytes / 4 * bw);
+          g.threads = threads;
+          g.smem_bytes = fixed + 16 + walk_bytes * bw;
+        }
+        break;                                       // lower occupancies of the same geometry only score worse
       }
     }
-    if (g.threads != 0 || threads == 32) break;
-    threads /= 2;                                   // very large templates: fewer warps per CTA
   }
   SCAE_REQUIRE(g.threads != 0, SCAE_ELIMIT, "tmpl bwd: a %dx%d template with a %dx%d image does not fit in shared memory",
                a->h, a->w, a->H, a->W);
@@ -529,12 +612,7 @@ static int tmpl_bwd_plan(const scae_tmpl_args* a, TmplGeom* gp) {
   // work units: (image, group of `warps` templates), one template per warp
   g.mc = 1;
   g.groups = (a->M + warps - 1) / warps;
-  int per = (int)(per_sm / (g.smem_bytes + 1024));
-  const int by_threads = 2048 / g.threads;
-  if (per > by_threads) per = by_threads;
-  if (per > cap) per = cap;
-  if (per < 1) per = 1;
-  const long slots = (long)sm_count() * per;
+  const long slots = (long)sm_count() * best_per;
   const long units = (long)a->B * g.groups;
   g.grid = units < slots ? (int)units : (int)slots;
   return SCAE_OK;
@@ -582,7 +660,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_ll_bwd(
   TmplBwdOut out{g_templates, g_color, a->template_color ? raw_partials : nullptr, g_pose, g_presence, g_bg_image,
                  (alpha && g_alpha) ? alpha_partials : nullptr, scalar_partials};
   SCAE_TMPL_DISPATCH(a->C, alpha, {
-    auto kern = tmpl_ll_bwd_run_kernel<kC, kA, false>;
+    auto kern = tmpl_ll_bwd_run_kernel<kC, kA, false, (kC == 1 ? 3 : 2)>;
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
     if (rc != SCAE_OK) return rc;
     kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, x, grad_log_prob, cache, out, g);
@@ -629,7 +707,7 @@ extern "C" __attribute__((visibility("default"))) int scae_tmpl_mode_bwd(
   TmplBwdOut out{g_templates, g_color, a->template_color ? raw_partials : nullptr, g_pose, nullptr, g_bg_image, nullptr,
                  scalar_partials};
   SCAE_TMPL_DISPATCH(a->C, alpha, {
-    auto kern = tmpl_ll_bwd_run_kernel<kC, kA, true>;
+    auto kern = tmpl_ll_bwd_run_kernel<kC, kA, true, (kC == 1 ? 3 : 2)>;
     rc = tmpl_prepare_kernel(kern, g.smem_bytes);
     if (rc != SCAE_OK) return rc;
     kern<<<g.grid, g.threads, g.smem_bytes, stream>>>(*a, grad_mode, grad_mode, component_cache, out, g);

@@ -29,7 +29,7 @@ struct TexTraits {
 // How one image is mapped on a CTA: threads form `k` row-groups of `tw` columns; a thread owns column j and rows
 // r, r+k, r+2k, ... (`ppt` of them) of the current pixel tile.
 struct TmplGeom {
-  int tw, k, ppt, threads;   // backward (tmpl_bwd_plan): tw = run length L, k = log2(runs per row), ppt = record pitch of a run
+  int tw, k, ppt, threads;   // backward (tmpl_bwd_plan): tw = run length L, k = log2(runs per row), ppt = shift of the record skew
   int tiles_x, tiles_y;      // backward: tiles_x = walks per staged band, tiles_y = walks per image
   int mc;             // forward: templates per shared-memory chunk; backward: templates per warp per work unit
   int pw, ph;         // padded atlas width / height
@@ -112,6 +112,14 @@ __device__ __forceinline__ Texel<4> lds_texel<4>(unsigned addr) {
   t.v[2] = q.z;
   t.v[3] = q.w;
   return t;
+}
+
+// ... reloaded only where `pred` holds
+template <int N>
+__device__ __forceinline__ void lds_texel_pred(unsigned addr, Texel<N>& t, bool pred) {
+  if (N == 1) lds_pred_f32(addr, t.v[0], pred);
+  else if (N == 2) lds_pred_f32x2(addr, t.v[0], t.v[N > 1 ? 1 : 0], pred);
+  else lds_pred_f32x4(addr, t.v[0], t.v[N > 1 ? 1 : 0], t.v[N > 2 ? 2 : 0], t.v[N > 3 ? 3 : 0], pred);
 }
 
 // ATen affine_grid base coordinates, align_corners=False: linspace(-1, 1, n) * (n - 1) / n, mirroring ATen's
