@@ -9,17 +9,13 @@
 // The template / alpha gradient is a *transposed* bilinear interpolation.  Written as a scatter it needs 8 float
 // atomics on shared memory per (pixel, template); on sm_100a those are ATOMS.CAST spin loops and neighbouring pixels hit
 // the same texel (templates are magnified), which made the first version of this kernel 18x slower than the forward
-// pass (profiles/r01a).  The shipped formulation is atomics-free and bit-reproducible:
+// pass (profiles/r01a).  The shipped formulation (tmpl_ll_bwd_run_kernel below) is atomics-free and bit-reproducible: a
+// warp owns one (image, template) pair, every lane walks runs of consecutive pixels and keeps the sums of the bilinear
+// cell it is in in registers; finished cells go through a per-warp queue to the warp's private gradient atlas.
 //
-//   one warp owns one (image, template) pair and walks the image row-major, 32 pixels per pass.  Along a row the
-//   sampling coordinates move on a straight line, so the bilinear cell index is monotone: pixels that fall into the same
-//   cell are CONTIGUOUS lanes.  A segmented warp scan (shuffles) pre-reduces the four corner contributions per cell, and
-//   only the last lane of each segment does a plain read-modify-write on the warp's private gradient atlas in shared
-//   memory -- corner by corner and row by row, so no two lanes ever touch the same address in the same step and the
-//   summation order is fixed.  No CTA barriers inside a template, no gradient buffer, any image size.
-//
-// (A texel-parallel gather formulation -- every texel inverts the affine map and walks its own footprint -- was
-// measured at 1.5 ms against this kernel's 1.0 ms at the MNIST config and removed; profiles/r01b.)
+// History (profiles/): texel-parallel gather, every texel inverting the affine map and walking its own footprint --
+// 1.5 ms at the MNIST config, divergent (r01b); segmented warp scan of the eight corner contributions on every 32-pixel
+// pass -- 0.77 ms, 313 warp instructions per pass (r01, r02 first half); this kernel -- 0.53 ms, ~190 (r02).
 #include <stdlib.h>
 #include <string.h>
 
@@ -84,15 +80,26 @@ __device__ __forceinline__ void bwd_background(const scae_tmpl_args& a, const Tm
   }
 }
 
+// One channel of the bilinear sample in difference form: value and its derivatives w.r.t. the two atlas coordinates
+//   loc = t00 + fx DX + fy (DY + fx DXY),  d loc / d tx = DX + fy DXY,  d loc / d ty = DY + fx DXY
+// with DX = t10 - t00, DY = t01 - t00, DXY = t11 - t10 - t01 + t00 (8 instructions instead of 12 for the weighted form
+// plus its two difference quotients)
+__device__ __forceinline__ float bilerp_d(float t00, float t10, float t01, float t11, float fx, float fy, float& dtx,
+                                          float& dty) {
+  const float DX = t10 - t00, DY = t01 - t00, DXY = (t11 - t01) - DX;
+  dty = fmaf(fx, DXY, DY);
+  dtx = fmaf(fy, DXY, DX);
+  return fmaf(fy, dty, fmaf(fx, DX, t00));
+}
+
 // per-(pixel, template) gradients.  Returns g_loc[c] (c < C) and, in v[C], the summed logit gradient (alpha mode).
 template <int C, bool kAlpha, int kPad, bool kMode>
 __device__ __forceinline__ Texel<kPad> bwd_pixel(const TmplScalars& sc, const Texel<kPad>& t00, const Texel<kPad>& t10,
-                                                 const Texel<kPad>& t01, const Texel<kPad>& t11, const Tap& t,
+                                                 const Texel<kPad>& t01, const Texel<kPad>& t11, float fx, float fy,
                                                  float lpres, const float* xv, const float* G, const float* Nc,
                                                  const float* Dc, ScalarAcc& acc, float& glp, float& gtx, float& gty,
                                                  float m_index) {
   const float two_i2s = 2.0f * sc.i2s;
-  const float gx1 = 1.0f - t.fx, gy1 = 1.0f - t.fy;
   Texel<kPad> out;
 #pragma unroll
   for (int c = 0; c < kPad; ++c) out.v[c] = 0.0f;
@@ -104,14 +111,16 @@ __device__ __forceinline__ Texel<kPad> bwd_pixel(const TmplScalars& sc, const Te
     for (int c = 0; c < C; ++c) {
       const float gl = Nc[c] == m_index ? G[c] : 0.0f;
       out.v[c] = gl;
-      gtx = fmaf(gl, fmaf(t11.v[c] - t01.v[c], t.fy, (t10.v[c] - t00.v[c]) * gy1), gtx);
-      gty = fmaf(gl, fmaf(t11.v[c] - t10.v[c], t.fx, (t01.v[c] - t00.v[c]) * gx1), gty);
+      float dtx, dty;
+      bilerp_d(t00.v[c], t10.v[c], t01.v[c], t11.v[c], fx, fy, dtx, dty);
+      gtx = fmaf(gl, dtx, gtx);
+      gty = fmaf(gl, dty, gty);
     }
     return out;
   }
-  float al = 0.0f, pD_shared = 0.0f;
+  float al = 0.0f, pD_shared = 0.0f, atx = 0.0f, aty = 0.0f;
   if (kAlpha) {
-    al = bilerp<kPad>(t00, t10, t01, t11, t, C) + lpres;
+    al = bilerp_d(t00.v[C], t10.v[C], t01.v[C], t11.v[C], fx, fy, atx, aty) + lpres;
     pD_shared = ex2_ftz((al - Dc[0]) * kLog2e);
   }
   glp = 0.0f;
@@ -119,7 +128,8 @@ __device__ __forceinline__ Texel<kPad> bwd_pixel(const TmplScalars& sc, const Te
   gty = 0.0f;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
-    const float loc = bilerp<kPad>(t00, t10, t01, t11, t, c);
+    float dtx, dty;
+    const float loc = bilerp_d(t00.v[c], t10.v[c], t01.v[c], t11.v[c], fx, fy, dtx, dty);
     const float d = xv[c] - loc;
     const float logit = kAlpha ? al : fmaf(loc, sc.inv_tau, lpres);
     const float pN = ex2_ftz((fmaf(d * d, -sc.i2s, logit) - Nc[c]) * kLog2e);
@@ -133,14 +143,13 @@ __device__ __forceinline__ Texel<kPad> bwd_pixel(const TmplScalars& sc, const Te
     acc.sig = fmaf(G[c] * pN, d * d, acc.sig);
     glp += glog;
     out.v[c] = gl;
-    // d loc / d tx = (ne - nw)(1 - fy) + (se - sw) fy ;  d loc / d ty = (sw - nw)(1 - fx) + (se - ne) fx
-    gtx = fmaf(gl, fmaf(t11.v[c] - t01.v[c], t.fy, (t10.v[c] - t00.v[c]) * gy1), gtx);
-    gty = fmaf(gl, fmaf(t11.v[c] - t10.v[c], t.fx, (t01.v[c] - t00.v[c]) * gx1), gty);
+    gtx = fmaf(gl, dtx, gtx);
+    gty = fmaf(gl, dty, gty);
   }
   if (kAlpha) {
     out.v[C] = glp;
-    gtx = fmaf(glp, fmaf(t11.v[C] - t01.v[C], t.fy, (t10.v[C] - t00.v[C]) * gy1), gtx);
-    gty = fmaf(glp, fmaf(t11.v[C] - t10.v[C], t.fx, (t01.v[C] - t00.v[C]) * gx1), gty);
+    gtx = fmaf(glp, atx, gtx);
+    gty = fmaf(glp, aty, gty);
   }
   return out;
 }
@@ -163,28 +172,36 @@ __device__ __forceinline__ void write_scalar_partials(const scae_tmpl_args& a, c
 }
 
 // ================================================================================================================
-// run kernel: warp per (image, template); a lane walks a run of consecutive pixels and keeps the four corner sums of
-// its current bilinear cell in registers
+// run kernel: warp per (image, template); a lane walks runs of consecutive pixels and keeps the sums of its current
+// bilinear cell in registers
 // ================================================================================================================
 //
-// The template / alpha gradient is a transposed bilinear interpolation.  Along an image row the sampling coordinates move
-// on a straight line, so the pixels that fall into one bilinear cell are CONSECUTIVE.  Every lane therefore walks its own
-// run of `L` consecutive pixels of one row, one pixel per step, and accumulates the four corner contributions of the
-// cell it is in (4 x NCH registers).  Only when the cell changes -- every `magnification` pixels, 7 at the MNIST
-// configuration -- does the lane add its sums to the warp's private gradient atlas in shared memory with plain vector
-// read-modify-writes.  Lanes that leave the SAME cell in the same step (neighbouring rows of an unrotated template) are
-// found with one MATCH.ANY and take turns in lane order; within a turn all cells are distinct, and the corners are
-// updated one after the other, so no two lanes touch an address in the same instruction and the summation order is
-// fixed by the program: bit-reproducible, no atomics, no cross-lane scan.  (The predecessor did a segmented warp scan of
-// all eight values on every 32-pixel pass: 313 warp instructions per pass against ~150 here; profiles/r02_*.)
+// Along an image row the sampling coordinates move on a straight line, so the pixels that fall into one bilinear cell are
+// CONSECUTIVE.  Every lane walks its own run of `L` consecutive pixels of one row, one pixel per step, and accumulates
+// the cell's contributions in registers, in the moment basis {sum g, sum g fx, sum g fy, sum g fx fy} (4 x NCH
+// registers; the four corner sums are linear combinations of these).  The cell's four texels stay in registers too: they
+// are re-read only when the cell changes -- every `magnification` pixels, 7 at the MNIST configuration -- and the sample
+// and its two coordinate derivatives come from the difference form (bilerp_d).
+//
+// When a lane's cell changes it appends {cell address, moments} to its warp's queue in shared memory (cells that touch
+// only the zero border -- pixels that miss the template, most of the image for a small part -- are dropped: their
+// gradient would be discarded).  A few lanes change cells in nearly every step, so writing to the gradient atlas right
+// away would run the read-modify-write sequence at 10-20 % lane utilisation; the queue is drained 32 entries at a time,
+// one entry per lane: entries of the SAME cell are found with one MATCH.ANY and take turns in queue order; within a turn
+// all cells are distinct and the corners are updated one after the other with predicated vector read-modify-writes, so
+// no two lanes touch an address in the same instruction and the summation order is fixed by the program:
+// bit-reproducible, no atomics, no cross-lane scan.
 //
 // Mapping.  A row is cut into k runs (k a power of two, L = ceil(W / k)); a "walk" is 32 runs in lock-step: lane ->
 // (row slot q = lane / k, segment lane % k).  Walk w takes the rows q * walks + w, so the rows a warp works on at the same
-// time are `walks` pixels apart and rarely share a cell.  Pixel records {x, upstream gradient, the two cached lse
-// terms} are staged per band of `band_walks` walks in the order the lanes read them ([walk][lane][step], one LDS.128 per
-// step); ragged ends and dead runs hold pad records {0, 0, 1e30, 1e30} that turn every contribution into an exact
-// zero without a select in the loop.  Images whose records do not fit next to the atlases are processed band by band
-// (two CTA barriers per band), the cell sums and pose sums carried in registers across bands.
+// time are `walks` pixels apart and rarely share a cell, and a lane's successive runs are vertically adjacent; odd
+// walks run right to left (boustrophedon), so the next run starts next to the pixel the last one ended on -- usually in
+// the same cell.  Pixel records {x, upstream gradient, the two cached lse terms} are staged per band of walks in the
+// order the lanes read them ([walk][lane][step], skewed so that one LDS.128 per step is bank-conflict-free); ragged ends
+// and dead runs hold pad records {0, 0, 1e30, 1e30} that turn every contribution into an exact zero without a select in
+// the loop.  Images whose records do not fit next to the atlases are processed band by band (two CTA barriers per band),
+// the cell state and pose sums carried in registers across bands.  tmpl_bwd_plan searches run geometry, warps per CTA
+// and band size for the best occupancy x lane-efficiency product.
 constexpr int kRunThreads = 256;
 
 // [addr] += the NCH live channels of one corner where `pred` holds: one predicated vector read-modify-write of the padded
@@ -198,7 +215,7 @@ __device__ __forceinline__ void texel_add_pred(unsigned addr, float v0, float v1
 #define SCAE_CORNER(k) acc[k][0], acc[k][NCH > 1 ? 1 : 0], NCH > 2 ? acc[k][NCH > 2 ? 2 : 0] : 0.0f, NCH > 3 ? acc[k][NCH > 3 ? 3 : 0] : 0.0f
 
 // ---- per-warp queue of finished cells ----------------------------------------------------------------------------------
-// A lane that leaves a cell appends {cell address, four corner sums} to its warp's queue in shared memory (a ring of
+// A lane that leaves a cell appends {cell address, the cell's four moment sums} to its warp's queue in shared memory (a ring of
 // kQueueCap entries: keys [cap] u32, sums [cap][kPad] float4).  Cells change for a few lanes in nearly every step, so
 // handing them to the gradient atlas right away would run the read-modify-write sequence at 10-20 % lane utilisation;
 // the queue is drained 32 entries at a time instead, one entry per lane.
@@ -246,6 +263,16 @@ __device__ __forceinline__ void queue_drain(CellQueue& q, unsigned gat, unsigned
   for (int p4 = 0; p4 < kPad; ++p4) {
     const float4 v = lds_f32x4(q.sums + slot * (unsigned)(16 * kPad) + 16u * p4);
     e[4 * p4 + 0] = v.x, e[4 * p4 + 1] = v.y, e[4 * p4 + 2] = v.z, e[4 * p4 + 3] = v.w;
+  }
+  // {S, Sx, Sy, Sxy} -> corner sums: se = Sxy, ne = Sx - Sxy, sw = Sy - Sxy, nw = (S - Sx) - sw   (weights (1-fx)(1-fy),
+  // fx (1-fy), (1-fx) fy, fx fy summed over the cell's pixels)
+#pragma unroll
+  for (int c = 0; c < kPad; ++c) {
+    const float S = e[c], Sx = e[kPad + c], Sy = e[2 * kPad + c], Sxy = e[3 * kPad + c];
+    const float sw = Sy - Sxy;
+    e[c] = (S - Sx) - sw;
+    e[kPad + c] = Sx - Sxy;
+    e[2 * kPad + c] = sw;
   }
   const unsigned peers = __match_any_sync(0xffffffffu, cell);
   const unsigned rank = (unsigned)__popc(peers & lane_lt);
@@ -359,7 +386,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
     for (int c = 0; c < C; ++c) colv[c] = colored ? __ldg(a.template_color + ((size_t)b * a.M + mm) * C + c) : 1.0f;
     if (has_m) {
       const float inv_w = 1.0f / (float)a.w;
-      #pragma unroll 1
+      #pragma unroll 4
       for (int e = lane; e < hw; e += 32) {
         const int y = (int)(((float)e + 0.5f) * inv_w), xx = e - y * a.w;
         float* q = atlas + ((size_t)(y + 2) * pw + (xx + 2)) * kPad;
@@ -370,8 +397,9 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
     }
     float sgx = 0.f, sgxX = 0.f, sgxY = 0.f, sgy = 0.f, sgyX = 0.f, sgyY = 0.f, spres = 0.f;
     // the lane's current cell (starts in the border corner: zero texels, gradient discarded): its four texels and its
-    // four corner sums
+    // four moment sums
     unsigned cur_off = atlas_off;
+    bool cur_in = false;
     Texel<kPad> t00, t10, t01, t11;
 #pragma unroll
     for (int c = 0; c < kPad; ++c) t00.v[c] = t10.v[c] = t01.v[c] = t11.v[c] = 0.0f;
@@ -386,11 +414,14 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
       // ---- pixel records of the band (whole CTA) and, once per image, the background component -------------------
       __syncthreads();                       // the previous band's records are no longer read
       const int w0 = band * bw;
-      #pragma unroll 1
+      #pragma unroll 2
       for (int e = threadIdx.x; e < bw * 32 * L; e += blockDim.x) {
         const int slot = (int)(((float)e + 0.5f) * inv_L), s = e - slot * L;
         const int ln = slot & 31, wk = slot >> 5;
-        const int r_img = (ln >> kshift) * walks + w0 + wk, c_img = (ln & (kruns - 1)) * L + s;
+        // walk w takes the rows q * walks + w; odd walks run right to left, so a lane's next run starts next to the pixel
+        // its last one ended on (usually the same cell: no cell change at the turn)
+        const int r_img = (ln >> kshift) * walks + w0 + wk;
+        const int c_img = (ln & (kruns - 1)) * L + (((w0 + wk) & 1) ? L - 1 - s : s);
         const bool ok = r_img < H && c_img < W && w0 + wk < walks;
         const int p = r_img * W + c_img;
         float xv[C], G[C], Nc[C], Dc[C];
@@ -414,11 +445,13 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
         const int r_img = q_lane * walks + w0 + wk;
         const float Y = ys[r_img < H ? r_img : H - 1];       // (a dead run reads pad records: every contribution is 0)
         const float yx = fmaf(Y, Bx, Cx), yy = fmaf(Y, By, Cy);
-        unsigned xa = keep(xs_addr + (unsigned)col0 * 4u);                        // loop-carried addresses: X of the
+        const bool backward = ((w0 + wk) & 1) != 0;
+        const unsigned xstep = backward ? 0u - 4u : 4u;
+        unsigned xa = keep(xs_addr + (unsigned)(col0 + (backward ? L - 1 : 0)) * 4u);   // loop-carried addresses: X of the
         unsigned ra = keep(pix_addr + (unsigned)(wk * walk_recs + lane * L + (lane >> skew_shift)) * 16u);   // its records
         float wgx = 0.f, wgy = 0.f;
         #pragma unroll 1
-        for (int s = 0; s < L; ++s, xa += 4u, ra += 16u) {
+        for (int s = 0; s < L; ++s, xa += xstep, ra += 16u) {
           float xv[C], G[C], Nc[C], Dc[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
@@ -436,13 +469,18 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
           const bool changed = t.off != cur_off;
           const unsigned chm = __ballot_sync(0xffffffffu, changed);
           if (chm != 0u) {
-            queue_append<kPad, NCH>(queue, chm, changed, lane_lt, cur_off, cs);
+            // cells that touch no interior texel (the zero border: pixels that miss the template) are not queued --
+            // their gradient would be discarded; parts cover a fraction of the image, so this is most cells
+            const bool app = changed && cur_in;
+            const unsigned am = __ballot_sync(0xffffffffu, app);
+            if (am != 0u) queue_append<kPad, NCH>(queue, am, app, lane_lt, cur_off, cs);
             if (changed) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) cs[k][c] = 0.0f;
               cur_off = t.off;
+              cur_in = t.tx >= 1.0f && t.tx < lim_x - 0.5f && t.ty >= 1.0f && t.ty < lim_y - 0.5f;
             }
             lds_texel_pred<kPad>(t.off, t00, changed);
             lds_texel_pred<kPad>(t.off + kPad * 4, t10, changed);
@@ -452,18 +490,20 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
           }
           float glp, gtx, gty;
           const Texel<kPad> gv =
-              bwd_pixel<C, kAlpha, kPad, kMode>(sc, t00, t10, t01, t11, t, lpres, xv, G, Nc, Dc, acc, glp, gtx, gty, (float)m);
+              bwd_pixel<C, kAlpha, kPad, kMode>(sc, t00, t10, t01, t11, t.fx, t.fy, lpres, xv, G, Nc, Dc, acc, glp, gtx, gty, (float)m);
           wgx += gtx;
           sgxX = fmaf(gtx, X, sgxX);
           wgy += gty;
           sgyX = fmaf(gty, X, sgyX);
           spres += glp;
+          // the cell's sums in the basis {1, fx, fy, fx fy}; the drain turns them into the four corner sums
+          const float fxy = t.fx * t.fy;
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
-            cs[0][c] = fmaf(gv.v[c], t.w00, cs[0][c]);
-            cs[1][c] = fmaf(gv.v[c], t.w10, cs[1][c]);
-            cs[2][c] = fmaf(gv.v[c], t.w01, cs[2][c]);
-            cs[3][c] = fmaf(gv.v[c], t.w11, cs[3][c]);
+            cs[0][c] += gv.v[c];
+            cs[1][c] = fmaf(gv.v[c], t.fx, cs[1][c]);
+            cs[2][c] = fmaf(gv.v[c], t.fy, cs[2][c]);
+            cs[3][c] = fmaf(gv.v[c], fxy, cs[3][c]);
           }
         }
         sgx += wgx;                  // Y is constant along a run
@@ -473,7 +513,10 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
       }
     }
     if (!has_m) continue;
-    queue_append<kPad, NCH>(queue, 0xffffffffu, true, lane_lt, cur_off, cs);
+    {
+      const unsigned am = __ballot_sync(0xffffffffu, cur_in);
+      if (am != 0u) queue_append<kPad, NCH>(queue, am, cur_in, lane_lt, cur_off, cs);
+    }
     while (queue.tail != queue.head) queue_drain<kPad>(queue, gat, row, lane, lane_lt);
     __syncwarp();
 
@@ -500,7 +543,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
       float gcol[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) gcol[c] = 0.0f;
-      #pragma unroll 1
+      #pragma unroll 4
       for (int e = lane; e < pw * ph; e += 32) {
         const int yy = (int)(((float)e + 0.5f) * inv_pw), xx = e - yy * pw;
         float* q = gatlas + (size_t)e * kPad;

@@ -160,6 +160,7 @@ struct PixLse {
 struct Tap {
   unsigned off;               // in floats, relative to the atlas base (template offset included)
   bool interior;              // the cell touches at least one interior (non-border) texel
+  float tx, ty;               // clamped atlas coordinates
   float fx, fy;
   float w00, w10, w01, w11;   // nw, ne, sw, se  (ATen grid_sampler_2d naming)
 };
@@ -175,6 +176,8 @@ __device__ __forceinline__ void tap_setup(float tx, float ty, float lim_x, float
   const float ux = __fadd_rd(tx, kMagic), uy = __fadd_rd(ty, kMagic);   // 2^23 + floor(t): exact floor, no F2I
   // interior texels sit at 2 .. w + 1, a cell (cx, cy) touches texels cx, cx + 1: interior iff 1 <= cx <= w + 1
   t.interior = tx >= 1.0f && tx < lim_x - 0.5f && ty >= 1.0f && ty < lim_y - 0.5f;
+  t.tx = tx;
+  t.ty = ty;
   t.fx = tx - (ux - kMagic);
   t.fy = ty - (uy - kMagic);
   t.off = __float_as_uint(uy) * row + __float_as_uint(ux) * (unsigned)(kPad * kUnit) + base;
