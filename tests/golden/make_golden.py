@@ -233,6 +233,44 @@ def make_explicit_likelihood(seed=400):
     _save('capsule_likelihood_explicit', **out)
 
 
+def make_hierarchical(seed=500):
+    """The reference's CapsuleLayer with the hierarchical inputs parent_transform (B,O,1,3,3) and parent_presence (B,O,1)
+    (object_decoder.py:183-188, :214-217): outputs and the gradients w.r.t. the feature, both parents and the
+    non-MLP parameters."""
+    torch.manual_seed(seed)
+    c = CAPSULE_CASES['default']
+    B, O, V = c['B'], c['O'], c['V']
+    layer = CapsuleLayer(O, c['F'], V, c['D'], hidden_sizes=c['hidden'], learn_vote_scale=True, allow_deformations=True,
+                         noise_type='uniform', noise_scale=4., similarity_transform=False)
+    with torch.no_grad():
+        for k, p in layer.named_parameters():
+            if 'mlps' not in k:
+                p.copy_(torch.randn_like(p) * 0.3)
+    feature = torch.randn(B, O, c['F']).requires_grad_(True)
+    parent_transform = cv_ops.geometric_transform(0.5 * torch.randn(B, O, 1, 6), as_matrix=True).detach().requires_grad_(True)
+    parent_presence = torch.rand(B, O, 1).requires_grad_(True)
+    with _RecordRand() as rr:
+        res = layer(feature, parent_transform, parent_presence)
+    out = dict(feature=_np(feature), parent_transform=_np(parent_transform), parent_presence=_np(parent_presence),
+               noise_caps=_np((rr.drawn[0] - 0.5) * 4.), noise_vote=_np((rr.drawn[1] - 0.5) * 4.))
+    loss = 0.9 * res.cpr_dynamic_reg_loss
+    for k in ('vote', 'scale', 'vote_presence', 'presence_logit_per_caps', 'presence_logit_per_vote'):
+        w = torch.randn_like(res[k])
+        out['weight.' + k] = _np(w)
+        loss = loss + 0.3 * (res[k] * w).sum()
+    loss.backward()
+    for k, v in res.items():
+        out['out.' + k] = _np(v)
+    out.update(g_feature=_np(feature.grad), g_parent_transform=_np(parent_transform.grad),
+               g_parent_presence=_np(parent_presence.grad))
+    for k, p in layer.state_dict().items():
+        out['param.' + k] = _np(p)
+    for k, p in layer.named_parameters():
+        if 'mlps' not in k:
+            out['g_param.' + k] = _np(p.grad) if p.grad is not None else np.zeros_like(_np(p))
+    _save('capsule_hierarchical', **out)
+
+
 def make_factory():
     cases = dict(
         mnist=dict(image_shape=(1, 40, 40), n_classes=10, n_part_caps=40, n_obj_caps=32),
@@ -255,4 +293,5 @@ if __name__ == '__main__':
     for i, (n, c) in enumerate(SCAE_CASES.items()):
         make_scae(n, c, 300 + i)
     make_explicit_likelihood()
+    make_hierarchical()
     make_factory()

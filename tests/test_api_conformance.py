@@ -76,6 +76,40 @@ def test_capsule_likelihood_values_and_gradients_vs_reference_golden():
         assert rel_err(t.grad, g['g_' + k]) < 1e-4, k
 
 
+def test_capsule_layer_hierarchical_inputs_vs_reference_golden(monkeypatch):
+    """CapsuleLayer(feature, parent_transform, parent_presence) (object_decoder.py:183-188, :214-217) on the inputs and
+    noise draws recorded from the reference: every output, the gradients w.r.t. the feature, both parents and the
+    non-MLP parameters"""
+    from golden.cases import CAPSULE_CASES
+    from torch_scae_b200.object_decoder import CapsuleLayer
+    g = load_golden('capsule_hierarchical')
+    c = CAPSULE_CASES['default']
+    layer = CapsuleLayer(c['O'], c['F'], c['V'], c['D'], hidden_sizes=c['hidden'], learn_vote_scale=True,
+                         allow_deformations=True, noise_type='uniform', noise_scale=4., similarity_transform=False)
+    layer.load_state_dict(sub(g, 'param.'), strict=True)
+    monkeypatch.setattr(layer, 'draw_noise', lambda all_param: (g['noise_caps'], g['noise_vote']))
+    leaf = {k: g[k].clone().requires_grad_(True) for k in ('feature', 'parent_transform', 'parent_presence')}
+    res = layer(leaf['feature'], leaf['parent_transform'], leaf['parent_presence'])
+    out = sub(g, 'out.')
+    assert set(out) == set(res.keys())
+    for k, ref in out.items():
+        assert rel_err(res[k], ref) < 1e-5, k
+    loss = 0.9 * res.cpr_dynamic_reg_loss
+    for k, w in sub(g, 'weight.').items():
+        loss = loss + 0.3 * (res[k] * w).sum()
+    loss.backward()
+    for k, t in leaf.items():
+        assert rel_err(t.grad, g['g_' + k]) < 1e-4, k
+    grads = dict(layer.named_parameters())
+    for k, ref in sub(g, 'g_param.').items():
+        got = grads[k].grad if grads[k].grad is not None else torch.zeros_like(grads[k])
+        assert rel_err(got, ref) < 1e-4, k
+    # one parent at a time: the other quantity comes from the layer's own parameters
+    only_t = layer(leaf['feature'], parent_transform=leaf['parent_transform'])
+    only_p = layer(leaf['feature'], parent_presence=leaf['parent_presence'])
+    assert rel_err(only_t.vote, out['vote']) < 1e-5 and rel_err(only_p.vote_presence, out['vote_presence']) < 1e-5
+
+
 @pytest.mark.gpu
 def test_capsule_object_decoder_shapes():
     """test_object_decoder.py:115-194"""

@@ -194,7 +194,7 @@ class CapsuleLayer(nn.Module):
     def forward(self, feature, parent_transform=None, parent_presence=None):
         """Stand-alone use (no likelihood).  Returns the reference's keys, with ``vote`` as (B,O,V,3,3)."""
         if parent_transform is not None or parent_presence is not None:
-            raise NotImplementedError('hierarchical parent_transform / parent_presence are not supported')
+            return self._forward_hierarchical(feature, parent_transform, parent_presence)
         all_param = self.predict_all_param(feature, grad_is_masked=True)
         B, O, _ = all_param.shape
         V = self.n_votes
@@ -211,6 +211,34 @@ class CapsuleLayer(nn.Module):
                         presence_logit_per_caps=out['presence_logit_per_caps'],
                         presence_logit_per_vote=out['presence_logit_per_vote'],
                         cpr_dynamic_reg_loss=out['reg_per_example'].sum() / B)
+
+
+    def _forward_hierarchical(self, feature, parent_transform, parent_presence):
+        """``parent_transform`` (B,O,1,3,3) replaces the capsule -> viewer transform and / or ``parent_presence`` (B,O,1)
+        the capsule presence (object_decoder.py:183-188, :214-217; stacked capsule layers).  Not on the hot path -- SCAE
+        never passes them -- so this is the reference's sequence with PyTorch ops, differentiable w.r.t. both."""
+        from . import cv_ops
+        all_param = self.predict_all_param(feature)
+        B, O, V = all_param.shape[0], self.n_caps, self.n_votes
+        parts = torch.split(all_param, self.splits, -1)
+        cpr_dynamic, cvr, logit_caps, logit_vote, scale = [t.view(B, O, *shape) for t, shape in zip(parts, self.output_shapes)]
+        if not self.allow_deformations:
+            cpr_dynamic = torch.zeros_like(cpr_dynamic)
+        reg = math_ops.l2_loss(cpr_dynamic) / B
+        as_matrix = lambda t: cv_ops.geometric_transform(t, self.similarity_transform, nonlinear=True, as_matrix=True)
+        cpr = as_matrix(cpr_dynamic + self.cpr_static)
+        cvr, logit_caps, logit_vote, scale = [t + bias for t, bias in zip((cvr, logit_caps, logit_vote, scale),
+                                                                        self.caps_bias_list)]
+        cvr = as_matrix(cvr) if parent_transform is None else parent_transform
+        vote = torch.matmul(cvr.expand(B, O, V, 3, 3), cpr)
+        noise_caps, noise_vote = self.draw_noise(all_param)
+        if noise_caps is not None:
+            logit_caps, logit_vote = logit_caps + noise_caps, logit_vote + noise_vote
+        presence_caps = torch.sigmoid(logit_caps) if parent_presence is None else parent_presence
+        vote_presence = presence_caps * torch.sigmoid(logit_vote)
+        scale = torch.nn.functional.softplus(scale + .5) + 1e-2 if self.learn_vote_scale else torch.ones_like(scale)
+        return AttrDict(vote=vote, scale=scale, vote_presence=vote_presence, presence_logit_per_caps=logit_caps,
+                        presence_logit_per_vote=logit_vote, cpr_dynamic_reg_loss=reg)
 
 
 class CapsuleLikelihood:
