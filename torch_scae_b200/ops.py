@@ -525,9 +525,9 @@ def loss_head(caps_presence, posterior, label, classifier, n_classes, prior_type
     SCAE.loss adds, or None when the kernels do not cover the request (the caller then runs the PyTorch ops).
 
     ``label`` values must lie in [0, n_classes): the kernel does no range check (a host-side check would be a device
-    sync inside the captured step).  ``F.cross_entropy`` would raise on an out-of-range label and skip
-    ``ignore_index=-100`` rows; here such a row silently contributes ``-log(0 + eps)``-free zeros to neither head's
-    numerator, i.e. a finite but meaningless loss -- validate labels in the data pipeline."""
+    sync inside the captured step).  ``F.cross_entropy`` raises on an out-of-range label and leaves ``ignore_index``
+    rows out of the mean; here such a row matches no class and yields a finite but meaningless term -- validate labels
+    in the data pipeline."""
     if not (caps_presence.is_cuda and caps_presence.dtype == torch.float32 and posterior.dtype == torch.float32
             and posterior.dim() == 3 and tuple(caps_presence.shape) == tuple(posterior.shape[:2])
             and 0 < posterior.shape[1] <= 64 and posterior.shape[0] > 0 and posterior.shape[2] > 0):
