@@ -15,6 +15,9 @@ accesses (the CPU counterpart of compute-sanitizer memcheck):
     LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 \\
         python tests/emu/sanitizer_run.py /tmp/scae_emu_asan/libscae_b200_emu.so 2> asan.txt
 
+Round 2: the rewritten path-1 backward (run-walk kernel with the per-warp cell queue, tmpl_bwd.cu) is clean under both
+passes at the MNIST, stress and colour shapes (whole-image and banded pixel records) and the C=3 temperature case.
+
 Round 1 result (the shapes below and both hot paths again at the MNIST / stress shapes with their real launch
 configurations): no memory errors; no races in the template, capsule (general and TMA-staged, with the deferred
 asynchronous copies), loss-head, pooling, im2col / col2im, transpose and LayerNorm kernels.  The set-attention kernels
@@ -42,6 +45,12 @@ d = f32(gpu_util.make_template_inputs(2,4,3,7,9,12,10, alpha=False, presence=Tru
 gpu_util.template_cuda(d)
 print('template MNIST-ish', flush=True)
 d = f32(gpu_util.make_template_inputs(2,12,1,11,11,40,40, alpha=True, seed=2))
+gpu_util.template_cuda(d)
+print('template stress shape (banded pixel records)', flush=True)
+d = f32(gpu_util.make_template_inputs(1,9,1,21,21,64,64, alpha=True, seed=3))
+gpu_util.template_cuda(d)
+print('template colour shape (banded pixel records, 128-register variant)', flush=True)
+d = f32(gpu_util.make_template_inputs(1,9,3,11,11,32,32, alpha=True, seed=4))
 gpu_util.template_cuda(d)
 flags = dict(similarity=False, learn_vote_scale=True, allow_deformations=True)
 print('capsule general', flush=True)

@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
   for (int e = threadIdx.x; e < H; e += blockDim.x) ys[e] = base_coord(e, H);
   const TmplScalars sc = tmpl_scalars(a);
   const float lim_x = keep((float)a.w + 2.5f), lim_y = keep((float)a.h + 2.5f);
+  const float in_x = keep((float)a.w + 2.0f), in_y = keep((float)a.h + 2.0f);   // interior cells: 1 <= t < size + 2
   // the hot loop addresses shared memory by 32-bit byte address: tap offsets carry the warp's atlas address, so a tap is
   // one LDS [reg + imm] and a cell's identity (the flush key) is the address of its north-west texel
   const unsigned sbase = smem_u32(smem);
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
     // the lane's current cell (starts in the border corner: zero texels, gradient discarded): its four texels and its
     // four moment sums
     unsigned cur_off = atlas_off;
-    bool cur_in = false;
+    unsigned cur_in = 0u;      // the current cell touches an interior texel
     Texel<kPad> t00, t10, t01, t11;
 #pragma unroll
     for (int c = 0; c < kPad; ++c) t00.v[c] = t10.v[c] = t01.v[c] = t11.v[c] = 0.0f;
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
         const float Y = ys[r_img < H ? r_img : H - 1];       // (a dead run reads pad records: every contribution is 0)
         const float yx = fmaf(Y, Bx, Cx), yy = fmaf(Y, By, Cy);
         const bool backward = ((w0 + wk) & 1) != 0;
-        const unsigned xstep = backward ? 0u - 4u : 4u;
+        const unsigned xstep = keep(backward ? 0u - 4u : 4u);
         unsigned xa = keep(xs_addr + (unsigned)(col0 + (backward ? L - 1 : 0)) * 4u);   // loop-carried addresses: X of the
         unsigned ra = keep(pix_addr + (unsigned)(wk * walk_recs + lane * L + (lane >> skew_shift)) * 16u);   // its records
         float wgx = 0.f, wgy = 0.f;
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
           if (chm != 0u) {
             // cells that touch no interior texel (the zero border: pixels that miss the template) are not queued --
             // their gradient would be discarded; parts cover a fraction of the image, so this is most cells
-            const bool app = changed && cur_in;
+            const bool app = changed && cur_in != 0u;
             const unsigned am = __ballot_sync(0xffffffffu, app);
             if (am != 0u) queue_append<kPad, NCH>(queue, am, app, lane_lt, cur_off, cs);
             if (changed) {
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) cs[k][c] = 0.0f;
               cur_off = t.off;
-              cur_in = t.tx >= 1.0f && t.tx < lim_x - 0.5f && t.ty >= 1.0f && t.ty < lim_y - 0.5f;
+              cur_in = (t.tx >= 1.0f && t.tx < in_x && t.ty >= 1.0f && t.ty < in_y) ? 1u : 0u;
             }
             lds_texel_pred<kPad>(t.off, t00, changed);
             lds_texel_pred<kPad>(t.off + kPad * 4, t10, changed);
@@ -514,8 +515,8 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
     }
     if (!has_m) continue;
     {
-      const unsigned am = __ballot_sync(0xffffffffu, cur_in);
-      if (am != 0u) queue_append<kPad, NCH>(queue, am, cur_in, lane_lt, cur_off, cs);
+      const unsigned am = __ballot_sync(0xffffffffu, cur_in != 0u);
+      if (am != 0u) queue_append<kPad, NCH>(queue, am, cur_in != 0u, lane_lt, cur_off, cs);
     }
     while (queue.tail != queue.head) queue_drain<kPad>(queue, gat, row, lane, lane_lt);
     __syncwarp();
