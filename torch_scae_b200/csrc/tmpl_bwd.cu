@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
   const unsigned gat = keep((unsigned)atlas_floats * 4u);
   const unsigned pix_addr = smem_u32(PIX), xs_addr = smem_u32(xs);
   const float hw_x = 0.5f * (float)a.w, hw_y = 0.5f * (float)a.h;
-  const float inv_pw = 1.0f / (float)pw, inv_L = 1.0f / (float)L;
+  const float inv_L = 1.0f / (float)L;
   float* my_alpha_partial = (kAlpha && out.alpha_partials) ? out.alpha_partials + (size_t)blockIdx.x * a.M * hw : nullptr;
   if (my_alpha_partial)
     #pragma unroll 1
@@ -544,25 +544,25 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
       float gcol[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) gcol[c] = 0.0f;
-      #pragma unroll 4
-      for (int e = lane; e < pw * ph; e += 32) {
-        const int yy = (int)(((float)e + 0.5f) * inv_pw), xx = e - yy * pw;
-        float* q = gatlas + (size_t)e * kPad;
-        if (yy >= 2 && yy < ph - 2 && xx >= 2 && xx < pw - 2) {
-          const int te = (yy - 2) * a.w + (xx - 2);
-          if (colored) {
-            // template = raw * colour: d/d raw = colour * g (summed over the batch), d/d colour = sum_texels raw * g
+      // interior texels only: the border of the gradient atlas collects what the cells on the template's edge spill
+      // over it, is never read and therefore never cleared
+      const float inv_w = 1.0f / (float)a.w;
+#pragma unroll 4
+      for (int te = lane; te < hw; te += 32) {
+        const int yy = (int)(((float)te + 0.5f) * inv_w), xx = te - yy * a.w;
+        float* q = gatlas + ((size_t)(yy + 2) * pw + (xx + 2)) * kPad;
+        if (colored) {
+          // template = raw * colour: d/d raw = colour * g (summed over the batch), d/d colour = sum_texels raw * g
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              dst[(size_t)c * hw + te] += colv[c] * q[c];
-              gcol[c] = fmaf(__ldg(src + (size_t)c * hw + te), q[c], gcol[c]);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < C; ++c) dst[(size_t)c * hw + te] = q[c];
+          for (int c = 0; c < C; ++c) {
+            dst[(size_t)c * hw + te] += colv[c] * q[c];
+            gcol[c] = fmaf(__ldg(src + (size_t)c * hw + te), q[c], gcol[c]);
           }
-          if (kAlpha && my_alpha_partial) my_alpha_partial[(size_t)m * hw + te] += q[C];
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) dst[(size_t)c * hw + te] = q[c];
         }
+        if (kAlpha && my_alpha_partial) my_alpha_partial[(size_t)m * hw + te] += q[C];
 #pragma unroll
         for (int c = 0; c < kPad; ++c) q[c] = 0.0f;
       }
