@@ -212,7 +212,6 @@ __device__ __forceinline__ void texel_add_pred(unsigned addr, float v0, float v1
   else if (kPad == 2) smem_add_pred_f32x2(addr, v0, v1, pred);
   else smem_add_pred_f32x4(addr, v0, v1, v2, v3, pred);
 }
-#define SCAE_CORNER(k) acc[k][0], acc[k][NCH > 1 ? 1 : 0], NCH > 2 ? acc[k][NCH > 2 ? 2 : 0] : 0.0f, NCH > 3 ? acc[k][NCH > 3 ? 3 : 0] : 0.0f
 
 // ---- per-warp queue of finished cells ----------------------------------------------------------------------------------
 // A lane that leaves a cell appends {cell address, the cell's four moment sums} to its warp's queue in shared memory (a ring of
@@ -297,8 +296,8 @@ __device__ __forceinline__ void queue_drain(CellQueue& q, unsigned gat, unsigned
 }
 
 // Work unit = (image b, template group grp): the CTA's warps take the templates grp * nwarps + warp.  Units are dealt
-// round-robin to the persistent CTAs, so a batch of 1024 images is 5120 units over 592 CTAs (8.6 each) instead of
-// 1.7 whole images each -- the tail of the last wave shrinks from 14 % to 4 % of the kernel.
+// round-robin to the persistent CTAs, so a batch of 1024 images is 5120 units over 444 CTAs (11.5 each) instead of
+// 2.3 whole images each -- the tail of the last wave stays a few per cent of the kernel.
 // kMode: the same scatter for the backward of pdf.mode() -- `gout` is the gradient w.r.t. the mode image and `cache`'s
 // first C planes hold the index of the component each pixel took its value from (scae_tmpl_mode_bwd)
 template <int C, bool kAlpha, bool kMode, int kOcc>
