@@ -457,7 +457,7 @@ def run_gpu(args):
     eager_steps = steps if graphed is None else min(steps, 20)
     with ops.KernelTimer() as timer:
         ms_eager = timed(h.step, eager_steps)
-    kstats = timer.summary()
+    kstats, kmedian = timer.summary(), timer.medians()
     # >= 100 replays inside the timed region, whatever --steps says; `steps` is what the line reports
     reps = max(steps, 100) if graphed is not None else steps
     ms_step = timed(h.run, reps)
@@ -539,14 +539,16 @@ def run_gpu(args):
     plumbing = {}
     launches = 0
     for name, (calls, n_launch, total_ms) in kstats.items():
-        avg_ms = total_ms / calls
+        # median over the calls of the eager pass: the event pair around a C-ABI call also spans what the host does
+        # between the two records, and one late launch would move the mean of a 40 us kernel
+        avg_ms = kmedian[name]
         launches += (n_launch // eager_steps) * steps      # launches of OUR kernels inside the timed region of `value`
         if name not in bytes_per_image:        # small kernels serving the callers of the hot paths (e.g. scae_colsum)
             plumbing[name] = dict(calls_per_step=calls // eager_steps, launches_per_step=n_launch // eager_steps,
                                   ms_per_step=round(total_ms / eager_steps, 4))
             continue
         gbs = bytes_per_image[name] * B / (avg_ms * 1e-3) / 1e9
-        kernels[name] = dict(ms=round(avg_ms, 4), launches_per_call=n_launch // calls,
+        kernels[name] = dict(ms=round(avg_ms, 4), ms_is=f'median of {calls} calls', launches_per_call=n_launch // calls,
                              algorithmic_bytes=bytes_per_image[name] * B, achieved_gbs=round(gbs, 1),
                              frac_of_hbm_peak=round(gbs / peak, 4), share_of_step=round(avg_ms / ms_step, 4))
         if name in ISSUE_LANE_INSTR:

@@ -42,6 +42,15 @@ class KernelTimer:
             out[name] = (len(recs), sum(r[2] for r in recs), sum(r[0].elapsed_time(r[1]) for r in recs))
         return out
 
+    def medians(self):
+        """{entry point: median ms per call}: an event pair also spans whatever the host did between the two records, so
+        one late launch (a busy host core) inflates the mean of a 40 us kernel; the median does not move."""
+        out = {}
+        for name, recs in self.records.items():
+            ms = sorted(r[0].elapsed_time(r[1]) for r in recs)
+            out[name] = ms[len(ms) // 2]
+        return out
+
 
 def _timed(name, fn, *args):
     """Calls a C-ABI entry point, bracketing it with CUDA events when a KernelTimer is active; the number of kernels
