@@ -87,11 +87,11 @@ def algorithmic_bytes(M=40, C=1, h=11, w=11, H=40, W=40, O=32, fused_color=False
 # Path 1 is bound by the SM issue rate, not by HBM: work units = (M+1) * H * W (pixel, component)
 # pairs per image and an ALGORITHMIC lane-instruction count per unit -- 50 for the forward (coordinates, floor/weights,
 # four taps, two bilinear blends, two streaming-logsumexp updates; SURVEY's figure) and 120 for the backward: the SASS
-# of tmpl_ll_bwd_run_kernel<1,1> issues 91 instructions per (pixel, template) on the path that every pixel takes (record
+# of tmpl_ll_bwd_run_kernel<1,1> issues 81 instructions per (pixel, template) on the path that every pixel takes (record
 # and coordinate loads, clamp / floor, the two difference-form samples with their coordinate derivatives, the two
 # responsibilities, pose / presence sums, 8 FFMAs of cell sums) plus the cell-change handling, which is about 30 when
 # amortised perfectly over a warp (one queue append per cell visit, one conflict-free drain per 32 of them).  The rest
-# of what ncu counts (191 per pixel and template in profiles/r02b_*: turn-taking for repeated cells, staging, atlas
+# of what ncu counts (about 180 per pixel and template in profiles/r02b_*: turn-taking for repeated cells, staging, atlas
 # flushes) is overhead this figure leaves out.  t_issue = units * instr / (SMs * 128 lanes * f_clk) is the time at a
 # perfect issue rate; `measured_issue_ms` below uses the instruction count ncu measured for this build instead.
 ISSUE_LANE_INSTR = dict(scae_tmpl_ll_fwd=50, scae_tmpl_ll_bwd=120)
