@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SCAE_B200_ABI_VERSION 4
+#define SCAE_B200_ABI_VERSION 5
 
 #define SCAE_OK 0
 #define SCAE_EINVAL (-1)   /* bad shape / flag / NULL where a pointer is required / misaligned pointer */
@@ -211,6 +211,35 @@ size_t scae_caps_ll_bwd_workspace_bytes(const scae_caps_args* a);
 int scae_caps_ll_bwd(const scae_caps_args* a, const scae_caps_saved* saved, const scae_caps_upstream* up,
                      float* g_all_param, float* g_shared, float* g_dummy_vote, float* g_x, float* g_presence,
                      void* workspace, size_t workspace_bytes, scae_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Hot path 2 on EXPLICIT vote tensors (csrc/caps_explicit.cu): the reference's standalone
+ *   CapsuleLikelihood(vote, scale, vote_presence, dummy_vote)(x, presence)          object_decoder.py:243-372
+ * for callers that build their own votes instead of going through CapsuleLayer (its own test does,
+ * tests/test_object_decoder.py:62-112).  Same outputs as scae_caps_ll_fwd minus the ones that come from the parameter
+ * head: of scae_caps_outputs, vote / scale / vote_presence / presence_logit_* / caps_presence(_arg) / reg_per_example
+ * are ignored; log_prob = mean over B of ll_per_example.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct scae_caps_explicit_args {
+  const float* vote;          /* [B,O,V,6]  rows 0-1 of the 3x3 vote matrices (the reference's [B,O,V,6] `vote`)     */
+  const float* scale;         /* [B,O,V]    > 0                                                                      */
+  const float* vote_presence; /* [B,O,V]                                                                             */
+  const float* dummy_vote;    /* [V,6]                                                                               */
+  const float* x;             /* [B,V,6]                                                                             */
+  const float* presence;      /* [B,V] nullable (= ones)                                                             */
+  float* point_ll;            /* [B,V] scratch: presence * logsumexp_o, summed per example in a fixed order          */
+  int B, O, V;
+} scae_caps_explicit_args;
+
+int scae_caps_explicit_fwd(const scae_caps_explicit_args* a, const scae_caps_outputs* out, scae_stream_t stream);
+size_t scae_caps_explicit_bwd_workspace_bytes(const scae_caps_explicit_args* a);
+/* Of scae_caps_upstream: g_ll_per_example, g_posterior_mixing_prob, g_soft_winner(_presence), g_winner(_presence),
+ * g_mixing_logit, g_mixing_log_prob are honoured.  g_vote[B,O,V,6], g_scale[B,O,V], g_vote_presence[B,O,V] required;
+ * g_dummy_vote[V,6] (summed over the batch in a fixed order; needs the workspace), g_x[B,V,6], g_presence[B,V]
+ * nullable.  Deterministic. */
+int scae_caps_explicit_bwd(const scae_caps_explicit_args* a, const scae_caps_saved* saved, const scae_caps_upstream* up,
+                           float* g_vote, float* g_scale, float* g_vote_presence, float* g_dummy_vote, float* g_x,
+                           float* g_presence, void* workspace, size_t workspace_bytes, scae_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Plumbing for the callers of hot path 2: column sums of a tall-skinny matrix.

@@ -76,6 +76,61 @@ def test_capsule_likelihood_values_and_gradients_vs_reference_golden():
         assert rel_err(t.grad, g['g_' + k]) < 1e-4, k
 
 
+@pytest.mark.gpu
+def test_capsule_likelihood_kernel_vs_reference_golden_and_pytorch_ops():
+    """On CUDA tensors CapsuleLikelihood runs csrc/caps_explicit.cu: the reference's recorded values and gradients, then
+    a larger random case against the class's own PyTorch-op path in fp64 on the host"""
+    from torch_scae_b200.object_decoder import CapsuleLikelihood
+
+    def run(inp, dev, dtype):
+        leaf = {k: v.detach().to(dev, dtype).requires_grad_(True) for k, v in inp.items()}
+        res = CapsuleLikelihood(vote=leaf['vote'], scale=leaf['scale'], vote_presence=leaf['vote_presence'],
+                                dummy_vote=leaf['dummy_vote'])(leaf['x'], leaf['presence'])
+        return leaf, res
+
+    g = load_golden('capsule_likelihood_explicit')
+    names = ('vote', 'scale', 'vote_presence', 'dummy_vote', 'x', 'presence')
+    leaf, res = run({k: g[k] for k in names}, DEV, torch.float32)
+    out = sub(g, 'out.')
+    assert set(out) == set(res.keys())
+    for k, ref in out.items():
+        if ref.dtype == torch.int64:
+            assert torch.equal(res[k].cpu(), ref), k
+        else:
+            assert rel_err(res[k].cpu(), ref) < 1e-5, k
+    loss = 1.3 * res.log_prob
+    for k, w in sub(g, 'weight.').items():
+        loss = loss + 0.4 * (res[k] * w.to(DEV)).sum()
+    loss.backward()
+    for k, t in leaf.items():
+        assert rel_err(t.grad.cpu(), g['g_' + k]) < 1e-4, k
+
+    torch.manual_seed(5)
+    B, O, V = 9, 12, 21
+    inp = dict(vote=torch.rand(B, O, V, 6), scale=torch.rand(B, O, V) + 0.2, vote_presence=torch.rand(B, O, V),
+               dummy_vote=torch.rand(1, 1, V, 6), x=torch.rand(B, V, 6), presence=torch.rand(B, V))
+    inp = {k: v.float().double() for k, v in inp.items()}
+    weights = {k: torch.randn(s, dtype=torch.float64) for k, s in dict(
+        winner=(B, V, 6), winner_presence=(B, V), soft_winner=(B, V, 6), soft_winner_presence=(B, V),
+        posterior_mixing_prob=(B, O, V), mixing_log_prob=(B, O + 1, V), mixing_logit=(B, O + 1, V)).items()}
+    results = {}
+    for dev, dtype in ((DEV, torch.float32), ('cpu', torch.float64)):
+        leaf, res = run(inp, dev, dtype)
+        loss = 0.7 * res.log_prob
+        for k, w in weights.items():
+            loss = loss + 0.3 * (res[k] * w.to(dev, dtype)).sum()
+        loss.backward()
+        results[dev] = (res, {k: t.grad for k, t in leaf.items()})
+    (rk, gk), (rr, gr) = results[DEV], results['cpu']
+    for k in rr.keys():
+        if rr[k].dtype == torch.int64:
+            assert torch.equal(rk[k].cpu(), rr[k]), k
+        else:
+            assert rel_err(rk[k].cpu().double(), rr[k]) < 1e-5, k
+    for k in gr:
+        assert rel_err(gk[k].cpu().double(), gr[k]) < 1e-4, k
+
+
 def test_capsule_layer_hierarchical_inputs_vs_reference_golden(monkeypatch):
     """CapsuleLayer(feature, parent_transform, parent_presence) (object_decoder.py:183-188, :214-217) on the inputs and
     noise draws recorded from the reference: every output, the gradients w.r.t. the feature, both parents and the

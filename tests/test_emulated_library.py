@@ -84,6 +84,45 @@ def test_emulated_template_path_matches_the_oracle(emu, B, M, C, h, w, H, W, alp
             assert rel_err(got[k], ref[k]) < 1e-4, k
 
 
+def test_emulated_explicit_vote_likelihood_vs_reference_golden(emu):
+    """scae_caps_explicit_fwd / _bwd (csrc/caps_explicit.cu): the standalone CapsuleLikelihood on explicit votes, every
+    output and every input gradient against the values recorded from the reference (object_decoder.py:243-372)"""
+    from conftest import load_golden, sub
+    from torch_scae_b200 import ops
+    g = load_golden('capsule_likelihood_explicit')
+    leaf = {k: g[k].clone().requires_grad_(True) for k in ('vote', 'scale', 'vote_presence', 'dummy_vote', 'x', 'presence')}
+    res = dict(zip(ops.EXPLICIT_RETURNS, ops.CapsuleExplicitLikelihood.apply(
+        leaf['vote'], leaf['scale'], leaf['vote_presence'], leaf['dummy_vote'], leaf['x'], leaf['presence'])))
+    res['log_prob'] = res.pop('ll_per_example').mean()
+    out = sub(g, 'out.')
+    assert set(out) == set(res)
+    for k, ref in out.items():
+        if ref.dtype == torch.int64:
+            assert torch.equal(res[k], ref), k
+        else:
+            assert rel_err(res[k], ref) < 1e-5, k
+    loss = 1.3 * res['log_prob']
+    for k, w in sub(g, 'weight.').items():
+        loss = loss + 0.4 * (res[k] * w).sum()
+    loss.backward()
+    for k, t in leaf.items():
+        assert rel_err(t.grad, g['g_' + k]) < 1e-4, k
+    # presence=None is presence = ones; only the likelihood differentiated
+    ones = torch.ones_like(leaf['presence'])
+    a = ops.CapsuleExplicitLikelihood.apply(leaf['vote'], leaf['scale'], leaf['vote_presence'], leaf['dummy_vote'],
+                                            leaf['x'], None)[0]
+    b = ops.CapsuleExplicitLikelihood.apply(leaf['vote'], leaf['scale'], leaf['vote_presence'], leaf['dummy_vote'],
+                                            leaf['x'], ones)[0]
+    assert torch.equal(a, b)
+    for t in leaf.values():
+        t.grad = None
+    a.sum().backward()
+    ga = leaf['vote'].grad.clone()
+    leaf['vote'].grad = None
+    b.sum().backward()
+    assert torch.equal(ga, leaf['vote'].grad)
+
+
 @pytest.mark.parametrize('B,O,V,part_grads', [(3, 4, 5, True), (3, 4, 5, False), (2, 32, 40, False), (4, 10, 40, False)])
 def test_emulated_capsule_path_matches_the_oracle(emu, B, O, V, part_grads):
     """Hot path 2 through scae_caps_ll_fwd / _bwd: with gradients for the part poses the general kernels (csrc/caps_ll.cu)

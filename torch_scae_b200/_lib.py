@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_size_
 
 from .build import LIB_PATH
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 TMPL_MODE_ALPHA = 0
 TMPL_MODE_TEMPERATURE = 1
@@ -47,6 +47,11 @@ class CapsArgs(Structure):
     _fields_ = [(n, c_void_p) for n in ('all_param', 'cpr_static', 'bias_cvr', 'bias_caps', 'bias_vote', 'bias_scale',
                                         'noise_caps', 'noise_vote', 'x', 'presence', 'dummy_vote')] + \
                [('B', c_int), ('O', c_int), ('V', c_int), ('flags', c_uint)]
+
+
+class CapsExplicitArgs(Structure):
+    _fields_ = [(n, c_void_p) for n in ('vote', 'scale', 'vote_presence', 'dummy_vote', 'x', 'presence', 'point_ll')] + \
+               [('B', c_int), ('O', c_int), ('V', c_int)]
 
 
 CAPS_OUTPUT_FIELDS = ('vote', 'scale', 'vote_presence', 'presence_logit_per_caps', 'presence_logit_per_vote',
@@ -91,6 +96,10 @@ SYMBOLS = {
     'scae_caps_ll_bwd_workspace_bytes': (c_size_t, [POINTER(CapsArgs)]),
     'scae_caps_ll_bwd': (c_int, [POINTER(CapsArgs), POINTER(CapsSaved), POINTER(CapsUpstream)] + [c_void_p] * 6 +
                          [c_size_t, c_void_p]),
+    'scae_caps_explicit_fwd': (c_int, [POINTER(CapsExplicitArgs), POINTER(CapsOutputs), c_void_p]),
+    'scae_caps_explicit_bwd_workspace_bytes': (c_size_t, [POINTER(CapsExplicitArgs)]),
+    'scae_caps_explicit_bwd': (c_int, [POINTER(CapsExplicitArgs), POINTER(CapsSaved), POINTER(CapsUpstream)] +
+                               [c_void_p] * 7 + [c_size_t, c_void_p]),
     'scae_colsum_workspace_bytes': (c_size_t, [c_long, c_int]),
     'scae_colsum': (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     'scae_layernorm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_long, c_int, c_void_p, c_void_p, c_void_p]),

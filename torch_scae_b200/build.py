@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libscae_b200.so')
-SOURCES = ['api.cu', 'support.cu', 'loss_head.cu', 'attnpool_cl.cu', 'conv_cols.cu', 'sab.cu', 'caps_ll.cu', 'caps_ll2.cu', 'caps_ll3.cu', 'caps_ll3_bwd.cu', 'tmpl_fwd.cu', 'tmpl_bwd.cu']
+SOURCES = ['api.cu', 'support.cu', 'loss_head.cu', 'attnpool_cl.cu', 'conv_cols.cu', 'sab.cu', 'caps_ll.cu', 'caps_ll2.cu', 'caps_ll3.cu', 'caps_ll3_bwd.cu', 'caps_explicit.cu', 'tmpl_fwd.cu', 'tmpl_bwd.cu']
 HEADERS = ['common.cuh', 'caps_common.cuh', 'ptx_sm100.cuh', 'tmpl_common.cuh', os.path.join('..', '..', 'include', 'scae_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']

@@ -244,8 +244,10 @@ class CapsuleLayer(nn.Module):
 class CapsuleLikelihood:
     """Capsule voting mechanism on explicit vote tensors (object_decoder.py:243-372).
 
-    Kept for API compatibility with code that builds the likelihood from its own votes; implemented with PyTorch CUDA
-    ops.  ``CapsuleObjectDecoder`` does NOT go through this class -- it uses the fused kernel.
+    For code that builds the likelihood from its own votes (the reference's own test does).  CUDA tensors go through
+    one kernel per direction (``ops.CapsuleExplicitLikelihood``, csrc/caps_explicit.cu: same mixture arithmetic as the
+    fused decoder path minus the vote composition); host tensors run the reference's op sequence in PyTorch (this class
+    is not on a hot path -- ``CapsuleObjectDecoder`` uses the fused kernels and never comes here).
     """
 
     def __init__(self, vote, scale, vote_presence, dummy_vote):
@@ -253,6 +255,11 @@ class CapsuleLikelihood:
         self.vote, self.scale, self.vote_presence, self.dummy_vote = vote, scale, vote_presence, dummy_vote
 
     def __call__(self, x, presence=None):
+        if x.is_cuda and x.shape[-1] == 6 and self.vote.shape[-1] == 6:
+            r = dict(zip(ops.EXPLICIT_RETURNS, ops.CapsuleExplicitLikelihood.apply(
+                self.vote, self.scale, self.vote_presence, self.dummy_vote, x, presence)))
+            ll = r.pop('ll_per_example')
+            return AttrDict(log_prob=ll.mean(), **r)
         import torch.nn.functional as F
         B, V, P = x.shape
         O = self.n_caps

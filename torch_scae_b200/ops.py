@@ -9,8 +9,8 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (CAPS_OUTPUT_FIELDS, CAPS_UPSTREAM_FIELDS, CapsArgs, CapsOutputs, CapsSaved, CapsUpstream, TmplArgs,
-                   check, ptr)
+from ._lib import (CAPS_OUTPUT_FIELDS, CAPS_UPSTREAM_FIELDS, CapsArgs, CapsExplicitArgs, CapsOutputs, CapsSaved,
+                   CapsUpstream, TmplArgs, check, ptr)
 
 
 def _stream():
@@ -821,6 +821,70 @@ def caps_fast_path_count():
     """hot-path-2 calls served by the persistent kernels (csrc/caps_ll3*.cu) so far; bench.py and tests guard against
     silent fall-backs to the older paths with it"""
     return int(_lib.load().scae_caps_persistent_path_count())
+
+
+EXPLICIT_RETURNS = ('ll_per_example', 'vote_presence_binary', 'winner', 'winner_presence', 'soft_winner',
+                    'soft_winner_presence', 'posterior_mixing_prob', 'mixing_log_prob', 'mixing_logit', 'is_from_capsule')
+
+
+class CapsuleExplicitLikelihood(torch.autograd.Function):
+    """The standalone ``CapsuleLikelihood(vote, scale, vote_presence, dummy_vote)(x, presence)`` of the reference
+    (object_decoder.py:243-372) on explicit vote tensors, one kernel per direction (csrc/caps_explicit.cu).
+    ``vote`` (B,O,V,6), ``dummy_vote`` (1,1,V,6) | (V,6), ``x`` (B,V,6); returns EXPLICIT_RETURNS."""
+
+    @staticmethod
+    def forward(ctx, vote, scale, vote_presence, dummy_vote, x, presence):
+        lib = _lib.load()
+        vote, scale, vote_presence, dummy_vote, x, presence = [_f32c(t) for t in (vote, scale, vote_presence, dummy_vote, x,
+                                                                                  presence)]
+        B, O, V, P = vote.shape
+        if P != 6 or tuple(x.shape) != (B, V, 6) or dummy_vote.numel() != V * 6:
+            raise ValueError(f'expected vote (B,O,V,6), x (B,V,6), dummy_vote (1,1,V,6); got {tuple(vote.shape)}, '
+                             f'{tuple(x.shape)}, {tuple(dummy_vote.shape)}')
+        dev = vote.device
+        f = dict(device=dev, dtype=torch.float32)
+        shapes = dict(log_prob_per_point=(B, V), ll_per_example=(B,), vote_presence_binary=(B, O, V), winner=(B, V, 6),
+                      winner_presence=(B, V), soft_winner=(B, V, 6), soft_winner_presence=(B, V),
+                      posterior_mixing_prob=(B, O, V), mixing_log_prob=(B, O + 1, V), mixing_logit=(B, O + 1, V))
+        out = {k: torch.empty(s, **f) for k, s in shapes.items()}
+        out['winner_idx'] = torch.empty(B, V, device=dev, dtype=torch.int64)
+        out['is_from_capsule'] = torch.empty(B, V, device=dev, dtype=torch.int64)
+        point_ll = torch.empty(B, V, **f)
+        args = CapsExplicitArgs(ptr(vote), ptr(scale), ptr(vote_presence), ptr(dummy_vote), ptr(x), ptr(presence),
+                                ptr(point_ll), B, O, V)
+        outs = CapsOutputs(*[ptr(out.get(k)) for k in CAPS_OUTPUT_FIELDS])
+        check(_timed('scae_caps_explicit_fwd', lib.scae_caps_explicit_fwd, ctypes.byref(args), ctypes.byref(outs),
+                     _stream()), 'scae_caps_explicit_fwd')
+        ctx.has_presence = presence is not None
+        ctx.save_for_backward(vote, scale, vote_presence, dummy_vote, x, *([presence] if presence is not None else []),
+                              out['posterior_mixing_prob'], out['log_prob_per_point'], out['winner_idx'])
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(out['vote_presence_binary'], out['is_from_capsule'])
+        return tuple(out[k] for k in EXPLICIT_RETURNS)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        saved = list(ctx.saved_tensors)
+        winner_idx, lse, posterior = saved.pop(), saved.pop(), saved.pop()
+        vote, scale, vote_presence, dummy_vote, x = saved[:5]
+        presence = saved[5] if ctx.has_presence else None
+        B, O, V, _ = vote.shape
+        g = {k: _f32c(v) for k, v in zip(EXPLICIT_RETURNS, grads) if v is not None}
+        up = CapsUpstream(*[ptr(g.get(k[2:])) for k in CAPS_UPSTREAM_FIELDS])
+        sv = CapsSaved(ptr(posterior), ptr(lse), None, ptr(winner_idx))
+        args = CapsExplicitArgs(ptr(vote), ptr(scale), ptr(vote_presence), ptr(dummy_vote), ptr(x), ptr(presence), None,
+                                B, O, V)
+        g_vote, g_scale, g_vp = torch.empty_like(vote), torch.empty_like(scale), torch.empty_like(vote_presence)
+        g_dummy = torch.empty_like(dummy_vote) if ctx.needs_input_grad[3] else None
+        g_x = torch.empty_like(x) if ctx.needs_input_grad[4] else None
+        g_presence = torch.empty_like(presence) if presence is not None and ctx.needs_input_grad[5] else None
+        ws_bytes = lib.scae_caps_explicit_bwd_workspace_bytes(ctypes.byref(args))
+        ws = torch.empty(max(ws_bytes, 16), device=vote.device, dtype=torch.uint8)
+        check(_timed('scae_caps_explicit_bwd', lib.scae_caps_explicit_bwd, ctypes.byref(args), ctypes.byref(sv),
+                     ctypes.byref(up), ptr(g_vote), ptr(g_scale), ptr(g_vp), ptr(g_dummy), ptr(g_x), ptr(g_presence),
+                     ptr(ws), ws_bytes, _stream()), 'scae_caps_explicit_bwd')
+        return g_vote, g_scale, g_vp, g_dummy, g_x, g_presence
 
 
 class CapsuleVoteLikelihood(torch.autograd.Function):
