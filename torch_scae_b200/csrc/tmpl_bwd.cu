@@ -364,6 +364,11 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
   ScalarAcc acc;
   __syncthreads();   // partial row zeroed before any warp accumulates into it; xs / ys complete
   const int q_lane = lane >> kshift, col0 = (lane & (kruns - 1)) * L;
+  // per-lane constants of the walks: first row, record offset inside a walk, X addresses of a forward / backward run
+  const int row0 = q_lane * walks;
+  const unsigned rec_lane = keep((unsigned)(lane * L + (lane >> skew_shift)) * 16u);
+  const unsigned walk_bytes = (unsigned)walk_recs * 16u, ys_addr = smem_u32(ys);
+  const unsigned xa_fwd = keep(xs_addr + (unsigned)col0 * 4u), xa_bwd = xa_fwd + (unsigned)(L - 1) * 4u;
   const int nbands = (walks + bw - 1) / bw;
 
   const int groups = g.groups, n_units = a.B * groups;
@@ -410,6 +415,9 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
       for (int c = 0; c < NCH; ++c) cs[k][c] = 0.0f;
     queue.head = queue.tail = 0u;
 
+    const float* x_img = x + (size_t)b * C * HW;
+    const float* g_img = gout + (size_t)b * C * HW;
+    const float* c_img_ptr = cache + (size_t)b * 2 * C * HW;
     for (int band = 0; band < nbands; ++band) {
       // ---- pixel records of the band (whole CTA) and, once per image, the background component -------------------
       __syncthreads();                       // the previous band's records are no longer read
@@ -428,11 +436,11 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
         const size_t px0 = (size_t)b * C * HW + p;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const size_t cx = (size_t)b * 2 * C * HW + (size_t)c * HW + p;
-          xv[c] = ok ? __ldg(x + px0 + (size_t)c * HW) : 0.0f;
-          G[c] = ok ? __ldg(gout + px0 + (size_t)c * HW) : 0.0f;
-          Nc[c] = ok ? __ldg(cache + cx) : 1e30f;
-          Dc[c] = ok ? __ldg(cache + cx + (size_t)C * HW) : 1e30f;
+          const int pc = c * HW + p;          // 32-bit offsets from the image's base pointers: one IMAD.WIDE per load
+          xv[c] = ok ? __ldg(x_img + pc) : 0.0f;
+          G[c] = ok ? __ldg(g_img + pc) : 0.0f;
+          Nc[c] = ok ? __ldg(c_img_ptr + pc) : 1e30f;
+          Dc[c] = ok ? __ldg(c_img_ptr + C * HW + pc) : 1e30f;
           PIX[c * plane + wk * walk_recs + ln * L + (ln >> skew_shift) + s] = make_float4(xv[c], G[c], Nc[c], Dc[c]);
         }
         if (first && ok) bwd_background<C, kAlpha, kMode>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
@@ -442,13 +450,13 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
       // ---- walks of the band: 32 runs in lock-step, one pixel per lane per step -----------------------------------
       #pragma unroll 1
       for (int wk = 0; wk < bw && w0 + wk < walks; ++wk) {
-        const int r_img = q_lane * walks + w0 + wk;
-        const float Y = ys[r_img < H ? r_img : H - 1];       // (a dead run reads pad records: every contribution is 0)
+        const int w = w0 + wk, r_img = row0 + w;
+        const float Y = lds_f32(ys_addr + 4u * (unsigned)(r_img < H ? r_img : H - 1));   // (a dead run reads pad records)
         const float yx = fmaf(Y, Bx, Cx), yy = fmaf(Y, By, Cy);
-        const bool backward = ((w0 + wk) & 1) != 0;
+        const bool backward = (w & 1) != 0;
         const unsigned xstep = keep(backward ? 0u - 4u : 4u);
-        unsigned xa = keep(xs_addr + (unsigned)(col0 + (backward ? L - 1 : 0)) * 4u);   // loop-carried addresses: X of the
-        unsigned ra = keep(pix_addr + (unsigned)(wk * walk_recs + lane * L + (lane >> skew_shift)) * 16u);   // its records
+        unsigned xa = keep(backward ? xa_bwd : xa_fwd);                     // loop-carried addresses: X of the lane's
+        unsigned ra = keep(pix_addr + (unsigned)wk * walk_bytes + rec_lane);   // column, its pixel records
         float wgx = 0.f, wgy = 0.f;
         #pragma unroll 1
         for (int s = 0; s < L; ++s, xa += xstep, ra += 16u) {
