@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
   const int L = g.tw, skew_shift = g.ppt, kshift = g.k, kruns = 1 << kshift, walks = g.tiles_y, bw = g.tiles_x;
   float* xs = red + 64;                                   // [kruns * L] affine_grid base coordinates (0 past W)
   float* ys = xs + kruns * L;                             // [H]
-  const int HW = a.H * a.W, hw = a.h * a.w, pw = g.pw, ph = g.ph, W = a.W, H = a.H;
+  const int HW = a.H * a.W, hw = a.h * a.w, pw = g.pw, W = a.W, H = a.H;
   // records {x, upstream gradient, cached numerator lse, cached denominator lse} of the current band, [C][bw][32 L + 8]:
   // run `ln` of a walk starts at ln * L + (ln >> skew_shift); the skew spreads the eight lanes of a quarter-warp over the
   // eight 16-byte bank groups whatever the parity of L (one LDS.128 per step, conflict-free)
