@@ -59,16 +59,21 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     nvcc = _nvcc()
-    objs = []
     build_id = source_id()
-    for src in SOURCES:
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace('.cu', '.o'))
         cmd = [nvcc, *NVCC_FLAGS, f'-DSCAE_BUILD_ID="{build_id}"', '-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
             print(' '.join(cmd), flush=True)
         subprocess.run(cmd, check=True)
-        objs.append(obj)
+        return obj
+
+    # the translation units are independent: compile them side by side (verbose: one after the other, readable output)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=1 if verbose else min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
     cmd = [nvcc, '-shared', '-o', LIB_PATH, *objs, '-gencode', 'arch=compute_100a,code=sm_100a']
     subprocess.run(cmd, check=True)
     return LIB_PATH
