@@ -68,6 +68,12 @@ CONFIGS = [
     (2, 3, 1, 5, 5, 70, 9, True),          # several row tiles
     (2, 3, 1, 5, 5, 9, 70, False),         # several column tiles
     (1, 1, 1, 1, 1, 1, 1, True),           # degenerate sizes
+    # shapes that push the backward's plan search (tmpl_bwd_plan): ragged runs / dead lanes, more templates than a CTA
+    # group, large templates (fewer warps per CTA), a large image (banded pixel records), temperature mode in colour
+    (2, 70, 1, 7, 7, 17, 33, True),
+    (1, 3, 3, 40, 40, 96, 96, True),
+    (1, 2, 1, 9, 9, 128, 128, False),
+    (2, 9, 3, 13, 5, 31, 45, False),
 ]
 
 
