@@ -46,6 +46,9 @@ gpu_util.template_cuda(d)
 print('template MNIST-ish', flush=True)
 d = f32(gpu_util.make_template_inputs(2,12,1,11,11,40,40, alpha=True, seed=2))
 gpu_util.template_cuda(d)
+print('template, several template groups of one image per CTA (records staged once, no barrier between the groups)', flush=True)
+d = f32(gpu_util.make_template_inputs(2,40,1,7,7,20,20, alpha=True, seed=2))
+gpu_util.template_cuda(d)
 print('template stress shape (banded pixel records)', flush=True)
 d = f32(gpu_util.make_template_inputs(1,9,1,21,21,64,64, alpha=True, seed=3))
 gpu_util.template_cuda(d)

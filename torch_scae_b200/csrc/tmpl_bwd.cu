@@ -295,9 +295,9 @@ __device__ __forceinline__ void queue_drain(CellQueue& q, unsigned gat, unsigned
   q.head += n;
 }
 
-// Work unit = (image b, template group grp): the CTA's warps take the templates grp * nwarps + warp.  Units are dealt
-// round-robin to the persistent CTAs, so a batch of 1024 images is 5120 units over 444 CTAs (11.5 each) instead of
-// 2.3 whole images each -- the tail of the last wave stays a few per cent of the kernel.
+// Work unit = (image b, template group grp): the CTA's warps take the templates grp * nwarps + warp.  A batch of 1024
+// images is 5120 units; the persistent CTAs take contiguous chunks of them (11.5 each over 444 CTAs: chunk boundaries
+// fall inside images, so the last wave's tail stays a few per cent of the kernel instead of the 14 % whole images gave).
 // kMode: the same scatter for the backward of pdf.mode() -- `gout` is the gradient w.r.t. the mode image and `cache`'s
 // first C planes hold the index of the component each pixel took its value from (scae_tmpl_mode_bwd)
 template <int C, bool kAlpha, bool kMode, int kOcc>
@@ -371,11 +371,18 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
   const unsigned xa_fwd = keep(xs_addr + (unsigned)col0 * 4u), xa_bwd = xa_fwd + (unsigned)(L - 1) * 4u;
   const int nbands = (walks + bw - 1) / bw;
 
+  // Every CTA takes a CONTIGUOUS chunk of the units: consecutive units are the template groups of one image, so the
+  // image's pixel records are staged once per image (not once per group) and the groups in between need no CTA
+  // barrier at all -- a warp that finishes its template early starts the next group's while the others catch up.
   const int groups = g.groups, n_units = a.B * groups;
+  const int u_begin = (int)((long)blockIdx.x * n_units / gridDim.x), u_end = (int)((long)(blockIdx.x + 1) * n_units / gridDim.x);
+  int b_staged = -1;               // image whose records are in shared memory (whole-image staging only)
   #pragma unroll 1
-  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+  for (int u = u_begin; u < u_end; ++u) {
     const int b = u / groups, grp = u - b * groups;
     const bool first = grp == 0;   // the background component and g_bg_image belong to the image, not to a template
+    const bool restage = nbands > 1 || b != b_staged;
+    b_staged = b;
     const int m = grp * nwarps + warp;
     const bool has_m = m < a.M;    // (no early exit: every warp takes part in the band barriers)
     // ---- per-template setup (all lanes compute the same coefficients) -------------------------------------------
@@ -420,8 +427,9 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
     const float* c_img_ptr = cache + (size_t)b * 2 * C * HW;
     for (int band = 0; band < nbands; ++band) {
       // ---- pixel records of the band (whole CTA) and, once per image, the background component -------------------
-      __syncthreads();                       // the previous band's records are no longer read
       const int w0 = band * bw;
+      if (restage) {
+      __syncthreads();                       // the previous band's / image's records are no longer read
       #pragma unroll 2
       for (int e = threadIdx.x; e < bw * 32 * L; e += blockDim.x) {
         const int slot = (int)(((float)e + 0.5f) * inv_L), s = e - slot * L;
@@ -446,6 +454,7 @@ __global__ void __launch_bounds__(kRunThreads, kOcc) tmpl_ll_bwd_run_kernel(cons
         if (first && ok) bwd_background<C, kAlpha, kMode>(a, sc, xv, G, Nc, Dc, px0, HW, out.g_bg_image, acc);
       }
       __syncthreads();
+      }
       if (!has_m) continue;
       // ---- walks of the band: 32 runs in lock-step, one pixel per lane per step -----------------------------------
       #pragma unroll 1
